@@ -1,0 +1,190 @@
+/*
+ * sup3r_b200 C ABI  --  libsup3r_b200.so
+ *
+ * Drop-in boundary for the sup3r GAN hot path (Sup3rGan generator / discriminator forward and
+ * backward, losses, optimiser step).  The reference (NREL/sup3r @ dd96e798) has NO native FFI:
+ * its seam is the Python object protocol of phygnn.CustomNetwork + TensorFlow autodiff that
+ * sup3r.models consumes (sup3r/models/abstract.py:96-101, 1081-1092, 1157-1165, 1230-1238;
+ * sup3r/models/base.py:283-313, 505-549).  Each entry point below names the reference call it
+ * stands in for.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the library
+ *     allocates nothing after s3_init (one small internal scratch per device excepted);
+ *   - tensors are channels-last and dense: 4-D (n, y, x, c), 5-D (n, z, y, x, c); a 2-D op is a
+ *     3-D op with z extent 1 and kernel/stride 1 on z.  sup3r's (n, s1, s2, t, c) maps to
+ *     z = s1, y = s2, x = t; (n, s1, s2, c) maps to y = s1, x = s2;
+ *   - all calls are asynchronous on the given CUDA stream (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, < 0 = error (message from s3_last_error(), thread-local);
+ *   - no C++ exceptions, no exit(), no implicit device synchronisation.
+ */
+#ifndef SUP3R_B200_H_
+#define SUP3R_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3_OK 0
+#define S3_ERR_INVALID (-1)
+#define S3_ERR_CUDA (-2)
+#define S3_ERR_UNSUPPORTED (-3)
+
+#define S3_PAD_ZERO 0      /* keras padding='same' / tf.pad CONSTANT */
+#define S3_PAD_REFLECT 1   /* tf.pad REFLECT (phygnn FlexiblePadding) */
+#define S3_PAD_SYMMETRIC 2 /* tf.pad SYMMETRIC */
+
+#define S3_ACT_NONE 0
+#define S3_ACT_RELU 1
+#define S3_ACT_LEAKY 2
+#define S3_ACT_SIGMOID 3
+#define S3_ACT_TANH 4
+
+typedef void* s3_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution descriptor.  One fused op replaces the reference's
+ *   FlexiblePadding -> Conv2D/Conv3D/Conv2DTranspose -> Cropping -> [LeakyReLU|relu] ->
+ *   [SpatialExpansion|SpatioTemporalExpansion] -> [SkipConnection add]
+ * layer run (sup3r/configs/ ** /gen_*.json driven by abstract.py:1081-1092).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct s3_conv_desc {
+  int32_t ndim;        /* 2 or 3 convolved dims (2: z extent must be 1) */
+  int32_t n;           /* batch */
+  int32_t in_dims[3];  /* input extents (z, y, x) */
+  int32_t cin, cout;
+  int32_t ksize[3];    /* kernel extents, 1 on z for ndim == 2 */
+  int32_t stride[3];
+  int32_t pad_lo[3];   /* implicit padding in input voxels */
+  int32_t pad_hi[3];
+  int32_t pad_mode;    /* S3_PAD_ZERO | S3_PAD_REFLECT */
+  int32_t act;         /* S3_ACT_*, applied to conv + bias */
+  float alpha;         /* LeakyReLU slope */
+  /* epilogue scatter: conv-output voxel (z, y, x), channel c -> destination element */
+  int32_t d2s;         /* depth_to_space factor r over the spatial dims (3-D: z,y; 2-D: y,x) */
+  int32_t d2t;         /* depth_to_time factor m over x (3-D only), 1 = none */
+  int32_t t_roll;      /* tf.roll shift applied after depth_to_time */
+  int32_t out_repeat[3]; /* nearest-neighbour repeat of the mapped output per dim (>= 1) */
+  int32_t out_cstride; /* channels per voxel of the destination buffer (0 = mapped channels) */
+  int32_t out_coffset; /* first destination channel (concat-by-stride) */
+} s3_conv_desc;
+
+/* conv_dims: conv output extents before the scatter; out_dims/out_channels: after it. */
+int s3_conv_out_dims(const s3_conv_desc* d, int32_t conv_dims[3], int32_t out_dims[3],
+                     int32_t* out_channels);
+
+/* Tuning / probing knobs of the tcgen05 kernel (all 0 = library default). */
+typedef struct s3_umma_tuning {
+  int32_t tiles;            /* M tiles (128 voxels) per CTA work item, 1..8 */
+  int32_t w_stages;         /* weight ring depth */
+  int32_t box_x;            /* smem x extent of the activation box (>= 10) */
+  int32_t base_offset_mode; /* 0: descriptor base_offset 0; 1: (addr >> 7) & 7 */
+  int32_t max_ctas;         /* 0 = SM count */
+  int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
+} s3_umma_tuning;
+
+int s3_init(int device);
+const char* s3_last_error(void);
+int s3_version(void);
+int s3_sm_count(int device);
+
+/* ---- generic fp32 direct convolution (CUDA cores; every geometry) ------------------------
+ * x: (n, z, y, x, cin) f32.  w: keras kernel layout (kz, ky, kx, cin, cout) f32.
+ * bias: [cout] or NULL.  residual: conv-output geometry (n, Zo, Yo, Xo, cout) f32 or NULL,
+ * added after the activation.  post_scale/post_shift: [cout] or NULL, applied last
+ * (un-normalisation, abstract.py:240-275).  y: mapped f32 destination or NULL.
+ * y_hi / y_lo: optional 16-bit padded+mirrored destinations (see s3_pack_act_pad16). */
+int s3_conv_fwd_f32(const s3_conv_desc* d, const float* x, const float* w, const float* bias,
+                    const float* residual, const float* post_scale, const float* post_shift,
+                    float* y, void* y_hi, void* y_lo, s3_stream stream);
+
+/* Adjoint of the convolution w.r.t. its input: dy in conv-output geometry -> dx (n,z,y,x,cin).
+ * Stands in for tape.gradient through keras Conv* (abstract.py:1230-1238). */
+int s3_conv_dgrad_f32(const s3_conv_desc* d, const float* dy, const float* w, float* dx,
+                      s3_stream stream);
+/* Weight / bias gradients: dw (kz,ky,kx,cin,cout), dbias [cout] (either may be NULL).
+ * Results OVERWRITE the destinations.  scratch: >= s3_conv_wgrad_scratch_bytes() or NULL. */
+size_t s3_conv_wgrad_scratch_bytes(const s3_conv_desc* d);
+int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, float* dw,
+                      float* dbias, void* scratch, s3_stream stream);
+
+/* ---- tcgen05 implicit-GEMM convolution (cin == 64, 3x3[x3], stride 1, reflect-1) ---------
+ * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single-pass bf16, else the
+ * 3-pass split-precision product hi*hi + lo*hi + hi*lo).  w_hi/w_lo: from s3_pack_weights_umma. */
+int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi,
+                     const void* w_lo, const float* bias, const float* residual,
+                     const float* post_scale, const float* post_shift, float* y, void* y_hi,
+                     void* y_lo, const s3_umma_tuning* tune, s3_stream stream);
+/* rows of the packed weight tensor per tap (cout rounded up to a multiple of 16) */
+int s3_umma_npad(int cout);
+/* w (taps, cin=64, cout) f32 -> (taps, npad, 64) 16-bit, cout rows zero padded.  w_lo NULL ok. */
+int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
+                         int fmt, s3_stream stream);
+/* f32 (n, z, y, x, c) -> 16-bit (n, z+2*pz, y+2, x+2, c), pz = (ndim == 3), reflect halo. */
+int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
+                      void* lo, int fmt, s3_stream stream);
+/* inverse (interior only); lo may be NULL.  For tests. */
+int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int n, const int32_t dims[3],
+                        int c, float* x, int fmt, s3_stream stream);
+
+/* ---- stand-alone layers (eager path; the literal reference op order) ---------------------
+ * Shapes are given as up to 5 leading extents + channels: dims[0..4] (unused leading = 1). */
+/* tf.pad (phygnn FlexiblePadding.call) over dims (n, z, y, x) + channel pads. */
+int s3_pad_fwd(const float* x, float* y, const int32_t dims[5], const int32_t lo[5],
+               const int32_t hi[5], int mode, s3_stream stream);
+int s3_pad_bwd(const float* dy, float* dx, const int32_t dims[5], const int32_t lo[5],
+               const int32_t hi[5], int mode, s3_stream stream);
+/* keras Cropping2D/3D (also used as its own adjoint helper: bwd zero-fills the border). */
+int s3_crop_fwd(const float* x, float* y, const int32_t dims[5], const int32_t lo[5],
+                const int32_t hi[5], s3_stream stream);
+int s3_crop_bwd(const float* dy, float* dx, const int32_t dims[5], const int32_t lo[5],
+                const int32_t hi[5], s3_stream stream);
+/* LeakyReLU / Activation.  bwd takes the layer OUTPUT y (sign / value recompute). */
+int s3_act_fwd(const float* x, float* y, size_t n, int act, float alpha, s3_stream stream);
+int s3_act_bwd(const float* y, const float* dy, float* dx, size_t n, int act, float alpha,
+               s3_stream stream);
+/* y = a + b (SkipConnection second call, Sup3rAdder).  b is broadcast with period nb. */
+int s3_add(const float* a, const float* b, float* y, size_t n, size_t nb, s3_stream stream);
+/* SpatialExpansion / SpatioTemporalExpansion.  x: (n, z, y, x, c); method 0 nearest, 1 d2t. */
+int s3_expand_fwd(const float* x, float* y, int ndim, int n, const int32_t dims[3], int c,
+                  int spatial_mult, int temporal_mult, int method, int t_roll, s3_stream stream);
+int s3_expand_bwd(const float* dy, float* dx, int ndim, int n, const int32_t dims[3], int c,
+                  int spatial_mult, int temporal_mult, int method, int t_roll, s3_stream stream);
+/* Sup3rConcat: y[v, :ca] = a[v], y[v, ca:] = b[v].  split = adjoint. */
+int s3_concat_fwd(const float* a, int ca, const float* b, int cb, float* y, size_t nvox,
+                  s3_stream stream);
+int s3_concat_bwd(const float* dy, float* da, int ca, float* db, int cb, size_t nvox,
+                  s3_stream stream);
+/* y[v, c] = x[v, c] * scale[c] + shift[c]   (norm_input / un_norm_output, abstract.py:197-275) */
+int s3_channel_affine(const float* x, float* y, size_t nvox, int c, const float* scale,
+                      const float* shift, s3_stream stream);
+/* Dense: y[m, n] = act(x[m, :] @ w[:, n] + b[n]);  w is (k, n) row-major (keras). */
+int s3_dense_fwd(const float* x, const float* w, const float* b, float* y, int m, int k, int n,
+                 int act, float alpha, s3_stream stream);
+int s3_dense_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                 float* db, int m, int k, int n, s3_stream stream);
+
+/* ---- losses and optimiser ------------------------------------------------------------------
+ * Content loss (base.py:478-503): kind 0 MeanSquaredError, 1 MeanAbsoluteError over the first
+ * `c_use` of `c` channels of gen/true (exo channels sliced off).  loss: device scalar
+ * (overwritten).  dgen: NULL or gradient of (weight * loss) w.r.t. gen (zeros on unused ch). */
+int s3_content_loss(const float* gen, const float* truth, size_t nvox, int c, int c_use, int kind,
+                    float weight, float* loss, float* dgen, s3_stream stream);
+/* Relativistic average discriminator loss (base.py:505-549) for logits (b,) each.
+ * loss: device scalar; d_real / d_fake: NULL or gradients scaled by `weight`. */
+int s3_loss_disc(const float* out_real, const float* out_fake, int b, float weight, float* loss,
+                 float* d_real, float* d_fake, s3_stream stream);
+/* keras Adam step over a flat arena (abstract.py:899,912): step is the 1-based iteration. */
+int s3_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                 float beta2, float eps, int64_t step, s3_stream stream);
+/* out[0] = sum(x), out[1] = sum(|x|), out[2] = #nan-or-inf, out[3] = min, out[4] = max */
+int s3_stats(const float* x, size_t n, float* out5, s3_stream stream);
+/* per-channel min/max + NaN count for ForwardPass._output_check (forward_pass.py:384-425):
+ * out: [c][3] = (min, max, n_nan). */
+int s3_channel_check(const float* x, size_t nvox, int c, float* out, s3_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUP3R_B200_H_ */

@@ -1,0 +1,225 @@
+// Shared host/device helpers for libsup3r_b200: error convention, the conv epilogue
+// (bias / activation / residual / affine) and the output scatter (depth_to_space,
+// depth_to_time + roll, nearest repeat, concat-by-stride, padded+mirrored 16-bit copies).
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/sup3r_b200.h"
+
+namespace s3 {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define S3_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      ::s3::set_error(__VA_ARGS__);  \
+      return S3_ERR_INVALID;         \
+    }                                \
+  } while (0)
+
+#define S3_CUDA(expr)                                                  \
+  do {                                                                 \
+    cudaError_t e__ = (expr);                                          \
+    if (e__ != cudaSuccess) return ::s3::cuda_fail(e__, #expr);        \
+  } while (0)
+
+#define S3_LAUNCH_CHECK(name) S3_CUDA(cudaPeekAtLastError())
+
+inline cudaStream_t as_stream(s3_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+
+// ------------------------------------------------------------------ conv geometry (POD)
+struct ConvGeom {
+  int ndim, n;
+  int in[3], cin, cout, k[3], st[3], pl[3], ph[3], pad_mode;
+  int od[3];       // conv output extents
+  int act;
+  float alpha;
+  // scatter
+  int r, m, roll, rep[3];
+  int fd[3];       // final (mapped) extents
+  int cmap;        // mapped channels per voxel (cout / (r*r*m))
+  int cstride, coff;
+};
+
+int make_geom(const s3_conv_desc* d, ConvGeom* g);  // validates; returns S3_OK or error
+
+struct Epilogue {
+  const float* bias;
+  const float* residual;
+  const float* post_scale;
+  const float* post_shift;
+  float* y;          // f32 mapped destination (nullable)
+  void* y_hi;        // 16-bit padded mirrored destination (nullable)
+  void* y_lo;        // residual half of the split (nullable)
+  int fmt;           // 0 bf16, 1 fp16
+};
+
+// ------------------------------------------------------------------------ device side
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  switch (act) {
+    case S3_ACT_RELU: return v > 0.f ? v : 0.f;
+    case S3_ACT_LEAKY: return v >= 0.f ? v : alpha * v;
+    case S3_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case S3_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ uint16_t to16(float v, int fmt) {
+  if (fmt == 0) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
+__device__ __forceinline__ float from16(uint16_t h, int fmt) {
+  if (fmt == 0) return __bfloat162float(__ushort_as_bfloat16(h));
+  return __half2float(__ushort_as_half(h));
+}
+
+// Destination coordinates of one conv-output element after the scatter.
+struct Dest {
+  int z, y, x, c;  // mapped voxel (before out_repeat) and channel
+};
+
+__device__ __forceinline__ Dest map_dest(const ConvGeom& g, int z, int y, int x, int c) {
+  Dest d;
+  int c0 = c, tt = 0, i = 0, j = 0;
+  if (g.m > 1) {
+    int cq = g.cout / g.m;
+    tt = c0 / cq;
+    c0 -= tt * cq;
+  }
+  if (g.r > 1) {
+    int ij = c0 / g.cmap;
+    c0 -= ij * g.cmap;
+    i = ij / g.r;
+    j = ij - i * g.r;
+  }
+  if (g.ndim == 3) {
+    d.z = z * g.r + i;
+    d.y = y * g.r + j;
+    int xt = x * g.m + tt;
+    if (g.m > 1 && g.roll != 0) {
+      int T = g.od[2] * g.m;
+      xt = (xt + g.roll) % T;
+      if (xt < 0) xt += T;
+    }
+    d.x = xt;
+  } else {
+    d.z = 0;
+    d.y = y * g.r + i;
+    d.x = x * g.r + j;
+  }
+  d.c = c0;
+  return d;
+}
+
+// Padded positions (interior + mirrored halo copies) of coordinate o along a dim of extent F.
+// Returns count (1..3); positions are in padded coordinates (0..F+1).
+__device__ __forceinline__ int mirror_positions(int o, int F, int (&pos)[3]) {
+  int cnt = 0;
+  pos[cnt++] = o + 1;
+  if (o == 1) pos[cnt++] = 0;
+  if (o == F - 2) pos[cnt++] = F + 1;
+  return cnt;
+}
+
+// Store a run of `len` consecutive destination channels (same mapped voxel) starting at mapped
+// channel d.c.  `v` holds the final values.  Handles out_repeat and the 16-bit mirrored copies.
+template <int MAXLEN>
+__device__ __forceinline__ void store_run(const ConvGeom& g, const Epilogue& ep, int b,
+                                          const Dest& d, const float* v, int len) {
+  const int FZ = g.fd[0], FY = g.fd[1], FX = g.fd[2];
+  for (int rz = 0; rz < g.rep[0]; ++rz)
+    for (int ry = 0; ry < g.rep[1]; ++ry)
+      for (int rx = 0; rx < g.rep[2]; ++rx) {
+        const int oz = d.z * g.rep[0] + rz, oy = d.y * g.rep[1] + ry, ox = d.x * g.rep[2] + rx;
+        if (ep.y) {
+          size_t off = ((((size_t)b * FZ + oz) * FY + oy) * FX + ox) * g.cstride + g.coff + d.c;
+          float* dst = ep.y + off;
+          if ((len & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < MAXLEN / 4; ++q)
+              if (q * 4 < len)
+                reinterpret_cast<float4*>(dst)[q] =
+                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < MAXLEN; ++q)
+              if (q < len) dst[q] = v[q];
+          }
+        }
+        if (ep.y_hi) {
+          const int pz = (g.ndim == 3) ? 1 : 0;
+          const int PZ = FZ + 2 * pz, PY = FY + 2, PX = FX + 2;
+          int zs[3], ys[3], xs[3];
+          int nz = 1;
+          zs[0] = oz;
+          if (pz) nz = mirror_positions(oz, FZ, zs);
+          const int ny = mirror_positions(oy, FY, ys);
+          const int nx = mirror_positions(ox, FX, xs);
+          uint16_t hi[MAXLEN], lo[MAXLEN];
+#pragma unroll
+          for (int q = 0; q < MAXLEN; ++q) {
+            float f = q < len ? v[q] : 0.f;
+            hi[q] = to16(f, ep.fmt);
+            lo[q] = to16(f - from16(hi[q], ep.fmt), ep.fmt);
+          }
+          for (int a = 0; a < nz; ++a)
+            for (int bq = 0; bq < ny; ++bq)
+              for (int cq = 0; cq < nx; ++cq) {
+                size_t off =
+                    ((((size_t)b * PZ + zs[a]) * PY + ys[bq]) * PX + xs[cq]) * g.cstride +
+                    g.coff + d.c;
+                uint16_t* dh = reinterpret_cast<uint16_t*>(ep.y_hi) + off;
+                uint16_t* dl = ep.y_lo ? reinterpret_cast<uint16_t*>(ep.y_lo) + off : nullptr;
+                if ((len & 7) == 0 && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0)) {
+#pragma unroll
+                  for (int q = 0; q < MAXLEN / 8; ++q)
+                    if (q * 8 < len) {
+                      uint4 u;
+                      u.x = hi[q * 8] | (uint32_t(hi[q * 8 + 1]) << 16);
+                      u.y = hi[q * 8 + 2] | (uint32_t(hi[q * 8 + 3]) << 16);
+                      u.z = hi[q * 8 + 4] | (uint32_t(hi[q * 8 + 5]) << 16);
+                      u.w = hi[q * 8 + 6] | (uint32_t(hi[q * 8 + 7]) << 16);
+                      reinterpret_cast<uint4*>(dh)[q] = u;
+                      if (dl) {
+                        u.x = lo[q * 8] | (uint32_t(lo[q * 8 + 1]) << 16);
+                        u.y = lo[q * 8 + 2] | (uint32_t(lo[q * 8 + 3]) << 16);
+                        u.z = lo[q * 8 + 4] | (uint32_t(lo[q * 8 + 5]) << 16);
+                        u.w = lo[q * 8 + 6] | (uint32_t(lo[q * 8 + 7]) << 16);
+                        reinterpret_cast<uint4*>(dl)[q] = u;
+                      }
+                    }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < MAXLEN; ++q)
+                    if (q < len) {
+                      dh[q] = hi[q];
+                      if (dl) dl[q] = lo[q];
+                    }
+                }
+              }
+        }
+      }
+}
+
+// Finish one conv-output element: bias, activation, residual, affine.
+__device__ __forceinline__ float finish(const ConvGeom& g, const Epilogue& ep, float acc, int c,
+                                        size_t conv_vox) {
+  float v = acc;
+  if (ep.bias) v += ep.bias[c];
+  v = apply_act(v, g.act, g.alpha);
+  if (ep.residual) v += ep.residual[conv_vox * g.cout + c];
+  if (ep.post_scale) v = v * ep.post_scale[c] + (ep.post_shift ? ep.post_shift[c] : 0.f);
+  return v;
+}
+
+}  // namespace s3

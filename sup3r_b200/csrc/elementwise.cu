@@ -1,0 +1,794 @@
+// HBM-bound layer kernels of the eager path and the training step: padding, cropping,
+// activations, skip add, depth_to_space / depth_to_time / nearest expansion (+ adjoints),
+// channel concat, per-channel affine, 16-bit padded-activation and weight packing for the
+// tcgen05 kernel, content / adversarial losses, Adam, tensor statistics.
+// All are grid-stride, coalesced on the channel-fastest axis, grids sized to the SM count.
+#include "common.cuh"
+
+namespace s3 {
+
+static inline unsigned grid_for(size_t n, int threads = 256) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+struct Shape5 {
+  int d[5], lo[5], hi[5];
+};
+
+__device__ __forceinline__ int fold_pad(int q, int n, int mode, bool* ok) {
+  if (q >= 0 && q < n) return q;
+  if (mode == S3_PAD_REFLECT) {
+    q = q < 0 ? -q : 2 * n - 2 - q;
+  } else if (mode == S3_PAD_SYMMETRIC) {
+    q = q < 0 ? -q - 1 : 2 * n - 1 - q;
+  } else {
+    *ok = false;
+    return 0;
+  }
+  if (q < 0 || q >= n) *ok = false;
+  return q;
+}
+
+__global__ void pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Shape5 s,
+                               int mode, size_t total) {
+  int od[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) od[i] = s.d[i] + s.lo[i] + s.hi[i];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int c[5];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      c[i] = (int)(t % od[i]);
+      t /= od[i];
+    }
+    bool ok = true;
+    size_t src = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int q = fold_pad(c[i] - s.lo[i], s.d[i], mode, &ok);
+      src = src * s.d[i] + q;
+    }
+    y[idx] = ok ? x[src] : 0.f;
+  }
+}
+
+// adjoint of pad: gather every padded position that reads input element idx
+__global__ void pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, Shape5 s,
+                               int mode, size_t total) {
+  int od[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) od[i] = s.d[i] + s.lo[i] + s.hi[i];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int c[5];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      c[i] = (int)(t % s.d[i]);
+      t /= s.d[i];
+    }
+    int pos[5][3], cnt[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int n = s.d[i], k = 0;
+      pos[i][k++] = c[i] + s.lo[i];
+      if (mode == S3_PAD_REFLECT) {
+        if (c[i] >= 1 && c[i] <= s.lo[i]) pos[i][k++] = s.lo[i] - c[i];
+        if (c[i] <= n - 2 && c[i] >= n - 1 - s.hi[i]) pos[i][k++] = s.lo[i] + 2 * n - 2 - c[i];
+      } else if (mode == S3_PAD_SYMMETRIC) {
+        if (c[i] <= s.lo[i] - 1) pos[i][k++] = s.lo[i] - 1 - c[i];
+        if (c[i] >= n - s.hi[i]) pos[i][k++] = s.lo[i] + 2 * n - 1 - c[i];
+      }
+      cnt[i] = k;
+    }
+    float acc = 0.f;
+    for (int a = 0; a < cnt[0]; ++a)
+      for (int b = 0; b < cnt[1]; ++b)
+        for (int cc = 0; cc < cnt[2]; ++cc)
+          for (int e = 0; e < cnt[3]; ++e)
+            for (int f = 0; f < cnt[4]; ++f) {
+              size_t o = pos[0][a];
+              o = o * od[1] + pos[1][b];
+              o = o * od[2] + pos[2][cc];
+              o = o * od[3] + pos[3][e];
+              o = o * od[4] + pos[4][f];
+              acc += dy[o];
+            }
+    dx[idx] = acc;
+  }
+}
+
+__global__ void crop_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Shape5 s,
+                                size_t total) {
+  int od[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) od[i] = s.d[i] - s.lo[i] - s.hi[i];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int c[5];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      c[i] = (int)(t % od[i]);
+      t /= od[i];
+    }
+    size_t src = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) src = src * s.d[i] + c[i] + s.lo[i];
+    y[idx] = x[src];
+  }
+}
+
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
+                               int act, float alpha) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] = apply_act(x[i], act, alpha);
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                               float* __restrict__ dx, size_t n, int act, float alpha) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float o = y[i], g = dy[i];
+    float d;
+    switch (act) {
+      case S3_ACT_RELU: d = o > 0.f ? g : 0.f; break;
+      case S3_ACT_LEAKY: d = o >= 0.f ? g : alpha * g; break;
+      case S3_ACT_SIGMOID: d = g * o * (1.f - o); break;
+      case S3_ACT_TANH: d = g * (1.f - o * o); break;
+      default: d = g;
+    }
+    dx[i] = d;
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                           float* __restrict__ y, size_t n, size_t nb) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[nb == n ? i : i % nb];
+}
+
+struct ExpandGeom {
+  int ndim, n, d[3], c, r, m, method, roll;
+  int od[3], oc;
+};
+
+// element of the expansion INPUT that lands on output element (b, oz, oy, ox, c0)
+__device__ __forceinline__ size_t expand_src(const ExpandGeom& g, int b, int oz, int oy, int ox,
+                                             int c0) {
+  int z, y, x, i, j, tt = 0;
+  if (g.ndim == 3) {
+    z = oz / g.r; i = oz % g.r;
+    y = oy / g.r; j = oy % g.r;
+    if (g.m > 1 && g.method == 1) {
+      int T = g.d[2] * g.m;
+      int xt = (ox - g.roll) % T;
+      if (xt < 0) xt += T;
+      x = xt / g.m;
+      tt = xt % g.m;
+    } else {
+      x = ox / g.m;
+    }
+  } else {
+    z = 0; i = oy % g.r; y = oy / g.r; j = ox % g.r; x = ox / g.r;
+  }
+  const int cq = (g.m > 1 && g.method == 1) ? g.c / g.m : g.c;
+  const int c = tt * cq + (i * g.r + j) * g.oc + c0;
+  return ((((size_t)b * g.d[0] + z) * g.d[1] + y) * g.d[2] + x) * g.c + c;
+}
+
+__global__ void expand_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                  ExpandGeom g, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int c0 = (int)(t % g.oc); t /= g.oc;
+    int ox = (int)(t % g.od[2]); t /= g.od[2];
+    int oy = (int)(t % g.od[1]); t /= g.od[1];
+    int oz = (int)(t % g.od[0]);
+    int b = (int)(t / g.od[0]);
+    y[idx] = x[expand_src(g, b, oz, oy, ox, c0)];
+  }
+}
+
+// adjoint: thread per INPUT element; gathers its (one or m) output images
+__global__ void expand_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                  ExpandGeom g, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int c = (int)(t % g.c); t /= g.c;
+    int x = (int)(t % g.d[2]); t /= g.d[2];
+    int y = (int)(t % g.d[1]); t /= g.d[1];
+    int z = (int)(t % g.d[0]);
+    int b = (int)(t / g.d[0]);
+    const bool d2t = g.m > 1 && g.method == 1;
+    const int cq = d2t ? g.c / g.m : g.c;
+    int tt = c / cq;
+    int cr = c - tt * cq;
+    int ij = cr / g.oc;
+    int c0 = cr - ij * g.oc;
+    int i = ij / g.r, j = ij % g.r;
+    float acc = 0.f;
+    if (g.ndim == 3) {
+      int oz = z * g.r + i, oy = y * g.r + j;
+      if (d2t) {
+        int T = g.d[2] * g.m;
+        int ox = (x * g.m + tt + g.roll) % T;
+        if (ox < 0) ox += T;
+        acc = dy[((((size_t)b * g.od[0] + oz) * g.od[1] + oy) * g.od[2] + ox) * g.oc + c0];
+      } else {
+        for (int k = 0; k < g.m; ++k)
+          acc += dy[((((size_t)b * g.od[0] + oz) * g.od[1] + oy) * g.od[2] + x * g.m + k) * g.oc +
+                    c0];
+      }
+    } else {
+      int oy = y * g.r + i, ox = x * g.r + j;
+      acc = dy[(((size_t)b * g.od[1] + oy) * g.od[2] + ox) * g.oc + c0];
+    }
+    dx[idx] = acc;
+  }
+}
+
+__global__ void concat_fwd_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
+                                  int cb, float* __restrict__ y, size_t total) {
+  const int ct = ca + cb;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t v = idx / ct;
+    int c = (int)(idx - v * ct);
+    y[idx] = c < ca ? a[v * ca + c] : b[v * cb + (c - ca)];
+  }
+}
+
+__global__ void concat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, int ca,
+                                  float* __restrict__ db, int cb, size_t total) {
+  const int ct = ca + cb;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t v = idx / ct;
+    int c = (int)(idx - v * ct);
+    if (c < ca) {
+      if (da) da[v * ca + c] = dy[idx];
+    } else if (db) {
+      db[v * cb + (c - ca)] = dy[idx];
+    }
+  }
+}
+
+__global__ void channel_affine_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                      size_t total, int c, const float* __restrict__ scale,
+                                      const float* __restrict__ shift) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int ch = (int)(idx % c);
+    y[idx] = x[idx] * (scale ? scale[ch] : 1.f) + (shift ? shift[ch] : 0.f);
+  }
+}
+
+// ------------------------------------------------- 16-bit padded activations / weights
+__global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
+                                uint16_t* __restrict__ lo, int pz, int n, int Z, int Y, int X,
+                                int c, int fmt, size_t total) {
+  const int PZ = Z + 2 * pz, PY = Y + 2, PX = X + 2;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int ch = (int)(t % c); t /= c;
+    int px = (int)(t % PX); t /= PX;
+    int py = (int)(t % PY); t /= PY;
+    int pzc = (int)(t % PZ);
+    int b = (int)(t / PZ);
+    bool ok = true;
+    int z = pz ? fold_pad(pzc - 1, Z, S3_PAD_REFLECT, &ok) : pzc;
+    int y = fold_pad(py - 1, Y, S3_PAD_REFLECT, &ok);
+    int xx = fold_pad(px - 1, X, S3_PAD_REFLECT, &ok);
+    float v = ok ? x[((((size_t)b * Z + z) * Y + y) * X + xx) * c + ch] : 0.f;
+    uint16_t h = to16(v, fmt);
+    hi[idx] = h;
+    if (lo) lo[idx] = to16(v - from16(h, fmt), fmt);
+  }
+}
+
+__global__ void unpack_act_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                  float* __restrict__ x, int pz, int n, int Z, int Y, int X, int c,
+                                  int fmt, size_t total) {
+  const int PZ = Z + 2 * pz, PY = Y + 2, PX = X + 2;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int ch = (int)(t % c); t /= c;
+    int xx = (int)(t % X); t /= X;
+    int y = (int)(t % Y); t /= Y;
+    int z = (int)(t % Z);
+    int b = (int)(t / Z);
+    size_t p = ((((size_t)b * PZ + z + pz) * PY + y + 1) * PX + xx + 1) * c + ch;
+    float v = from16(hi[p], fmt);
+    if (lo) v += from16(lo[p], fmt);
+    x[idx] = v;
+  }
+}
+
+__global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi,
+                              uint16_t* __restrict__ lo, int taps, int cin, int cout, int npad,
+                              int fmt, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t t = idx;
+    int ci = (int)(t % cin); t /= cin;
+    int co = (int)(t % npad);
+    int tap = (int)(t / npad);
+    float v = co < cout ? w[((size_t)tap * cin + ci) * cout + co] : 0.f;
+    uint16_t h = to16(v, fmt);
+    hi[idx] = h;
+    if (lo) lo[idx] = to16(v - from16(h, fmt), fmt);
+  }
+}
+
+// ------------------------------------------------------------------------------ losses
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sh[32];
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // valid in thread 0
+}
+
+__global__ void content_loss_kernel(const float* __restrict__ gen, const float* __restrict__ tru,
+                                    size_t total, int c, int c_use, int kind, float weight,
+                                    float inv_count, float* __restrict__ loss,
+                                    float* __restrict__ dgen) {
+  float acc = 0.f;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int ch = (int)(idx % c);
+    float g = 0.f;
+    if (ch < c_use) {
+      float d = gen[idx] - tru[idx];
+      if (kind == 0) {
+        acc += d * d;
+        g = 2.f * d * inv_count * weight;
+      } else {
+        acc += fabsf(d);
+        g = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_count * weight;
+      }
+    }
+    if (dgen) dgen[idx] = g;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_count);
+}
+
+__device__ __forceinline__ float sce_logits(float x, float z) {
+  return fmaxf(x, 0.f) - x * z + log1pf(__expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// single block; b <= a few thousand logits
+__global__ void loss_disc_kernel(const float* __restrict__ t, const float* __restrict__ f, int b,
+                                 float weight, float* __restrict__ loss, float* __restrict__ dt,
+                                 float* __restrict__ df) {
+  __shared__ float sm[4];
+  float st = 0.f, sf = 0.f;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    st += t[i];
+    sf += f[i];
+  }
+  st = block_sum(st);
+  if (threadIdx.x == 0) sm[0] = st / b;
+  sf = block_sum(sf);
+  if (threadIdx.x == 0) sm[1] = sf / b;
+  __syncthreads();
+  const float tbar = sm[0], fbar = sm[1];
+  float l = 0.f, sa = 0.f, sb = 0.f;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float xt = t[i] - fbar, xf = f[i] - tbar;
+    l += sce_logits(xt, 1.f) + sce_logits(xf, 0.f);
+    sa += sigmoidf_(xt) - 1.f;
+    sb += sigmoidf_(xf);
+  }
+  l = block_sum(l);
+  if (threadIdx.x == 0) loss[0] = l / (2.f * b);
+  sa = block_sum(sa);
+  if (threadIdx.x == 0) sm[2] = sa;
+  sb = block_sum(sb);
+  if (threadIdx.x == 0) sm[3] = sb;
+  __syncthreads();
+  const float inv = weight / (2.f * b);
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float a_i = sigmoidf_(t[i] - fbar) - 1.f, b_i = sigmoidf_(f[i] - tbar);
+    if (dt) dt[i] = inv * (a_i - sm[3] / b);
+    if (df) df[i] = inv * (b_i - sm[2] / b);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, size_t n, float lr_t,
+                            float b1, float b2, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+__global__ void stats_kernel(const float* __restrict__ x, size_t n, float* __restrict__ out) {
+  float s = 0.f, sa = 0.f, bad = 0.f, mn = INFINITY, mx = -INFINITY;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (isfinite(v)) {
+      s += v;
+      sa += fabsf(v);
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    } else {
+      bad += 1.f;
+    }
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(out + 0, s);
+  sa = block_sum(sa);
+  if (threadIdx.x == 0) atomicAdd(out + 1, sa);
+  bad = block_sum(bad);
+  if (threadIdx.x == 0) atomicAdd(out + 2, bad);
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // float atomics via int ordering tricks: values compared as ordered ints
+    int imn = __float_as_int(mn), imx = __float_as_int(mx);
+    if (mn >= 0.f) atomicMin(reinterpret_cast<int*>(out + 3), imn);
+    else atomicMax(reinterpret_cast<unsigned*>(out + 3), (unsigned)imn);
+    if (mx >= 0.f) atomicMax(reinterpret_cast<int*>(out + 4), imx);
+    else atomicMin(reinterpret_cast<unsigned*>(out + 4), (unsigned)imx);
+  }
+}
+
+__global__ void stats_init_kernel(float* out) {
+  out[0] = out[1] = out[2] = 0.f;
+  out[3] = INFINITY;
+  out[4] = -INFINITY;
+}
+
+// per-channel (min, max, nan count); one block per channel chunk, loops voxels
+__global__ void channel_check_kernel(const float* __restrict__ x, size_t nvox, int c,
+                                     float* __restrict__ out) {
+  const int ch = blockIdx.x;
+  float mn = INFINITY, mx = -INFINITY, bad = 0.f;
+  for (size_t v = blockIdx.y * (size_t)blockDim.x + threadIdx.x; v < nvox;
+       v += (size_t)gridDim.y * blockDim.x) {
+    float val = x[v * c + ch];
+    if (isnan(val)) bad += 1.f;
+    else {
+      mn = fminf(mn, val);
+      mx = fmaxf(mx, val);
+    }
+  }
+  __shared__ float smn[32], smx[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  bad = block_sum(bad);
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (blockDim.x >> 5); ++i) {
+      mn = fminf(mn, smn[i]);
+      mx = fmaxf(mx, smx[i]);
+    }
+    // out rows are initialised to (+inf, -inf, 0) by the caller-side init kernel
+    int imn = __float_as_int(mn), imx = __float_as_int(mx);
+    if (mn >= 0.f) atomicMin(reinterpret_cast<int*>(out + ch * 3 + 0), imn);
+    else atomicMax(reinterpret_cast<unsigned*>(out + ch * 3 + 0), (unsigned)imn);
+    if (mx >= 0.f) atomicMax(reinterpret_cast<int*>(out + ch * 3 + 1), imx);
+    else atomicMin(reinterpret_cast<unsigned*>(out + ch * 3 + 1), (unsigned)imx);
+    atomicAdd(out + ch * 3 + 2, bad);
+  }
+}
+
+__global__ void channel_check_init_kernel(float* out, int c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    out[i * 3 + 0] = INFINITY;
+    out[i * 3 + 1] = -INFINITY;
+    out[i * 3 + 2] = 0.f;
+  }
+}
+
+static int fill_shape(Shape5* s, const int32_t dims[5], const int32_t lo[5], const int32_t hi[5],
+                      bool crop) {
+  for (int i = 0; i < 5; ++i) {
+    s->d[i] = dims[i];
+    s->lo[i] = lo[i];
+    s->hi[i] = hi[i];
+    S3_REQUIRE(dims[i] > 0 && lo[i] >= 0 && hi[i] >= 0, "bad pad/crop shape on dim %d", i);
+    if (crop) S3_REQUIRE(dims[i] - lo[i] - hi[i] > 0, "cropping removes dim %d entirely", i);
+  }
+  return S3_OK;
+}
+
+static int fill_expand(ExpandGeom* g, int ndim, int n, const int32_t dims[3], int c, int r, int m,
+                       int method, int roll) {
+  S3_REQUIRE(ndim == 2 || ndim == 3, "expand: ndim must be 2 or 3");
+  S3_REQUIRE(r >= 1 && m >= 1 && n > 0 && c > 0, "expand: bad multipliers");
+  S3_REQUIRE(ndim == 3 || m == 1, "expand: temporal_mult needs a 5-D tensor");
+  g->ndim = ndim; g->n = n; g->c = c; g->r = r; g->m = m; g->method = method; g->roll = roll;
+  for (int i = 0; i < 3; ++i) g->d[i] = dims[i];
+  int cq = c;
+  if (m > 1 && method == 1) {
+    S3_REQUIRE(c % m == 0, "depth_to_time: channels %d not divisible by temporal_mult %d", c, m);
+    cq = c / m;
+  }
+  S3_REQUIRE(cq % (r * r) == 0, "depth_to_space: channels %d not divisible by spatial_mult^2 %d",
+             cq, r * r);
+  g->oc = cq / (r * r);
+  if (ndim == 3) {
+    g->od[0] = dims[0] * r; g->od[1] = dims[1] * r; g->od[2] = dims[2] * m;
+  } else {
+    S3_REQUIRE(dims[0] == 1, "expand: 2-D tensors must have z extent 1");
+    g->od[0] = 1; g->od[1] = dims[1] * r; g->od[2] = dims[2] * r;
+  }
+  return S3_OK;
+}
+
+}  // namespace s3
+
+using namespace s3;
+
+extern "C" int s3_pad_fwd(const float* x, float* y, const int32_t dims[5], const int32_t lo[5],
+                          const int32_t hi[5], int mode, s3_stream stream) {
+  Shape5 s;
+  int rc = fill_shape(&s, dims, lo, hi, false);
+  if (rc) return rc;
+  S3_REQUIRE(x && y, "s3_pad_fwd: null pointer");
+  size_t total = 1;
+  for (int i = 0; i < 5; ++i) {
+    if (mode == S3_PAD_REFLECT)
+      S3_REQUIRE(lo[i] < dims[i] && hi[i] < dims[i], "REFLECT pad %d/%d >= extent %d", lo[i],
+                 hi[i], dims[i]);
+    if (mode == S3_PAD_SYMMETRIC)
+      S3_REQUIRE(lo[i] <= dims[i] && hi[i] <= dims[i], "SYMMETRIC pad larger than extent");
+    total *= (size_t)(dims[i] + lo[i] + hi[i]);
+  }
+  pad_fwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, y, s, mode, total);
+  S3_LAUNCH_CHECK("pad_fwd");
+  return S3_OK;
+}
+
+extern "C" int s3_pad_bwd(const float* dy, float* dx, const int32_t dims[5], const int32_t lo[5],
+                          const int32_t hi[5], int mode, s3_stream stream) {
+  Shape5 s;
+  int rc = fill_shape(&s, dims, lo, hi, false);
+  if (rc) return rc;
+  S3_REQUIRE(dy && dx, "s3_pad_bwd: null pointer");
+  size_t total = 1;
+  for (int i = 0; i < 5; ++i) total *= (size_t)dims[i];
+  pad_bwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, dx, s, mode, total);
+  S3_LAUNCH_CHECK("pad_bwd");
+  return S3_OK;
+}
+
+extern "C" int s3_crop_fwd(const float* x, float* y, const int32_t dims[5], const int32_t lo[5],
+                           const int32_t hi[5], s3_stream stream) {
+  Shape5 s;
+  int rc = fill_shape(&s, dims, lo, hi, true);
+  if (rc) return rc;
+  S3_REQUIRE(x && y, "s3_crop_fwd: null pointer");
+  size_t total = 1;
+  for (int i = 0; i < 5; ++i) total *= (size_t)(dims[i] - lo[i] - hi[i]);
+  crop_fwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, y, s, total);
+  S3_LAUNCH_CHECK("crop_fwd");
+  return S3_OK;
+}
+
+extern "C" int s3_crop_bwd(const float* dy, float* dx, const int32_t dims[5], const int32_t lo[5],
+                           const int32_t hi[5], s3_stream stream) {
+  int32_t cd[5];
+  for (int i = 0; i < 5; ++i) cd[i] = dims[i] - lo[i] - hi[i];
+  return s3_pad_fwd(dy, dx, cd, lo, hi, S3_PAD_ZERO, stream);
+}
+
+extern "C" int s3_act_fwd(const float* x, float* y, size_t n, int act, float alpha,
+                          s3_stream stream) {
+  S3_REQUIRE(x && y, "s3_act_fwd: null pointer");
+  if (n == 0) return S3_OK;
+  act_fwd_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, y, n, act, alpha);
+  S3_LAUNCH_CHECK("act_fwd");
+  return S3_OK;
+}
+
+extern "C" int s3_act_bwd(const float* y, const float* dy, float* dx, size_t n, int act,
+                          float alpha, s3_stream stream) {
+  S3_REQUIRE(y && dy && dx, "s3_act_bwd: null pointer");
+  if (n == 0) return S3_OK;
+  act_bwd_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(y, dy, dx, n, act, alpha);
+  S3_LAUNCH_CHECK("act_bwd");
+  return S3_OK;
+}
+
+extern "C" int s3_add(const float* a, const float* b, float* y, size_t n, size_t nb,
+                      s3_stream stream) {
+  S3_REQUIRE(a && b && y && nb > 0 && n % nb == 0, "s3_add: bad arguments");
+  if (n == 0) return S3_OK;
+  add_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, y, n, nb);
+  S3_LAUNCH_CHECK("add");
+  return S3_OK;
+}
+
+extern "C" int s3_expand_fwd(const float* x, float* y, int ndim, int n, const int32_t dims[3],
+                             int c, int spatial_mult, int temporal_mult, int method, int t_roll,
+                             s3_stream stream) {
+  ExpandGeom g;
+  int rc = fill_expand(&g, ndim, n, dims, c, spatial_mult, temporal_mult, method, t_roll);
+  if (rc) return rc;
+  S3_REQUIRE(x && y, "s3_expand_fwd: null pointer");
+  size_t total = (size_t)n * g.od[0] * g.od[1] * g.od[2] * g.oc;
+  expand_fwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, y, g, total);
+  S3_LAUNCH_CHECK("expand_fwd");
+  return S3_OK;
+}
+
+extern "C" int s3_expand_bwd(const float* dy, float* dx, int ndim, int n, const int32_t dims[3],
+                             int c, int spatial_mult, int temporal_mult, int method, int t_roll,
+                             s3_stream stream) {
+  ExpandGeom g;
+  int rc = fill_expand(&g, ndim, n, dims, c, spatial_mult, temporal_mult, method, t_roll);
+  if (rc) return rc;
+  S3_REQUIRE(dy && dx, "s3_expand_bwd: null pointer");
+  size_t total = (size_t)n * dims[0] * dims[1] * dims[2] * c;
+  expand_bwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, dx, g, total);
+  S3_LAUNCH_CHECK("expand_bwd");
+  return S3_OK;
+}
+
+extern "C" int s3_concat_fwd(const float* a, int ca, const float* b, int cb, float* y,
+                             size_t nvox, s3_stream stream) {
+  S3_REQUIRE(a && b && y && ca > 0 && cb > 0, "s3_concat_fwd: bad arguments");
+  size_t total = nvox * (size_t)(ca + cb);
+  if (total == 0) return S3_OK;
+  concat_fwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(a, ca, b, cb, y, total);
+  S3_LAUNCH_CHECK("concat_fwd");
+  return S3_OK;
+}
+
+extern "C" int s3_concat_bwd(const float* dy, float* da, int ca, float* db, int cb, size_t nvox,
+                             s3_stream stream) {
+  S3_REQUIRE(dy && ca > 0 && cb > 0, "s3_concat_bwd: bad arguments");
+  size_t total = nvox * (size_t)(ca + cb);
+  if (total == 0) return S3_OK;
+  concat_bwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, da, ca, db, cb, total);
+  S3_LAUNCH_CHECK("concat_bwd");
+  return S3_OK;
+}
+
+extern "C" int s3_channel_affine(const float* x, float* y, size_t nvox, int c, const float* scale,
+                                 const float* shift, s3_stream stream) {
+  S3_REQUIRE(x && y && c > 0, "s3_channel_affine: bad arguments");
+  size_t total = nvox * (size_t)c;
+  if (total == 0) return S3_OK;
+  channel_affine_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, y, total, c, scale,
+                                                                          shift);
+  S3_LAUNCH_CHECK("channel_affine");
+  return S3_OK;
+}
+
+extern "C" int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c,
+                                 void* hi, void* lo, int fmt, s3_stream stream) {
+  S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_pack_act_pad16: bad arguments");
+  const int pz = ndim == 3 ? 1 : 0;
+  S3_REQUIRE(dims[1] >= 2 && dims[2] >= 2 && (!pz || dims[0] >= 2),
+             "s3_pack_act_pad16: reflect halo needs extents >= 2");
+  size_t total = (size_t)n * (dims[0] + 2 * pz) * (dims[1] + 2) * (dims[2] + 2) * c;
+  pack_act_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
+      x, (uint16_t*)hi, (uint16_t*)lo, pz, n, dims[0], dims[1], dims[2], c, fmt, total);
+  S3_LAUNCH_CHECK("pack_act");
+  return S3_OK;
+}
+
+extern "C" int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int n,
+                                   const int32_t dims[3], int c, float* x, int fmt,
+                                   s3_stream stream) {
+  S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_unpack_act_pad16: bad arguments");
+  const int pz = ndim == 3 ? 1 : 0;
+  size_t total = (size_t)n * dims[0] * dims[1] * dims[2] * c;
+  unpack_act_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
+      (const uint16_t*)hi, (const uint16_t*)lo, x, pz, n, dims[0], dims[1], dims[2], c, fmt,
+      total);
+  S3_LAUNCH_CHECK("unpack_act");
+  return S3_OK;
+}
+
+extern "C" int s3_umma_npad(int cout) { return (cout + 15) / 16 * 16; }
+
+extern "C" int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi,
+                                    void* w_lo, int fmt, s3_stream stream) {
+  S3_REQUIRE(w && w_hi && taps > 0 && cin == 64 && cout > 0 && cout <= 256,
+             "s3_pack_weights_umma: needs cin == 64 and cout <= 256 (got %d, %d)", cin, cout);
+  const int npad = s3_umma_npad(cout);
+  size_t total = (size_t)taps * npad * cin;
+  pack_w_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
+      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, total);
+  S3_LAUNCH_CHECK("pack_w");
+  return S3_OK;
+}
+
+extern "C" int s3_content_loss(const float* gen, const float* truth, size_t nvox, int c, int c_use,
+                               int kind, float weight, float* loss, float* dgen,
+                               s3_stream stream) {
+  S3_REQUIRE(gen && truth && loss && c > 0 && c_use > 0 && c_use <= c && (kind == 0 || kind == 1),
+             "s3_content_loss: bad arguments");
+  size_t total = nvox * (size_t)c;
+  S3_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream)));
+  if (total == 0) return S3_OK;
+  float inv = 1.f / ((float)nvox * (float)c_use);
+  content_loss_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(gen, truth, total, c, c_use,
+                                                                        kind, weight, inv, loss,
+                                                                        dgen);
+  S3_LAUNCH_CHECK("content_loss");
+  return S3_OK;
+}
+
+extern "C" int s3_loss_disc(const float* out_real, const float* out_fake, int b, float weight,
+                            float* loss, float* d_real, float* d_fake, s3_stream stream) {
+  S3_REQUIRE(out_real && out_fake && loss && b > 0, "s3_loss_disc: bad arguments");
+  loss_disc_kernel<<<1, 256, 0, as_stream(stream)>>>(out_real, out_fake, b, weight, loss, d_real,
+                                                     d_fake);
+  S3_LAUNCH_CHECK("loss_disc");
+  return S3_OK;
+}
+
+extern "C" int s3_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr,
+                            float beta1, float beta2, float eps, int64_t step, s3_stream stream) {
+  S3_REQUIRE(p && g && m && v && step >= 1, "s3_adam_step: bad arguments");
+  if (n == 0) return S3_OK;
+  // keras Adam: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)
+  double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) /
+                (1.0 - pow((double)beta1, (double)step));
+  adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, (float)lr_t, beta1, beta2,
+                                                          eps);
+  S3_LAUNCH_CHECK("adam");
+  return S3_OK;
+}
+
+extern "C" int s3_stats(const float* x, size_t n, float* out5, s3_stream stream) {
+  S3_REQUIRE(x && out5, "s3_stats: null pointer");
+  stats_init_kernel<<<1, 1, 0, as_stream(stream)>>>(out5);
+  if (n) stats_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, n, out5);
+  S3_LAUNCH_CHECK("stats");
+  return S3_OK;
+}
+
+extern "C" int s3_channel_check(const float* x, size_t nvox, int c, float* out, s3_stream stream) {
+  S3_REQUIRE(x && out && c > 0, "s3_channel_check: bad arguments");
+  channel_check_init_kernel<<<(c + 255) / 256, 256, 0, as_stream(stream)>>>(out, c);
+  if (nvox) {
+    unsigned gy = (unsigned)((nvox + 255) / 256);
+    unsigned cap = (unsigned)(sm_count() * 8 / (c < 1 ? 1 : c)) + 1;
+    if (gy > cap) gy = cap;
+    dim3 grid(c, gy);
+    channel_check_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, nvox, c, out);
+  }
+  S3_LAUNCH_CHECK("channel_check");
+  return S3_OK;
+}

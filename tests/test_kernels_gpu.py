@@ -1,0 +1,346 @@
+"""Parity of every C-ABI kernel against the CPU oracle (numpy restatement of the reference's
+layer semantics, oracle/layers_ref.py) on seeded inputs.  fp32 kernels: rtol 1e-4 of the tensor
+scale (the north-star bound is 1e-3 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as L
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def dev(a, cuda):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=cuda)
+
+
+def rng_arr(rng, shape, scale=1.0):
+    return (rng.standard_normal(shape) * scale).astype(np.float32)
+
+
+CONV_CASES = [
+    # ndim, in shape, cout, k, stride, padding, act
+    (3, (1, 6, 7, 9, 4), 64, 3, 1, "valid", None),
+    (3, (2, 8, 8, 8, 64), 64, 3, 1, "same", "leaky"),
+    (3, (1, 9, 10, 11, 6), 32, 3, 2, "same", "leaky"),
+    (3, (1, 9, 10, 11, 32), 20, 3, 2, "valid", None),
+    (2, (3, 12, 13, 2), 64, 3, 1, "valid", "relu"),
+    (2, (2, 11, 12, 64), 256, 3, 2, "same", "leaky"),
+    (2, (2, 20, 20, 8), 4, 3, 1, "same", None),
+    (3, (1, 5, 5, 12, 18), 14, 3, 1, "same", None),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_matches_oracle(cuda, case):
+    from sup3r_b200 import ops
+    ndim, shape, cout, k, s, padding, act = case
+    rng = np.random.default_rng(1)
+    x = rng_arr(rng, shape)
+    w = rng_arr(rng, (k,) * ndim + (shape[-1], cout), 0.1)
+    b = rng_arr(rng, (cout,), 0.1)
+    ref = L.conv_nd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), s, padding)
+    if act == "leaky":
+        ref = np.where(ref >= 0, ref, 0.2 * ref)
+    elif act == "relu":
+        ref = np.maximum(ref, 0)
+    sp = shape[1:-1]
+    if padding == "same":
+        pads = [L.same_pads(n, k, s) for n in sp]
+    else:
+        pads = [(0, 0)] * ndim
+    z = [(0, 0)] * (3 - ndim)
+    spec = ops.ConvSpec(ndim, shape[-1], cout, (1,) * (3 - ndim) + (k,) * ndim,
+                        stride=(1,) * (3 - ndim) + (s,) * ndim,
+                        pad_lo=tuple(p[0] for p in z + pads), pad_hi=tuple(p[1] for p in z + pads),
+                        pad_mode=0, act={None: 0, "relu": 1, "leaky": 2}[act], alpha=0.2)
+    y = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec).cpu().numpy()
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("ndim,shape,cout", [(3, (1, 5, 6, 7, 3), 8), (2, (2, 9, 8, 5), 12),
+                                             (3, (1, 4, 4, 6, 64), 64)])
+def test_fused_reflect_conv_equals_pad_conv_crop(cuda, ndim, shape, cout):
+    """FlexiblePadding(3, REFLECT) -> Conv(valid) -> Cropping(2) == reflect-1 fused conv."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(7)
+    x = rng_arr(rng, shape)
+    w = rng_arr(rng, (3,) * ndim + (shape[-1], cout), 0.1)
+    b = rng_arr(rng, (cout,), 0.1)
+    pads = [[0, 0]] + [[3, 3]] * ndim + [[0, 0]]
+    ref = L.crop_nd(L.conv_nd(L.tf_pad(x.astype(np.float64), pads, "REFLECT"),
+                              w.astype(np.float64), b.astype(np.float64)), 2)
+    one = (0,) * (3 - ndim) + (1,) * ndim
+    spec = ops.ConvSpec(ndim, shape[-1], cout, (1,) * (3 - ndim) + (3,) * ndim, pad_lo=one,
+                        pad_hi=one, pad_mode=1)
+    y = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec).cpu().numpy()
+    assert rel_err(y, ref) < TOL
+
+
+def test_conv_transpose_as_flipped_conv(cuda):
+    """Conv2DTranspose(valid, stride 1) == zero-pad-2 conv with the flipped, swapped kernel."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(3)
+    x = rng_arr(rng, (2, 7, 8, 5))
+    wt = rng_arr(rng, (3, 3, 6, 5), 0.1)  # (kh, kw, cout, cin)
+    b = rng_arr(rng, (6,), 0.1)
+    ref = L.conv_transpose_nd(x.astype(np.float64), wt.astype(np.float64), b.astype(np.float64))
+    w = np.ascontiguousarray(wt[::-1, ::-1].transpose(0, 1, 3, 2))
+    spec = ops.ConvSpec(2, 5, 6, (1, 3, 3), pad_lo=(0, 2, 2), pad_hi=(0, 2, 2), pad_mode=0)
+    y = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec).cpu().numpy()
+    assert y.shape == ref.shape and rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("r,m,method,roll,rep", [(2, 1, 0, 0, (1, 1, 1)), (1, 3, 1, 2, (1, 1, 1)),
+                                                 (1, 1, 0, 0, (1, 1, 3)), (5, 1, 0, 0, (1, 1, 1)),
+                                                 (2, 2, 1, -1, (1, 1, 1))])
+def test_conv_epilogue_scatter_3d(cuda, r, m, method, roll, rep):
+    """conv -> LeakyReLU -> SpatioTemporalExpansion fused == oracle layer sequence; also the
+    16-bit padded + mirrored copy equals a REFLECT pad of the result."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(11)
+    cmap = 3
+    cout = cmap * r * r * m
+    x = rng_arr(rng, (2, 4, 5, 6, 7))
+    w = rng_arr(rng, (3, 3, 3, 7, cout), 0.1)
+    b = rng_arr(rng, (cout,), 0.1)
+    ref = L.conv_nd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), 1, "same")
+    ref = np.where(ref >= 0, ref, 0.2 * ref)
+    if rep[2] > 1:
+        ref = L.spatiotemporal_expansion(ref, 1, rep[2], "nearest")
+    else:
+        ref = L.spatiotemporal_expansion(ref, r, m, "depth_to_time", roll)
+    spec = ops.ConvSpec(3, 7, cout, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=0,
+                        act=2, alpha=0.2, d2s=r, d2t=m, t_roll=roll, out_repeat=rep)
+    y, y_hi, y_lo = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec, want_pad16=True,
+                                 split=True)
+    assert tuple(y.shape) == ref.shape
+    assert rel_err(y.cpu().numpy(), ref) < TOL
+    full = (y_hi.float() + y_lo.float()).cpu().numpy()
+    ref_pad = np.pad(ref, [(0, 0), (1, 1), (1, 1), (1, 1), (0, 0)], mode="reflect")
+    assert rel_err(full, ref_pad) < 2e-5  # two bf16 terms carry ~16 mantissa bits
+
+
+def test_conv_epilogue_d2s_2d_and_concat_stride(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(12)
+    x = rng_arr(rng, (2, 6, 7, 5))
+    w = rng_arr(rng, (3, 3, 5, 16), 0.1)
+    b = rng_arr(rng, (16,), 0.1)
+    ref = L.depth_to_space(L.conv_nd(x.astype(np.float64), w.astype(np.float64),
+                                     b.astype(np.float64), 1, "same"), 2)
+    spec = ops.ConvSpec(2, 5, 16, (1, 3, 3), pad_lo=(0, 1, 1), pad_hi=(0, 1, 1), d2s=2,
+                        out_cstride=6, out_coffset=1)
+    out = torch.full((2, 12, 14, 6), -7.0, device=cuda)
+    ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec, out=out)
+    o = out.cpu().numpy()
+    assert rel_err(o[..., 1:5], ref) < TOL
+    assert np.all(o[..., 0] == -7.0) and np.all(o[..., 5] == -7.0)
+
+
+def test_conv_residual_and_affine(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(13)
+    x = rng_arr(rng, (1, 4, 5, 6, 8))
+    w = rng_arr(rng, (3, 3, 3, 8, 8), 0.1)
+    b = rng_arr(rng, (8,), 0.1)
+    res = rng_arr(rng, (1, 4, 5, 6, 8))
+    sc, sh = rng_arr(rng, (8,)), rng_arr(rng, (8,))
+    ref = (L.conv_nd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), 1, "same")
+           + res) * sc + sh
+    spec = ops.ConvSpec(3, 8, 8, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1))
+    y = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec, residual=dev(res, cuda),
+                     post_scale=dev(sc, cuda), post_shift=dev(sh, cuda)).cpu().numpy()
+    assert rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("case", [(3, (2, 6, 7, 8, 5), 9, 1, "same"), (3, (1, 9, 8, 7, 6), 32, 2, "same"),
+                                  (2, (2, 11, 10, 64), 70, 2, "valid"), (2, (1, 9, 9, 3), 4, 1, "valid")])
+def test_conv_backward_matches_autograd(cuda, case):
+    """dgrad / wgrad / dbias against float64 torch autograd of the same cross-correlation."""
+    from sup3r_b200 import ops
+    import torch.nn.functional as F
+    ndim, shape, cout, s, padding = case
+    rng = np.random.default_rng(5)
+    x = rng_arr(rng, shape)
+    w = rng_arr(rng, (3,) * ndim + (shape[-1], cout), 0.1)
+    sp = shape[1:-1]
+    pads = [L.same_pads(n, 3, s) for n in sp] if padding == "same" else [(0, 0)] * ndim
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    perm_in = (0, ndim + 1) + tuple(range(1, ndim + 1))
+    xin = xt.permute(*perm_in)
+    fpad = []
+    for lo, hi in reversed(pads):
+        fpad += [lo, hi]
+    xin = F.pad(xin, fpad)
+    wk = wt.permute(ndim + 1, ndim, *range(ndim))
+    conv = F.conv3d if ndim == 3 else F.conv2d
+    yt = conv(xin, wk, stride=s)
+    yt = yt.permute(0, *range(2, ndim + 2), 1)
+    dy = rng_arr(rng, tuple(yt.shape))
+    yt.backward(torch.tensor(dy, dtype=torch.float64))
+    z = [(0, 0)] * (3 - ndim)
+    spec = ops.ConvSpec(ndim, shape[-1], cout, (1,) * (3 - ndim) + (3,) * ndim,
+                        stride=(1,) * (3 - ndim) + (s,) * ndim,
+                        pad_lo=tuple(p[0] for p in z + pads), pad_hi=tuple(p[1] for p in z + pads))
+    dx = ops.conv_dgrad(dev(dy, cuda), dev(w, cuda), spec, shape).cpu().numpy()
+    dw, db = ops.conv_wgrad(dev(x, cuda), dev(dy, cuda), spec, w.shape)
+    assert rel_err(dx, xt.grad.numpy()) < TOL
+    assert rel_err(dw.cpu().numpy(), wt.grad.numpy()) < TOL
+    assert rel_err(db.cpu().numpy(), dy.reshape(-1, cout).sum(0)) < TOL
+
+
+@pytest.mark.parametrize("mode", ["REFLECT", "CONSTANT", "SYMMETRIC"])
+def test_pad_fwd_bwd(cuda, mode):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(2)
+    x = rng_arr(rng, (2, 5, 6, 7, 3))
+    pads = [[0, 0], [3, 3], [2, 1], [3, 0], [0, 0]]
+    ref = L.tf_pad(x, pads, mode)
+    code = ops.PAD_CODES[mode]
+    y = ops.pad_fwd(dev(x, cuda), pads, code)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    # adjoint identity <pad(x), dy> == <x, pad_bwd(dy)>
+    dy = rng_arr(rng, ref.shape)
+    dx = ops.pad_bwd(dev(dy, cuda), x.shape, pads, code).cpu().numpy()
+    lhs = float((ref.astype(np.float64) * dy).sum())
+    rhs = float((x.astype(np.float64) * dx).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_crop_act_add_concat_affine(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(4)
+    x = rng_arr(rng, (2, 6, 7, 8, 5))
+    y = ops.crop_fwd(dev(x, cuda), [(0, 0), (2, 2), (1, 2), (0, 3), (0, 0)]).cpu().numpy()
+    assert np.array_equal(y, x[:, 2:-2, 1:-2, :-3])
+    dx = ops.crop_bwd(dev(y, cuda), x.shape, [(0, 0), (2, 2), (1, 2), (0, 3), (0, 0)]).cpu().numpy()
+    ref = np.zeros_like(x)
+    ref[:, 2:-2, 1:-2, :-3] = y
+    assert np.array_equal(dx, ref)
+    for act, name in [(1, "relu"), (2, "leaky_relu"), (3, "sigmoid"), (4, "tanh")]:
+        a = ops.act_fwd(dev(x, cuda), act, 0.2).cpu().numpy()
+        assert rel_err(a, L.activation(x.astype(np.float64), name, 0.2)) < 1e-5
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    out = torch.nn.functional.leaky_relu(xt, 0.2)
+    g = rng_arr(rng, x.shape)
+    out.backward(torch.tensor(g, dtype=torch.float64))
+    got = ops.act_bwd(dev(out.detach().numpy(), cuda), dev(g, cuda), 2, 0.2).cpu().numpy()
+    assert rel_err(got, xt.grad.numpy()) < 1e-6
+    b = rng_arr(rng, x.shape)
+    assert np.array_equal(ops.add(dev(x, cuda), dev(b, cuda)).cpu().numpy(), x + b)
+    e = rng_arr(rng, x.shape[:-1] + (1,))
+    cat = ops.concat_fwd(dev(x, cuda), dev(e, cuda)).cpu().numpy()
+    assert np.array_equal(cat, np.concatenate((x, e), -1))
+    da, db = ops.concat_bwd(dev(cat, cuda), 5, 1, want_b=True)
+    assert np.array_equal(da.cpu().numpy(), x) and np.array_equal(db.cpu().numpy(), e)
+    sc, sh = rng_arr(rng, (5,)), rng_arr(rng, (5,))
+    aff = ops.channel_affine(dev(x, cuda), dev(sc, cuda), dev(sh, cuda)).cpu().numpy()
+    assert rel_err(aff, x * sc + sh) < 1e-6
+
+
+@pytest.mark.parametrize("r,m,method,roll", [(2, 1, 0, 0), (1, 3, 0, 0), (3, 2, 0, 0),
+                                             (1, 4, 1, 2), (2, 2, 1, -3), (5, 1, 0, 0)])
+def test_expand_3d_fwd_bwd(cuda, r, m, method, roll):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(6)
+    c = 2 * r * r * (m if method == 1 else 1)
+    x = rng_arr(rng, (2, 3, 4, 5, c))
+    meth = "depth_to_time" if method == 1 else "nearest"
+    ref = L.spatiotemporal_expansion(x, r, m, meth, roll)
+    y = ops.expand_fwd(dev(x, cuda), r, m, method, roll)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    dy = rng_arr(rng, ref.shape)
+    dx = ops.expand_bwd(dev(dy, cuda), x.shape, r, m, method, roll).cpu().numpy()
+    lhs = float((ref.astype(np.float64) * dy).sum())
+    rhs = float((x.astype(np.float64) * dx).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_expand_2d(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(8)
+    x = rng_arr(rng, (3, 4, 5, 18))
+    ref = L.depth_to_space(x, 3)
+    y = ops.expand_fwd(dev(x, cuda), 3)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    dx = ops.expand_bwd(dev(ref, cuda), x.shape, 3).cpu().numpy()
+    assert np.array_equal(dx, x)
+
+
+def test_dense_fwd_bwd(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(9)
+    m, k, n = 5, 777, 130
+    x, w, b = rng_arr(rng, (m, k)), rng_arr(rng, (k, n), 0.05), rng_arr(rng, (n,))
+    ref = x.astype(np.float64) @ w + b
+    y = ops.dense_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), 2, 0.2).cpu().numpy()
+    assert rel_err(y, np.where(ref >= 0, ref, 0.2 * ref)) < TOL
+    dy = rng_arr(rng, (m, n))
+    dx, dw, db = ops.dense_bwd(dev(x, cuda), dev(w, cuda), dev(dy, cuda))
+    assert rel_err(dx.cpu().numpy(), dy.astype(np.float64) @ w.T) < TOL
+    assert rel_err(dw.cpu().numpy(), x.T.astype(np.float64) @ dy) < TOL
+    assert rel_err(db.cpu().numpy(), dy.sum(0)) < TOL
+
+
+def test_losses_and_adam(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(10)
+    g, t = rng_arr(rng, (2, 6, 6, 4, 5)), rng_arr(rng, (2, 6, 6, 4, 5))
+    for kind in (0, 1):
+        gt = torch.tensor(g, dtype=torch.float64, requires_grad=True)
+        d = gt[..., :4] - torch.tensor(t, dtype=torch.float64)[..., :4]
+        ref = (d * d).mean() if kind == 0 else d.abs().mean()
+        (0.7 * ref).backward()
+        loss, dg = ops.content_loss(dev(g, cuda), dev(t, cuda), 4, kind, 0.7, want_grad=True)
+        assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+        assert rel_err(dg.cpu().numpy(), gt.grad.numpy()) < 1e-5
+    a, b = rng_arr(rng, (9, 1)), rng_arr(rng, (9, 1))
+    at = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    logits = torch.cat([at - bt.mean(), bt - at.mean()], 0)
+    labels = torch.cat([torch.ones_like(at), torch.zeros_like(bt)], 0)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels)
+    (0.3 * ref).backward()
+    loss, da, db = ops.loss_disc(dev(a, cuda), dev(b, cuda), 0.3, want_grad=True)
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert rel_err(da.cpu().numpy(), at.grad.numpy()) < 1e-4
+    assert rel_err(db.cpu().numpy(), bt.grad.numpy()) < 1e-4
+    # keras Adam, two steps
+    p0, gr = rng_arr(rng, (1000,)), rng_arr(rng, (1000,))
+    p = dev(p0, cuda)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pr, mr, vr = p0.astype(np.float64), np.zeros(1000), np.zeros(1000)
+    for step in (1, 2):
+        ops.adam_step(p, dev(gr, cuda), m, v, 1e-3, 0.9, 0.999, 1e-7, step)
+        mr = 0.9 * mr + 0.1 * gr
+        vr = 0.999 * vr + 0.001 * gr.astype(np.float64) ** 2
+        lr_t = 1e-3 * np.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)
+        pr = pr - lr_t * mr / (np.sqrt(vr) + 1e-7)
+    assert rel_err(p.cpu().numpy(), pr) < 1e-5
+
+
+def test_stats_and_channel_check(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(14)
+    x = rng_arr(rng, (3, 5, 5, 4))
+    x[..., 2] = 1.5
+    x[0, 0, 0, 3] = np.nan
+    st = ops.stats(dev(x, cuda)).cpu().numpy()
+    fin = x[np.isfinite(x)]
+    assert abs(st[0] - fin.sum()) < 1e-3 and st[2] == 1
+    assert st[3] == fin.min() and st[4] == fin.max()
+    cc = ops.channel_check(dev(x, cuda)).cpu().numpy()
+    assert cc[2, 0] == cc[2, 1] == 1.5 and cc[3, 2] == 1 and cc[0, 2] == 0
+    assert cc[0, 0] == x[..., 0].min() and cc[1, 1] == x[..., 1].max()
