@@ -79,7 +79,7 @@ typedef struct s3_umma_tuning {
   int32_t tiles;            /* M tiles (128 voxels) per CTA work item, 1..8 */
   int32_t w_stages;         /* weight ring depth */
   int32_t box_x;            /* smem x extent of the activation box (>= 10) */
-  int32_t base_offset_mode; /* 0: descriptor base_offset 0; 1: (addr >> 7) & 7 */
+  int32_t box_y;            /* smem y extent of one activation plane (zcat kernel; >= 18) */
   int32_t max_ctas;         /* 0 = SM count */
   int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
 } s3_umma_tuning;
@@ -118,9 +118,13 @@ int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const void* x_lo, 
                      void* y_lo, const s3_umma_tuning* tune, s3_stream stream);
 /* rows of the packed weight tensor per tap (cout rounded up to a multiple of 16) */
 int s3_umma_npad(int cout);
-/* w (taps, cin=64, cout) f32 -> (taps, npad, 64) 16-bit, cout rows zero padded.  w_lo NULL ok. */
+/* Weight layout the tcgen05 kernel expects for a conv with this rank / cout:
+ * 0 = tap-major (taps, npad, 64); 1 = "zcat" (9 (dy,dx), 3 (dz), npad, 64) (3-D, 3*npad <= 256). */
+int s3_umma_weight_layout(int ndim, int cout, int split);
+/* w (taps, cin=64, cout) f32 (keras tap order dz, dy, dx) -> 16-bit packed tensor in `layout`,
+ * cout rows zero padded to npad.  w_lo NULL = no split. */
 int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
-                         int fmt, s3_stream stream);
+                         int fmt, int layout, s3_stream stream);
 /* f32 (n, z, y, x, c) -> 16-bit (n, z+2*pz, y+2, x+2, c), pz = (ndim == 3), reflect halo. */
 int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
                       void* lo, int fmt, s3_stream stream);

@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
 class UmmaTuning(C.Structure):
     """``s3_umma_tuning``"""
     _fields_ = [("tiles", C.c_int32), ("w_stages", C.c_int32), ("box_x", C.c_int32),
-                ("base_offset_mode", C.c_int32), ("max_ctas", C.c_int32), ("fmt", C.c_int32)]
+                ("box_y", C.c_int32), ("max_ctas", C.c_int32), ("fmt", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -55,7 +55,8 @@ SIGNATURES = {
     "s3_conv_wgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "s3_conv_fwd_umma": (_I, [C.POINTER(ConvDesc)] + [_P] * 11 + [C.POINTER(UmmaTuning), _P]),
     "s3_umma_npad": (_I, [_I]),
-    "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
+    "s3_umma_weight_layout": (_I, [_I, _I, _I]),
+    "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "s3_pack_act_pad16": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _P]),
     "s3_unpack_act_pad16": (_I, [_P, _P, _I, _I, c_i32x3, _I, _P, _I, _P]),
     "s3_pad_fwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),

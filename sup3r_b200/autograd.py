@@ -1,0 +1,213 @@
+"""Differentiable wrappers: every forward AND backward below is one of our CUDA kernels
+(``ops``); ``torch.autograd`` is used only as the tape that orders them, standing in for
+``tf.GradientTape`` in the reference (sup3r/models/abstract.py:1230-1238).
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+
+from . import ops
+from ._cabi import S3_ACT_NONE, S3_PAD_ZERO
+
+
+class ConvFn(torch.autograd.Function):
+    """conv (+ implicit zero / reflect / symmetric pad) + bias + activation."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, spec):
+        y = ops.conv_fwd(x, w, b, spec)
+        ctx.spec = spec
+        ctx.x_shape = tuple(x.shape)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w, y if spec.act != S3_ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        spec = ctx.spec
+        dy = dy.contiguous()
+        if spec.act != S3_ACT_NONE:
+            dy = ops.act_bwd(y, dy, spec.act, spec.alpha)
+        lin = dataclasses.replace(spec, act=S3_ACT_NONE)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
+        if ctx.needs_input_grad[0]:
+            if spec.pad_mode == S3_PAD_ZERO:
+                dx = ops.conv_dgrad(dy, w, lin, ctx.x_shape)
+            else:
+                # adjoint of an implicit REFLECT / SYMMETRIC pad: valid-conv dgrad on the padded
+                # extent, then fold the halo back with the pad adjoint kernel
+                nd = spec.ndim
+                lo, hi = spec.pad_lo[3 - nd:], spec.pad_hi[3 - nd:]
+                pads = [(0, 0)] + list(zip(lo, hi)) + [(0, 0)]
+                pshape = tuple(s + p[0] + p[1] for s, p in zip(ctx.x_shape, pads))
+                valid = dataclasses.replace(lin, pad_lo=(0, 0, 0), pad_hi=(0, 0, 0),
+                                            pad_mode=S3_PAD_ZERO)
+                dxp = ops.conv_dgrad(dy, w, valid, pshape)
+                dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
+        return dx, dw, db, None
+
+
+class PadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, paddings, mode):
+        ctx.meta = (tuple(x.shape), paddings, mode)
+        return ops.pad_fwd(x, paddings, mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, paddings, mode = ctx.meta
+        return ops.pad_bwd(dy.contiguous(), shape, paddings, mode), None, None
+
+
+class CropFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cropping):
+        ctx.meta = (tuple(x.shape), cropping)
+        return ops.crop_fwd(x, cropping)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, cropping = ctx.meta
+        return ops.crop_bwd(dy.contiguous(), shape, cropping), None
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, alpha):
+        y = ops.act_fwd(x, act, alpha)
+        ctx.meta = (act, alpha)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        act, alpha = ctx.meta
+        return ops.act_bwd(y, dy.contiguous(), act, alpha), None, None
+
+
+class AddFn(torch.autograd.Function):
+    """a + b with b broadcast over leading dims (SkipConnection, Sup3rAdder)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.b_shape = tuple(b.shape)
+        ctx.same = a.numel() == b.numel()
+        return ops.add(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        db = None
+        if ctx.needs_input_grad[1]:
+            if not ctx.same:
+                raise RuntimeError("gradient w.r.t. a broadcast addend is not supported")
+            db = dy
+        return dy, db
+
+
+class ExpandFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, r, m, method, roll):
+        ctx.meta = (tuple(x.shape), r, m, method, roll)
+        return ops.expand_fwd(x, r, m, method, roll)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, r, m, method, roll = ctx.meta
+        return ops.expand_bwd(dy.contiguous(), shape, r, m, method, roll), None, None, None, None
+
+
+class ConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.meta = (a.shape[-1], b.shape[-1])
+        return ops.concat_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ca, cb = ctx.meta
+        da, db = ops.concat_bwd(dy.contiguous(), ca, cb, want_b=ctx.needs_input_grad[1])
+        return da, db
+
+
+class DenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act, alpha):
+        y = ops.dense_fwd(x, w, b, act, alpha)
+        ctx.meta = (act, alpha, b is not None)
+        ctx.save_for_backward(x, w, y if act != S3_ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        act, alpha, has_b = ctx.meta
+        dy = dy.contiguous()
+        if act != S3_ACT_NONE:
+            dy = ops.act_bwd(y, dy, act, alpha)
+        dx, dw, db = ops.dense_bwd(x, w, dy, want_dx=ctx.needs_input_grad[0],
+                                   want_dw=ctx.needs_input_grad[1],
+                                   want_db=has_b and ctx.needs_input_grad[2])
+        return dx, dw, db, None, None
+
+
+class AffineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, shift):
+        ctx.save_for_backward(scale)
+        return ops.channel_affine(x, scale, shift)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        return ops.channel_affine(dy.contiguous(), scale, None), None, None
+
+
+class ContentLossFn(torch.autograd.Function):
+    """keras MeanSquaredError (kind 0) / MeanAbsoluteError (kind 1) over the first c_use
+    channels (base.py:478-503: exo channels sliced off; argument order (gen, true))."""
+
+    @staticmethod
+    def forward(ctx, gen, truth, c_use, kind):
+        loss, dgen = ops.content_loss(gen, truth, c_use, kind, 1.0, want_grad=True)
+        ctx.save_for_backward(dgen)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        (dgen,) = ctx.saved_tensors
+        return ScaleFn.apply(dgen, dl), None, None, None
+
+
+class DiscLossFn(torch.autograd.Function):
+    """Relativistic average discriminator loss (base.py:505-549)."""
+
+    @staticmethod
+    def forward(ctx, out_true, out_gen):
+        loss, dt, dg = ops.loss_disc(out_true, out_gen, 1.0, want_grad=True)
+        ctx.save_for_backward(dt, dg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        dt, dg = ctx.saved_tensors
+        return ScaleFn.apply(dt, dl), ScaleFn.apply(dg, dl)
+
+
+class ScaleFn(torch.autograd.Function):
+    """x * s for a 0-d device scalar s (chain rule through scalar loss weights)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        shp = x.shape
+        flat = x.reshape(-1, 1)
+        return ops.channel_affine(flat, s.reshape(1), None).reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dy):  # pragma: no cover - second order not needed
+        raise RuntimeError("double backward is not supported")

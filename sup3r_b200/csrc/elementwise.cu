@@ -319,13 +319,17 @@ __global__ void unpack_act_kernel(const uint16_t* __restrict__ hi, const uint16_
 
 __global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi,
                               uint16_t* __restrict__ lo, int taps, int cin, int cout, int npad,
-                              int fmt, size_t total) {
+                              int fmt, int layout, size_t total) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     size_t t = idx;
     int ci = (int)(t % cin); t /= cin;
     int co = (int)(t % npad);
     int tap = (int)(t / npad);
+    if (layout == 1) {  // destination order (dy*3+dx, dz) -> source tap (dz*9 + dy*3 + dx)
+      const int dz = tap % 3, dydx = tap / 3;
+      tap = dz * 9 + dydx;
+    }
     float v = co < cout ? w[((size_t)tap * cin + ci) * cout + co] : 0.f;
     uint16_t h = to16(v, fmt);
     hi[idx] = h;
@@ -722,13 +726,15 @@ extern "C" int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int
 extern "C" int s3_umma_npad(int cout) { return (cout + 15) / 16 * 16; }
 
 extern "C" int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi,
-                                    void* w_lo, int fmt, s3_stream stream) {
+                                    void* w_lo, int fmt, int layout, s3_stream stream) {
+  S3_REQUIRE(layout == 0 || (layout == 1 && taps == 27),
+             "s3_pack_weights_umma: layout 1 (zcat) needs 27 taps");
   S3_REQUIRE(w && w_hi && taps > 0 && cin == 64 && cout > 0 && cout <= 256,
              "s3_pack_weights_umma: needs cin == 64 and cout <= 256 (got %d, %d)", cin, cout);
   const int npad = s3_umma_npad(cout);
   size_t total = (size_t)taps * npad * cin;
   pack_w_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
-      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, total);
+      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, layout, total);
   S3_LAUNCH_CHECK("pack_w");
   return S3_OK;
 }

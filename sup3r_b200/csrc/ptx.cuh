@@ -181,6 +181,39 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t sb
   uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((base_offset & 7u) << 17) | (2u << 29);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+// Split form for hot loops: the high word is loop invariant, the low word is
+// ((addr >> 4) & 0x3FFF) | LBO(1) << 16 and advances by (bytes >> 4).
+__device__ __forceinline__ uint32_t sdesc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr) {
+  return ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// accumulate variants with an immediate predicate (no setp in the issue loop)
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_new(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, K-major A and B, M = 128.
 // fmt: 0 = fp16 operands, 1 = bf16 operands.
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n, uint32_t fmt) {

@@ -1,0 +1,243 @@
+// Lean epilogue for the tcgen05 convolutions: one thread owns one accumulator row (= one conv
+// output voxel, `cout` fp32 columns in TMEM).  Everything per-row lives in registers (the CTA
+// keeps ~215 KB of shared memory, which leaves almost no L1, so local-memory or repeated global
+// loads would each cost an L2 round trip): destinations are a base offset plus at most one
+// mirror delta per dim; the bias sits in shared memory; the residual row is prefetched.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace s3 {
+
+struct RowPlan {
+  bool valid, slow;
+  int b, z, y, x;
+  size_t conv_vox;
+  size_t base32;         // f32 element offset of the rx = 0 copy
+  size_t base16;         // 16-bit element offset of the rx = 0 copy (interior position)
+  long long mz, my;      // halo mirror deltas along z / y in elements (0 = none)
+};
+
+// plain mapping (no depth_to_space / depth_to_time); nearest repeat along x only
+__device__ __forceinline__ void plan_plain(const ConvGeom& g, const Epilogue& ep, RowPlan& rp) {
+  rp.slow = (g.rep[0] != 1 || g.rep[1] != 1 || g.rep[2] > 3 || g.r != 1 || g.m != 1);
+  rp.base32 = rp.base16 = 0;
+  rp.mz = rp.my = 0;
+  if (!rp.valid || rp.slow) return;
+  const int FZ = g.fd[0], FY = g.fd[1], FX = g.fd[2];
+  const int pz = (g.ndim == 3) ? 1 : 0;
+  const long long PY = FY + 2, PX = FX + 2;
+  const int ox0 = rp.x * g.rep[2];
+  rp.base32 = ((((size_t)rp.b * FZ + rp.z) * FY + rp.y) * FX + ox0) * g.cstride + g.coff;
+  rp.base16 = ((((size_t)rp.b * (FZ + 2 * pz) + rp.z + pz) * PY + rp.y + 1) * PX + ox0 + 1) *
+                  g.cstride + g.coff;
+  const long long sy = PX * g.cstride, sz = PY * sy;
+  if (pz) {
+    const bool lo = rp.z == 1, hi = rp.z == FZ - 2;
+    if (lo && hi) rp.slow = true;
+    rp.mz = lo ? -2 * sz : (hi ? 2 * sz : 0);
+  }
+  {
+    const bool lo = rp.y == 1, hi = rp.y == FY - 2;
+    if (lo && hi) rp.slow = true;
+    rp.my = lo ? -2 * sy : (hi ? 2 * sy : 0);
+  }
+  if (FX == 3) rp.slow = true;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == 0) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void store16x2(uint16_t* base, long long off, const uint4& a,
+                                          const uint4& b) {
+  uint4* d = reinterpret_cast<uint4*>(base + off);
+  d[0] = a;
+  d[1] = b;
+}
+
+// Process all column chunks of one accumulator row.  t_addr: TMEM address of column 0 of this
+// warp's lane quarter.  sbias: bias staged in shared memory (zeros when absent).
+// All 32 lanes must call (LDTM is warp-collective).
+template <bool kPrefetchResidual>
+__device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& ep,
+                                             const float* sbias, uint32_t t_addr, RowPlan& rp) {
+  const bool mapped = (g.r != 1 || g.m != 1);
+  const bool vec32 = (g.cstride % 4 == 0) && (g.coff % 4 == 0);
+  const bool vec16 = (g.cstride % 8 == 0) && (g.coff % 8 == 0);
+  const bool fast_plain = !mapped && !rp.slow && vec32 && vec16;
+
+  // residual row prefetch (cout <= 64): 16 x LDG.128 in flight before the first TMEM load
+  float4 rpre[kPrefetchResidual ? 16 : 1];
+  if (kPrefetchResidual) {
+    if (rp.valid && ep.residual) {
+      const float4* rr = reinterpret_cast<const float4*>(ep.residual + rp.conv_vox * g.cout);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q * 4 < g.cout) rpre[q] = __ldg(rr + q);
+    }
+  }
+
+#pragma unroll 1
+  for (int c0 = 0; c0 < g.cout; c0 += 16) {
+    uint32_t raw[16];
+    tmem_ld16(t_addr + c0, raw);
+    tmem_ld_wait();
+    if (!rp.valid) continue;
+    const int len = min(16, g.cout - c0);
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    if (len == 16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * q);
+        v[4 * q] += bv.x; v[4 * q + 1] += bv.y; v[4 * q + 2] += bv.z; v[4 * q + 3] += bv.w;
+      }
+      if (g.act == S3_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
+      } else if (g.act == S3_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (g.act != S3_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+      }
+      if (ep.residual) {
+        if (kPrefetchResidual) {
+          // select the prefetched quad for this chunk with static indices
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (c0 == cc * 16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 r4 = rpre[cc * 4 + q];
+                v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+              }
+            }
+        } else {
+          const float4* rr =
+              reinterpret_cast<const float4*>(ep.residual + rp.conv_vox * g.cout + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 r4 = __ldg(rr + q);
+            v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+          }
+        }
+      }
+      if (ep.post_scale) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = v[j] * ep.post_scale[c0 + j] + (ep.post_shift ? ep.post_shift[c0 + j] : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = j < len ? finish(g, ep, v[j], c0 + j, rp.conv_vox) : 0.f;
+    }
+
+    if (fast_plain && len == 16) {
+      // ---- fast path: the 16-channel run goes to every destination row
+      uint4 h0, h1, l0, l1;
+      if (ep.y_hi) {
+        h0.x = pack2(v[0], v[1], ep.fmt);   h0.y = pack2(v[2], v[3], ep.fmt);
+        h0.z = pack2(v[4], v[5], ep.fmt);   h0.w = pack2(v[6], v[7], ep.fmt);
+        h1.x = pack2(v[8], v[9], ep.fmt);   h1.y = pack2(v[10], v[11], ep.fmt);
+        h1.z = pack2(v[12], v[13], ep.fmt); h1.w = pack2(v[14], v[15], ep.fmt);
+        if (ep.y_lo) {
+          float e[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e[j] = v[j] - from16(to16(v[j], ep.fmt), ep.fmt);
+          l0.x = pack2(e[0], e[1], ep.fmt);   l0.y = pack2(e[2], e[3], ep.fmt);
+          l0.z = pack2(e[4], e[5], ep.fmt);   l0.w = pack2(e[6], e[7], ep.fmt);
+          l1.x = pack2(e[8], e[9], ep.fmt);   l1.y = pack2(e[10], e[11], ep.fmt);
+          l1.z = pack2(e[12], e[13], ep.fmt); l1.w = pack2(e[14], e[15], ep.fmt);
+        }
+      }
+#pragma unroll
+      for (int rx = 0; rx < 3; ++rx) {
+        if (rx >= g.rep[2]) break;
+        if (ep.y) {
+          float4* dst = reinterpret_cast<float4*>(ep.y + rp.base32 + (size_t)rx * g.cstride + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (ep.y_hi) {
+          const int ox = rp.x * g.rep[2] + rx;
+          const long long mx = ox == 1 ? -2LL * g.cstride
+                                       : (ox == g.fd[2] - 2 ? 2LL * g.cstride : 0LL);
+          const long long o0 = (long long)rp.base16 + (long long)rx * g.cstride + c0;
+          uint16_t* yh = reinterpret_cast<uint16_t*>(ep.y_hi);
+          uint16_t* yl = reinterpret_cast<uint16_t*>(ep.y_lo);
+#pragma unroll
+          for (int combo = 0; combo < 8; ++combo) {
+            const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+            if ((a && rp.mz == 0) || (bq && rp.my == 0) || (cq && mx == 0)) continue;
+            const long long o = o0 + (a ? rp.mz : 0) + (bq ? rp.my : 0) + (cq ? mx : 0);
+            store16x2(yh, o, h0, h1);
+            if (ep.y_lo) store16x2(yl, o, l0, l1);
+          }
+        }
+      }
+    } else if (mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !ep.y_hi && ep.y &&
+               (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && len % g.cmap == 0) {
+      // ---- depth_to_space / depth_to_time fast path: runs of cmap channels, f32 only
+      const int nrun = len / g.cmap;
+      for (int s = 0; s < nrun; ++s) {
+        const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + s * g.cmap);
+        float* dst = ep.y + ((((size_t)rp.b * g.fd[0] + d.z) * g.fd[1] + d.y) * g.fd[2] + d.x) *
+                                g.cstride + g.coff;
+        if (g.cmap == 4) {
+          float4 o;
+          if (s == 0) o = make_float4(v[0], v[1], v[2], v[3]);
+          else if (s == 1) o = make_float4(v[4], v[5], v[6], v[7]);
+          else if (s == 2) o = make_float4(v[8], v[9], v[10], v[11]);
+          else o = make_float4(v[12], v[13], v[14], v[15]);
+          if (vec32) *reinterpret_cast<float4*>(dst) = o;
+          else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
+        } else if (g.cmap == 8) {
+          float4 o0, o1;
+          if (s == 0) { o0 = make_float4(v[0], v[1], v[2], v[3]); o1 = make_float4(v[4], v[5], v[6], v[7]); }
+          else { o0 = make_float4(v[8], v[9], v[10], v[11]); o1 = make_float4(v[12], v[13], v[14], v[15]); }
+          if (vec32) {
+            reinterpret_cast<float4*>(dst)[0] = o0;
+            reinterpret_cast<float4*>(dst)[1] = o1;
+          } else {
+            dst[0] = o0.x; dst[1] = o0.y; dst[2] = o0.z; dst[3] = o0.w;
+            dst[4] = o1.x; dst[5] = o1.y; dst[6] = o1.z; dst[7] = o1.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (vec32)
+              reinterpret_cast<float4*>(dst)[q] =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            else { dst[4 * q] = v[4 * q]; dst[4 * q + 1] = v[4 * q + 1];
+                   dst[4 * q + 2] = v[4 * q + 2]; dst[4 * q + 3] = v[4 * q + 3]; }
+          }
+        }
+      }
+    } else {
+      // ---- generic scatter (rare shapes): element runs through store_run
+      int j = 0;
+      while (j < len) {
+        const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + j);
+        const int run = mapped ? min(g.cmap - d.c, len - j) : len - j;
+        float seg[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) seg[k] = v[(j + k) & 15];
+        store_run<16>(g, ep, rp.b, d, seg, run);
+        j += run;
+      }
+    }
+  }
+}
+
+}  // namespace s3

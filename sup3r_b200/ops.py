@@ -170,17 +170,21 @@ def umma_npad(cout):
     return _cabi.load().s3_umma_npad(cout)
 
 
-def pack_weights_umma(w, split=False, fmt=0):
-    """keras kernel ``(*k, 64, cout)`` f32 -> ``(taps, npad, 64)`` 16-bit (hi, lo|None)."""
+def pack_weights_umma(w, split=False, fmt=0, ndim=None):
+    """keras kernel ``(*k, 64, cout)`` f32 -> packed 16-bit (hi, lo|None) in the layout the
+    tcgen05 kernel wants for this rank / cout (``s3_umma_weight_layout``)."""
     w = _f32(w)
     ensure_device(w)
     cin, cout = w.shape[-2], w.shape[-1]
     taps = w.numel() // (cin * cout)
     npad = umma_npad(cout)
+    if ndim is None:
+        ndim = 3 if taps == 27 else 2
+    layout = _cabi.load().s3_umma_weight_layout(ndim, cout, 1 if split else 0)
     dt = torch.bfloat16 if fmt == 0 else torch.float16
     hi = torch.empty((taps, npad, cin), device=w.device, dtype=dt)
     lo = torch.empty_like(hi) if split else None
-    _cabi.call("s3_pack_weights_umma", _p(w), taps, cin, cout, _p(hi), _p(lo), fmt, _s())
+    _cabi.call("s3_pack_weights_umma", _p(w), taps, cin, cout, _p(hi), _p(lo), fmt, layout, _s())
     _count()
     return hi, lo
 

@@ -10,15 +10,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = [
-    # name, shape (n,z,y,x), ndim, cout, tuning dict, split
-    ("bo0_x10", (1, 4, 16, 16), 3, 64, dict(base_offset_mode=0, box_x=10), 0),
-    ("bo1_x10", (1, 4, 16, 16), 3, 64, dict(base_offset_mode=1, box_x=10), 0),
-    ("bo0_x16", (1, 4, 16, 16), 3, 64, dict(base_offset_mode=0, box_x=16), 0),
-    ("bo1_x16", (1, 4, 16, 16), 3, 64, dict(base_offset_mode=1, box_x=16), 0),
+    # name, shape (n,z,y,x), ndim, cout, tuning dict, split, extra spec kwargs
+    ("zcat_y20", (1, 4, 16, 16), 3, 64, dict(), 0, {}),
+    ("zcat_y18", (1, 4, 16, 16), 3, 64, dict(box_y=18), 0, {}),
+    ("zcat_z5_b2", (2, 5, 16, 24), 3, 64, dict(), 0, {}),
+    ("zcat_r2", (1, 7, 12, 10), 3, 64, dict(tiles=2), 0, {}),
+    ("zcat_r1", (1, 3, 20, 9), 3, 64, dict(tiles=1), 0, {}),
+    ("zcat_split", (1, 6, 16, 16), 3, 64, dict(), 1, {}),
+    ("zcat_rep3", (1, 4, 16, 8), 3, 64, dict(), 0, dict(out_repeat=(1, 1, 3))),
+    ("zcat_c72", (1, 4, 16, 16), 3, 72, dict(), 0, {}),
+    ("tile_2d", (3, 1, 20, 20), 2, 64, dict(), 0, {}),
+    ("tile_2d_big", (2, 1, 40, 36), 2, 64, dict(), 1, {}),
+    ("tile_head200", (1, 4, 16, 16), 3, 200, dict(), 0, dict(d2s=5)),
+    ("tile_c128", (1, 4, 10, 16), 3, 128, dict(), 0, {}),
 ]
 
 
-def run_case(name, shape, ndim, cout, tune, split):
+def run_case(name, shape, ndim, cout, tune, split, extra):
     import torch
     from sup3r_b200 import ops
     from sup3r_b200._cabi import UmmaTuning
@@ -31,27 +39,34 @@ def run_case(name, shape, ndim, cout, tune, split):
     w = torch.randn(k + (64, cout), device=dev) * 0.05
     b = torch.randn(cout, device=dev) * 0.1
     pad = (1, 1, 1) if ndim == 3 else (0, 1, 1)
-    spec = ops.ConvSpec(ndim, 64, cout, k, pad_lo=pad, pad_hi=pad, pad_mode=1, act=2, alpha=0.2)
+    spec = ops.ConvSpec(ndim, 64, cout, k, pad_lo=pad, pad_hi=pad, pad_mode=1, act=2, alpha=0.2,
+                        **extra)
     # reference on bf16-rounded operands with the exact fp32 kernel
     x_hi, x_lo = ops.pack_act_pad16(xt, split=bool(split))
-    w_hi, w_lo = ops.pack_weights_umma(w, split=bool(split))
+    w_hi, w_lo = ops.pack_weights_umma(w, split=bool(split), ndim=ndim)
     xr = ops.unpack_act_pad16(x_hi, x_lo, ndim)
-    wr = (w_hi.float() + (w_lo.float() if w_lo is not None else 0))[:, :cout, :]
-    wr = wr.permute(0, 2, 1).reshape(k + (64, cout)).contiguous()
+    # reference weights = the 16-bit rounded values (hi [+ lo]) in keras layout
+    wb = w.to(torch.bfloat16)
+    wr = wb.float()
+    if split:
+        wr = wr + (w - wr).to(torch.bfloat16).float()
     ref = ops.conv_fwd(xr, wr, b, spec)
     t = UmmaTuning(**tune)
     dims = (z, y, x) if ndim == 3 else (1, y, x)
-    out, out_hi, _ = ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims, want_pad16=True,
-                                       tune=t)
+    plain = spec.d2s == 1 and spec.d2t == 1
+    out, out_hi, out_lo = ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims,
+                                            want_pad16=plain, tune=t)
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     scale = ref.abs().max().item()
-    back = ops.unpack_act_pad16(out_hi, None, ndim)
-    err16 = (back - ref).abs().max().item()
-    # mirrored halo check: repack the fp32 result and compare the whole padded tensor
-    ref_hi, _ = ops.pack_act_pad16(out)
-    halo = (ref_hi.float() - out_hi.float()).abs().max().item()
-    return dict(name=name, max_err=err, ref_scale=scale, err_pad16=err16, halo_err=halo)
+    res = dict(name=name, max_err=err, ref_scale=scale)
+    if plain:
+        back = ops.unpack_act_pad16(out_hi, out_lo, ndim)
+        res["err_pad16"] = (back - ref).abs().max().item()
+        # mirrored halo check: repack the fp32 result and compare the whole padded tensor
+        ref_hi, _ = ops.pack_act_pad16(out)
+        res["halo_err"] = (ref_hi.float() - out_hi.float()).abs().max().item()
+    return res
 
 
 if __name__ == "__main__":
