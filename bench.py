@@ -1,0 +1,342 @@
+"""Benchmark of the sup3r hot path on B200: low-res voxels / second through the generator of
+the north-star configuration (derived 5x spatial / 12x temporal / 4 feature spatiotemporal
+Sup3rGan, LR chunks 16x16x24 -> HR 80x80x288; BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks B] [--precision bf16|bf16x3|fp32]
+  python bench.py --impl reference ...     # CPU stand-in for the reference's TensorFlow path
+
+One "step" = one generator pass over a batch of B synthetic LR chunks (seeded normal fields,
+random-init weights of the named architecture).  ``value`` is device-timed (CUDA events around
+each step, L2 flushed between steps, max over ranks) with inputs resident in HBM; ``e2e`` is
+the same metric through the public ``Sup3rGan.generate`` call with host buffers (H2D of the LR
+batch and D2H of the fp32 HR result inside the timed region).  Under torchrun every rank runs
+the same per-GPU work on its own chunks (weak scaling; the only collective is the weight
+broadcast at start-up, as the reference's nodes share nothing but the model files).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LR_CHUNK = (16, 16, 24, 4)          # s1, s2, t, features
+S_ENH, T_ENH = 5, 12
+WORKLOAD = "Sup3rGan spatiotemporal 5x/12x/4f generator forward, LR chunks 16x16x24x4 -> 80x80x288x4"
+METRIC = "lr_voxels_per_sec"
+
+
+def gen_config():
+    from sup3r_b200 import configs as C
+    return C.spatiotemporal_generator(4, S_ENH, (2, 2, 3), head_filters=200)
+
+
+def algorithmic_flops_per_chunk(hl, lr_shape):
+    """2 * sum over convs of (output voxels after crop) * taps * cin * cout."""
+    from sup3r_b200.network import CustomNetwork, _Conv
+    net = CustomNetwork(hl, name="generator", device="cpu")
+    shp = (1, *lr_shape)
+    flops = 0.0
+    pending = None
+    for lyr in net.layers:
+        out = lyr.out_shape(shp)
+        if isinstance(lyr, _Conv):
+            pending = (lyr, shp[-1])
+        elif pending is not None and type(lyr).__name__.startswith("Cropping"):
+            conv, cin = pending
+            vox = np.prod(out[1:-1])
+            flops += 2.0 * vox * np.prod(conv.kernel_size) * cin * conv.filters
+            pending = None
+        shp = out
+    return flops
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}",
+                                      f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6])
+                          if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def load_peaks():
+    fp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fp):
+        p = json.load(open(fp))
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_reference(steps, warmup, sample_chunks=1):
+    """torch-CPU port of the literal reference op order on all host cores."""
+    import torch
+    from oracle.torch_ref import TorchRefNet
+    from oracle import layers_ref as L
+    hl = gen_config()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    layers = L.build_layers(hl)
+    L.build_weights(layers, (1, *LR_CHUNK), seed=0)
+    net = TorchRefNet(hl, L.get_weights(layers), torch.float32)
+    x = torch.from_numpy(np.random.default_rng(42).standard_normal(
+        (sample_chunks, *LR_CHUNK)).astype(np.float32))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            y = net(x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert tuple(y.shape) == (sample_chunks, 80, 80, 288, 4)
+    vox = sample_chunks * int(np.prod(LR_CHUNK[:3]))
+    return vox, times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    vox, times, cores = cpu_reference(steps, warm)
+    ms = 1e3 * float(np.mean(times))
+    value = vox / (ms / 1e3)
+    sample = (f"{steps} timed pass(es) of 1 LR chunk {LR_CHUNK} through the torch-CPU port of the "
+              "literal reference op order (pad3 -> conv -> crop2 per layer, oneDNN, fp32)")
+    line = {"metric": METRIC, "value": value, "unit": "LR voxels/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": {"workload": WORKLOAD, "chunks_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": "LR voxels/s", "cores": cores,
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "LR voxels/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunks", type=int, default=8, help="LR chunks per step (batch)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--impl", default="sup3r_b200", choices=["sup3r_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from sup3r_b200 import ops, parallel
+    from sup3r_b200.models import Sup3rGan
+    from sup3r_b200 import configs as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        parallel.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.chunks
+
+    hl = gen_config()
+    Sup3rGan.seed(0)
+    model = Sup3rGan(hl, C.discriminator(3, "same", (2048, 1024)), precision=args.precision,
+                     default_device=f"/gpu:{local}",
+                     meta={"lr_features": ["u_10m", "v_10m", "u_100m", "v_100m"],
+                           "hr_out_features": ["u_10m", "v_10m", "u_100m", "v_100m"],
+                           "s_enhance": S_ENH, "t_enhance": T_ENH})
+    model.generator.build((B, *LR_CHUNK))
+    if world > 1:
+        parallel.broadcast_weights([model.generator])   # the one collective: weights, once
+    rng = np.random.default_rng(42 + rank)
+    x_host = torch.from_numpy(rng.standard_normal((B, *LR_CHUNK)).astype(np.float32)).pin_memory()
+    x_dev = x_host.to(dev)
+    plan = model.plan_for(model.generator, args.precision)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        return plan.run_graphed(x_dev)
+
+    for _ in range(W):
+        out = step_device()
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (B, 80, 80, 288, 4)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- device-timed value -------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    evs = []
+    for _ in range(K):
+        flush.zero_()                       # L2 flush between timed iterations (outside events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    barrier()
+    launches = ops.launch_count() - l0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.finish() if sampler else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    vox_step = B * int(np.prod(LR_CHUNK[:3]))
+    value = world * vox_step * K / (total_ms / 1e3)
+
+    # ---------------- end to end through the public API (host buffers) -------------------------
+    x_np = x_host.numpy()
+    for _ in range(2):
+        y_np = model.generate(x_np, precision=args.precision)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        y_np = model.generate(x_np, precision=args.precision)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * vox_step * K / float(te.item())
+    h2d = int(x_np.nbytes)
+    d2h = int(y_np.nbytes)
+
+    if rank != 0:
+        return
+
+    # ---------------- roofline of the dominant kernel (tcgen05 body conv) ----------------------
+    peaks, peaks_src = load_peaks()
+    flops_chunk = algorithmic_flops_per_chunk(hl, LR_CHUNK)
+    roof = None
+    try:
+        n, dims = B, (16, 16, 288)
+        xb = torch.randn((n, *dims, 64), device=dev)
+        wb = torch.randn((3, 3, 3, 64, 64), device=dev) * 0.03
+        bb = torch.randn(64, device=dev) * 0.1
+        split = args.precision == "bf16x3"
+        x_hi, x_lo = ops.pack_act_pad16(xb, split=split)
+        w_hi, w_lo = ops.pack_weights_umma(wb, split=split, ndim=3)
+        spec = ops.ConvSpec(3, 64, 64, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
+                            act=2, alpha=0.2)
+        y_hi = torch.empty_like(x_hi)
+        y_lo = torch.empty_like(x_hi) if split else None
+
+        def body():
+            ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
+                              out_hi=y_hi, out_lo=y_lo)
+        for _ in range(3):
+            body()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        k_ms = float(np.mean(ts))
+        k_flops = 2.0 * n * np.prod(dims) * 27 * 64 * 64
+        achieved = k_flops / (k_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_body_conv_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": "conv_umma_zcat_kernel (64->64 3x3x3, "
+                f"{n}x16x16x288 voxels, bf16 -> padded bf16)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": f"{peaks_src} bf16_tflops_sustained", "kernel_ms": k_ms,
+                "algorithmic_flops_per_launch": k_flops}
+    except Exception as e:  # pragma: no cover
+        roof = {"error": repr(e)[:300]}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        vox, times, cores = cpu_reference(1, 1)
+        cpu = {"value": vox / float(np.mean(times)), "unit": "LR voxels/s", "cores": cores,
+               "kind": "port",
+               "sample": "1 timed pass (after 1 warm-up) of 1 LR chunk 16x16x24x4 through the "
+                         "torch-CPU port of the literal reference op order (fp32, oneDNN)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "LR voxels/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[
+            args.precision], "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chunks_per_step": B, "precision": args.precision,
+                   "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
+                   "parallelism": f"chunk-dp{world}", "cuda_graph": True},
+        "algorithmic_tflops": flops_chunk * B * K * world / (total_ms / 1e3) / 1e12,
+        "frac_of_bf16_peak": (flops_chunk * B * K * world / (total_ms / 1e3) / 1e12)
+        / (world * (peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])),
+        "e2e": {"value": e2e_value, "unit": "LR voxels/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,12 @@ class FlexiblePadding(Layer):
     def out_shape(self, shp):
         if len(shp) != self.rank:
             raise RuntimeError(f"FlexiblePadding of rank {self.rank} got a tensor of rank {len(shp)}")
+        lim = {"REFLECT": 1, "SYMMETRIC": 0}.get(self.mode)
+        if lim is not None:
+            for n, (lo, hi) in zip(shp, self.paddings):
+                if max(lo, hi) > n - lim:
+                    raise RuntimeError(f"{self.mode} padding ({lo}, {hi}) is too large for a "
+                                       f"dimension of extent {n} (shape {tuple(shp)})")
         return tuple(n + lo + hi for n, (lo, hi) in zip(shp, self.paddings))
 
     def forward(self, x):

@@ -1,0 +1,280 @@
+"""``ForwardPass``: run the generator over the chunks of a strategy (mirrors
+sup3r/pipeline/forward_pass.py:32-673).
+
+Differences that are deliberate ("where time goes"):
+* the model stays resident on the GPU instead of being re-loaded from disk per chunk
+  (forward_pass.py:638);
+* chunks of equal padded shape can be stacked on the batch axis (``run_batched``);
+* multi-node distribution is one rank per GPU (``torch.distributed``): rank r runs
+  ``strategy.node_chunks[r]`` with no data-path collective.
+Exception types are the reference's: NaN input -> RuntimeError, failed generator ->
+RuntimeError, constant / NaN output -> MemoryError.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+import pprint
+from datetime import datetime as dt
+
+import numpy as np
+
+from ..utilities import Timer
+from .strategy import ForwardPassChunk, ForwardPassStrategy
+from .utilities import get_model
+
+logger = logging.getLogger(__name__)
+
+
+class ForwardPass:
+    """Forward-pass driver for one node (= one GPU rank)."""
+
+    def __init__(self, strategy, node_index=0):
+        self.timer = Timer()
+        self.strategy = strategy
+        self.model = strategy.get_model()
+        self.node_index = node_index
+        out = strategy.out_pattern
+        assert out is None or out.endswith(".npy"), (
+            f"Received bad output type {out}: sup3r_b200 writes .npy chunk files (h5 / nc "
+            "writers are out of scope)")
+
+    def get_input_chunk(self, chunk_index=0, mode="reflect"):
+        """Chunk with its extra edge padding applied (forward_pass.py:67-74)."""
+        chunk = self.strategy.init_chunk(chunk_index)
+        chunk.input_data, chunk.exo_data = self.pad_source_data(
+            chunk.input_data, chunk.pad_width, chunk.exo_data, mode=mode)
+        return chunk
+
+    @property
+    def meta(self):
+        return {"node_index": self.node_index,
+                "creation_date": dt.now().strftime("%d/%m/%Y %H:%M:%S"),
+                "model_meta": self.model.meta, "gan_params": self.model.model_params,
+                "strategy_meta": self.strategy.meta}
+
+    def _get_step_enhance(self, step):
+        """Enhancement of an exo step's data relative to the low-res input
+        (forward_pass.py:87-120)."""
+        combine_type = step["combine_type"]
+        model_step = step["model"]
+        assert combine_type in ("input", "output", "layer"), (
+            f"Received weird combine_type {combine_type} for step: {step}")
+        if combine_type.lower() == "input":
+            n = model_step
+        else:
+            n = model_step + 1
+        s = int(np.prod(self.model.s_enhancements[:n])) if n > 0 else 1
+        t = int(np.prod(self.model.t_enhancements[:n])) if n > 0 else 1
+        return s, t
+
+    def pad_source_data(self, input_data, pad_width, exo_data, mode="reflect"):
+        """Pad the chunk (and its exo data, scaled by the step enhancement) at domain edges
+        (forward_pass.py:122-186)."""
+        out = np.pad(input_data, (*pad_width, (0, 0)), mode=mode)
+        if exo_data is not None:
+            for feature in exo_data:
+                for i, step in enumerate(exo_data[feature]["steps"]):
+                    s_en, t_en = self._get_step_enhance(step)
+                    widths = (*((en * pw[0], en * pw[1])
+                                for en, pw in zip([s_en, s_en, t_en], pad_width)), (0, 0))
+                    new = step["data"]
+                    if new.ndim == 3:
+                        new = np.repeat(np.expand_dims(new, axis=2),
+                                        step["t_enhance"] * input_data.shape[2], axis=2)
+                    exo_data[feature]["steps"][i]["data"] = np.pad(new, widths, mode=mode)
+        return out, exo_data
+
+    @classmethod
+    def run_generator(cls, data_chunk, hr_crop_slices, model, s_enhance=None, t_enhance=None,
+                      exo_data=None):
+        """(s1, s2, t, f) chunk -> cropped (S1, S2, T, F) high-res output
+        (forward_pass.py:188-272)."""
+        data_chunk, exo_data, i_lr_t, i_lr_s = cls._reshape_data_chunk(model, data_chunk,
+                                                                       exo_data)
+        try:
+            hi_res = Timer()(model.generate, log=True)(data_chunk, exogenous_data=exo_data)
+        except Exception as e:
+            msg = f"Forward pass failed on chunk with shape {data_chunk.shape}."
+            logger.exception(msg)
+            raise RuntimeError(msg) from e
+        if hi_res.ndim == 4:
+            hi_res = np.expand_dims(np.transpose(hi_res, (1, 2, 0, 3)), axis=0)
+        cls._check_enhancement(hi_res, data_chunk, s_enhance, t_enhance, i_lr_s, i_lr_t)
+        return hi_res[0][hr_crop_slices]
+
+    @staticmethod
+    def _check_enhancement(hi_res, data_chunk, s_enhance, t_enhance, i_lr_s, i_lr_t):
+        if s_enhance is not None and hi_res.shape[1] != s_enhance * data_chunk.shape[i_lr_s]:
+            msg = (f"The stated spatial enhancement of {s_enhance}x did not match the low res / "
+                   f"high res shapes of {data_chunk.shape} -> {hi_res.shape}")
+            logger.error(msg)
+            raise RuntimeError(msg)
+        if t_enhance is not None and hi_res.shape[3] != t_enhance * data_chunk.shape[i_lr_t]:
+            msg = (f"The stated temporal enhancement of {t_enhance}x did not match the low res / "
+                   f"high res shapes of {data_chunk.shape} -> {hi_res.shape}")
+            logger.error(msg)
+            raise RuntimeError(msg)
+
+    @staticmethod
+    def _reshape_data_chunk(model, data_chunk, exo_data):
+        """5-D models get a leading obs axis; 4-D models get time as the obs axis
+        (forward_pass.py:274-337)."""
+        if exo_data is not None:
+            models = getattr(model, "models", [model])
+            for feature in exo_data:
+                for i, entry in enumerate(exo_data[feature]["steps"]):
+                    assert entry["model"] < len(models), (
+                        f'model index ({entry["model"]}) for exo step {i} exceeds the number of '
+                        "model steps")
+                    if models[entry["model"]].is_4d:
+                        out = np.transpose(entry["data"], axes=(2, 0, 1, 3))
+                    else:
+                        out = np.expand_dims(entry["data"], axis=0)
+                    exo_data[feature]["steps"][i]["data"] = np.asarray(out)
+        if model.is_4d:
+            i_lr_t, i_lr_s = 0, 1
+            data_chunk = np.transpose(data_chunk, axes=(2, 0, 1, 3))
+        else:
+            i_lr_t, i_lr_s = 3, 1
+            data_chunk = np.expand_dims(data_chunk, axis=0)
+        return np.ascontiguousarray(data_chunk), exo_data, i_lr_t, i_lr_s
+
+    @classmethod
+    def _output_check(cls, out_data, allowed_const):
+        """True when the output has NaNs or a constant channel that is not explicitly allowed
+        (forward_pass.py:384-425)."""
+        if allowed_const is True:
+            return False
+        if allowed_const is False or allowed_const is None:
+            allowed_const = []
+        elif not isinstance(allowed_const, (list, tuple)):
+            allowed_const = [allowed_const]
+        if np.isnan(out_data).any():
+            logger.error("Forward pass output contains NaN values!")
+            return True
+        for i in range(out_data.shape[-1]):
+            value0 = out_data[0, 0, 0, i]
+            if (value0 == out_data[..., i]).all() and value0 not in allowed_const:
+                logger.error("All values are the same for feature channel %d!", i)
+                return True
+        return False
+
+    # ---- drivers -----------------------------------------------------------------------------
+    @classmethod
+    def run(cls, strategy, node_index=0):
+        """Run every unfinished chunk of ``strategy.node_chunks[node_index]``
+        (forward_pass.py:427-449).  Returns {chunk_index: output} for in-memory runs."""
+        out = {}
+        if not strategy.node_finished(node_index):
+            if strategy.pass_workers == 1:
+                out = cls._run_serial(strategy, node_index)
+            else:
+                out = cls._run_batched(strategy, node_index, batch_size=strategy.pass_workers)
+            logger.debug("Timing report:\n%s", pprint.pformat(strategy.timer.log, indent=2))
+        return out
+
+    @classmethod
+    def _run_serial(cls, strategy, node_index):
+        start = dt.now()
+        fwp = cls(strategy, node_index=node_index)
+        outputs = {}
+        chunks = strategy.node_chunks[node_index]
+        for i, chunk_index in enumerate(chunks):
+            chunk_index = int(chunk_index)
+            now = dt.now()
+            if strategy.chunk_finished(chunk_index):
+                continue
+            chunk = fwp.get_input_chunk(chunk_index=chunk_index, mode=strategy.pad_mode)
+            failed, data = cls.run_chunk(
+                chunk=chunk, model_kwargs=strategy.model_kwargs, model_class=strategy.model_class,
+                allowed_const=strategy.allowed_const, output_workers=strategy.output_workers,
+                invert_uv=strategy.invert_uv, nn_fill=strategy.nn_fill, meta=fwp.meta,
+                model=fwp.model)
+            logger.info("Finished forward pass on chunk_index=%s in %s. %d of %d complete.",
+                        chunk_index, dt.now() - now, i + 1, len(chunks))
+            if failed:
+                raise MemoryError(f"Forward pass for chunk_index {chunk_index} failed with "
+                                  "constant output or NaNs.")
+            if chunk.out_file is None:
+                outputs[chunk_index] = data
+        logger.info("Finished forward passes on %d chunks in %s", len(chunks), dt.now() - start)
+        return outputs
+
+    @classmethod
+    def _run_batched(cls, strategy, node_index, batch_size=8):
+        """Stack chunks of equal padded shape on the obs axis (5-D models) -- the on-GPU
+        replacement for the reference's ``SpawnProcessPool`` (forward_pass.py:503-580)."""
+        fwp = cls(strategy, node_index=node_index)
+        model = fwp.model
+        if not model.is_5d or strategy.exo_data is not None:
+            return cls._run_serial(strategy, node_index)
+        groups = {}
+        for chunk_index in strategy.node_chunks[node_index]:
+            chunk_index = int(chunk_index)
+            if strategy.chunk_finished(chunk_index):
+                continue
+            chunk = fwp.get_input_chunk(chunk_index=chunk_index, mode=strategy.pad_mode)
+            cls._check_nan_input(chunk, model)
+            groups.setdefault(chunk.input_data.shape, []).append(chunk)
+        outputs = {}
+        for shape, chunks in groups.items():
+            for i in range(0, len(chunks), batch_size):
+                part = chunks[i:i + batch_size]
+                batch = np.stack([c.input_data for c in part], axis=0)
+                try:
+                    hi_res = model.generate(batch)
+                except Exception as e:
+                    msg = f"Forward pass failed on chunk batch with shape {batch.shape}."
+                    logger.exception(msg)
+                    raise RuntimeError(msg) from e
+                cls._check_enhancement(hi_res, batch, model.s_enhance, model.t_enhance, 1, 3)
+                for c, hr in zip(part, hi_res):
+                    data = hr[c.hr_crop_slice]
+                    if cls._output_check(data, strategy.allowed_const):
+                        raise MemoryError(f"Forward pass for chunk_index {c.index} failed with "
+                                          "constant output or NaNs.")
+                    if c.out_file is not None:
+                        cls._write_output(data, c, fwp.meta)
+                    else:
+                        outputs[c.index] = data
+        return outputs
+
+    @staticmethod
+    def _check_nan_input(chunk, model):
+        mask = np.isnan(chunk.input_data).any(axis=(0, 1, 2))
+        if np.any(mask):
+            feats = np.array(model.lr_features[: len(mask)])[mask] \
+                if len(model.lr_features) >= len(mask) else np.where(mask)[0]
+            msg = f"Input data for {feats} contains NaN values!"
+            logger.error(msg)
+            raise RuntimeError(msg)
+
+    @staticmethod
+    def _write_output(data, chunk, meta):
+        np.save(chunk.out_file, data)
+        import json
+        from ..utilities import safe_cast
+        with open(chunk.out_file + ".meta.json", "w") as f:
+            json.dump({"meta": meta, "hr_times": np.asarray(chunk.hr_times).tolist(),
+                       "index": chunk.index}, f, default=safe_cast)
+
+    @classmethod
+    def run_chunk(cls, chunk: ForwardPassChunk, model_kwargs, model_class, allowed_const,
+                  invert_uv=False, meta=None, nn_fill=True, output_workers=None, model=None):
+        """NaN check -> generator -> output check -> optional write
+        (forward_pass.py:582-673).  ``model``: resident model (else loaded from
+        ``model_kwargs`` like the reference)."""
+        logger.info("Running forward pass for chunk_index=%s.", chunk.index)
+        if model is None:
+            model = get_model(model_class, model_kwargs)
+        cls._check_nan_input(chunk, model)
+        output_data = cls.run_generator(
+            data_chunk=chunk.input_data, hr_crop_slices=chunk.hr_crop_slice,
+            s_enhance=model.s_enhance, t_enhance=model.t_enhance,
+            exo_data=copy.deepcopy(chunk.exo_data), model=model)
+        failed = cls._output_check(output_data, allowed_const=allowed_const)
+        if chunk.out_file is not None and not failed:
+            logger.info("Saving forward pass output to %s.", chunk.out_file)
+            cls._write_output(output_data, chunk, meta)
+        return failed, output_data

@@ -1,0 +1,394 @@
+"""Model-level parity on the GPU: ``Sup3rGan.generate`` / ``discriminate`` / gradients /
+``ForwardPass`` against the CPU oracle (oracle/) on seeded inputs, plus the reference's own
+property tests (tests/forward_pass/test_forward_pass.py:411-558, tests/training/
+test_train_gan.py:166-228, tests/forward_pass/test_multi_step.py:20-58).
+
+Tolerances (relative to the tensor's max magnitude):
+  fp32 path                  1e-4
+  bf16x3 (split tcgen05)     1e-3   <- the north-star bound (1e-3 relative, fp32 reference)
+  bf16 (single-pass tcgen05) 5e-2   (bf16 operands through ~38 stacked convolutions)
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as L
+from oracle.torch_ref import TorchRefNet, disc_loss
+from sup3r_b200 import configs as C
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 5e-2}
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def randomize_biases(net, rng, scale=0.05):
+    for v in net.weights:
+        if v.name.endswith("bias:0"):
+            v.assign(rng.standard_normal(v.shape).astype(np.float32) * scale)
+
+
+def make_model(gen_hl, disc_hl, lr_shape, hr_shape=None, exo=None, seed=0, **kw):
+    from sup3r_b200.models import Sup3rGan
+    Sup3rGan.seed(seed)
+    m = Sup3rGan(gen_hl, disc_hl, **kw)
+    rng = np.random.default_rng(seed + 1)
+    m.generator.build(lr_shape, exo)
+    randomize_biases(m.generator, rng)
+    if hr_shape is not None:
+        m.discriminator.build(hr_shape)
+        randomize_biases(m.discriminator, rng)
+    return m
+
+
+def oracle_out(hl, weights, x, exo=None):
+    layers = L.build_layers(hl)
+    L.set_weights(layers, weights)
+    return L.run_layers(layers, x.astype(np.float64), exo)
+
+
+GEN_CASES = [
+    ("st_5x_12x_4f", C.spatiotemporal_generator(4, 5, (2, 2, 3), head_filters=200),
+     (1, 6, 7, 5, 4), None),
+    ("st_3x_4x_2f_batch2", C.spatiotemporal_generator(2, 3, (2, 2)), (2, 5, 6, 4, 2), None),
+    ("s_2x_2f", C.spatial_generator(2, (2,)), (4, 10, 10, 2), None),
+    ("cc_trh_1x_24x", C.sup3rcc_temporal_d2t_generator(2, 24, 12, n_blocks=3), (1, 6, 5, 4, 2),
+     None),
+    ("cc_wind_5x_topo", C.sup3rcc_spatial_generator(6, 5, 4, exo="topography"), (3, 8, 8, 6),
+     ("topography", (3, 40, 40, 1))),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name,hl,shape,exo", GEN_CASES, ids=[c[0] for c in GEN_CASES])
+def test_generate_matches_oracle(cuda, name, hl, shape, exo, precision):
+    nd = len(shape) - 2
+    m = make_model(hl, C.discriminator(nd, "same", (32,)), shape,
+                   exo={exo[0]: 1} if exo else None)
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal(shape).astype(np.float32)
+    exo_np, exo_arg = None, None
+    if exo:
+        e = rng.standard_normal(exo[1]).astype(np.float32)
+        exo_np = {exo[0]: e}
+        exo_arg = {exo[0]: {"steps": [{"model": 0, "combine_type": "layer", "data": e}]}}
+    ref = oracle_out(hl, m.generator.get_weights(), x, exo_np)
+    y = m.generate(x, exogenous_data=exo_arg, precision=precision)
+    assert y.dtype == np.float32 and y.shape == ref.shape
+    err = rel_err(y, ref)
+    assert err < TOL[precision], f"{name} {precision}: rel err {err:.3e}"
+    # the graphed and the eager plan give bit-identical results
+    y2 = m.generate(x, exogenous_data=exo_arg, precision=precision, use_graph=False)
+    assert np.array_equal(y, y2)
+
+
+def test_generate_without_exo_raises(cuda):
+    hl = C.sup3rcc_spatial_generator(6, 5, 2, exo="topography")
+    m = make_model(hl, C.discriminator(2, "same", (8,)), (1, 8, 8, 6), exo={"topography": 1})
+    with pytest.raises(RuntimeError):
+        m.generate(np.ones((1, 8, 8, 6), np.float32))
+
+
+def test_fused_plan_equals_literal_layer_loop(cuda):
+    """plan (fused pad/conv/crop/act/expansion/skip) == eager per-layer kernels, fp32."""
+    from sup3r_b200.network import CustomNetwork
+    from sup3r_b200.plan import Plan
+    for hl, shape in [(C.spatiotemporal_generator(4, 5, (2, 3), head_filters=200, n_blocks=3),
+                       (1, 5, 6, 4, 4)),
+                      (C.spatial_generator(2, (2, 5), n_blocks=2), (2, 7, 6, 2)),
+                      (C.discriminator(3, "same", (16,)), (2, 9, 10, 11, 3))]:
+        CustomNetwork.seed(1)
+        net = CustomNetwork(hl, name="n")
+        x = torch.randn(shape, device=cuda)
+        net.build(shape)
+        randomize_biases(net, np.random.default_rng(0))
+        with torch.no_grad():
+            lit = net.forward(x)
+        out = Plan(net, "fp32").run(x)
+        assert tuple(lit.shape) == tuple(out.shape)
+        assert rel_err(out.cpu().numpy(), lit.cpu().numpy()) < 1e-5
+
+
+def test_layer_call_protocol(cuda):
+    """layer(x) accepts numpy, returns an object with .numpy() / .shape (abstract.py:1081-1100)"""
+    from sup3r_b200.network import CustomNetwork
+    net = CustomNetwork(C.spatial_generator(2, (2,), n_blocks=1), name="g")
+    x = np.ones((1, 6, 6, 2), np.float32)
+    out = net.layers[0](x)
+    for lyr in net.layers[1:]:
+        out = lyr(out)
+    assert out.shape == (1, 12, 12, 2) and out.numpy().dtype == np.float32
+    assert net.layers[0].rank == 4
+    assert len(net.weights) == 2 * sum(1 for lyr in net if lyr.has_weights)
+
+
+def test_normalisation_and_output_features(cuda):
+    hl = C.spatiotemporal_generator(2, 3, (2, 2), n_blocks=2)
+    means = {"u": 2.0, "v": -3.0}
+    stds = {"u": 4.0, "v": 0.5}
+    m = make_model(hl, C.discriminator(3, "same", (8,)), (1, 5, 5, 4, 2), means=means, stdevs=stds,
+                   meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"]})
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((1, 5, 5, 4, 2)) * 3 + 1).astype(np.float32)
+    xn = (x - np.array([2.0, -3.0])) / np.array([4.0, 0.5])
+    ref = oracle_out(hl, m.generator.get_weights(), xn) * np.array([4.0, 0.5]) \
+        + np.array([2.0, -3.0])
+    y = m.generate(x, precision="fp32")
+    assert rel_err(y, ref) < 1e-4
+    y_raw = m.generate(x, norm_in=False, un_norm_out=False, precision="fp32")
+    assert rel_err(y_raw, oracle_out(hl, m.generator.get_weights(), x)) < 1e-4
+
+
+def test_discriminate_matches_oracle(cuda):
+    hl = C.discriminator(3, "same", (64, 32))
+    m = make_model(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1), hl, (1, 4, 4, 4, 2),
+                   hr_shape=(2, 8, 9, 10, 2))
+    x = np.random.default_rng(7).standard_normal((2, 8, 9, 10, 2)).astype(np.float32)
+    ref = oracle_out(hl, m.discriminator.get_weights(), x)
+    out = m.discriminate(x)
+    assert out.shape == (2, 1) and rel_err(out, ref) < 1e-4
+
+
+def test_gradients_match_float64_autograd(cuda):
+    """get_single_grad (generator step incl. adversarial term, then discriminator step) vs
+    torch-CPU float64 autograd through the restated layer sequence (abstract.py:1190-1238)."""
+    gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
+    disc_hl = C.discriminator(3, "same", (16,))
+    lr_shape, hr_shape = (2, 4, 4, 3, 2), (2, 8, 8, 6, 2)
+    m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, loss="MeanAbsoluteError")
+    rng = np.random.default_rng(11)
+    lr = rng.standard_normal(lr_shape).astype(np.float32)
+    hr = rng.standard_normal(hr_shape).astype(np.float32)
+    w_adv = 0.05
+    g = TorchRefNet(gen_hl, m.generator.get_weights(), torch.float64, requires_grad=True)
+    d = TorchRefNet(disc_hl, m.discriminator.get_weights(), torch.float64, requires_grad=True)
+    hr_t = torch.tensor(hr, dtype=torch.float64)
+    gen = g(torch.tensor(lr, dtype=torch.float64))
+    dt, dg = d(hr_t), d(gen)
+    content = (gen - hr_t).abs().mean()
+    loss_gen = content + w_adv * disc_loss(dg, dt)
+    ref_g = torch.autograd.grad(loss_gen, g.weights, retain_graph=True)
+    loss_disc = disc_loss(dt, dg)
+    ref_d = torch.autograd.grad(loss_disc, d.weights)
+
+    grads, details = m.get_single_grad(lr, hr, m.generator_weights, weight_gen_advers=w_adv,
+                                       train_gen=True, train_disc=False, compute_disc=True)
+    assert abs(float(details["loss_gen"]) - loss_gen.item()) < 1e-4 * abs(loss_gen.item())
+    assert abs(float(details["loss_gen_content"]) - content.item()) < 1e-4
+    assert abs(float(details["loss_disc"]) - loss_disc.item()) < 1e-4
+    assert "mean_absolute_error" in details
+    for got, want, v in zip(grads, ref_g, m.generator_weights):
+        assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-3, v.name
+    grads, details = m.get_single_grad(lr, hr, m.discriminator_weights, weight_gen_advers=w_adv,
+                                       train_gen=False, train_disc=True)
+    for got, want, v in zip(grads, ref_d, m.discriminator_weights):
+        assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-3, v.name
+
+
+class _Batch:
+    def __init__(self, lr, hr):
+        self.low_res, self.high_res = lr, hr
+
+
+class SyntheticBatchHandler:
+    """The attributes Sup3rGan.train needs from a batch handler (base.py:728-733, 1138-1157)."""
+
+    def __init__(self, n_batches=4, batch=4, s=2, t=2, lr_sp=6, lr_t=4, f=2, seed=0):
+        rng = np.random.default_rng(seed)
+        self.s_enhance, self.t_enhance = s, t
+        self.lr_features = self.hr_out_features = ["u", "v"][:f]
+        self.hr_exo_features = []
+        self.means = {k: 0.0 for k in self.lr_features}
+        self.stds = {k: 1.0 for k in self.lr_features}
+        from sup3r_b200.utilities import spatial_coarsening, temporal_coarsening
+        self.batches = []
+        for _ in range(n_batches + 1):
+            z = rng.standard_normal((batch, lr_sp * s // 2, lr_sp * s // 2, lr_t * t, f))
+            hr = np.repeat(np.repeat(z, 2, axis=1), 2, axis=2).astype(np.float32)
+            lr = temporal_coarsening(spatial_coarsening(hr, s), t, "average").astype(np.float32)
+            self.batches.append(_Batch(lr, hr))
+        self.val_data = self.batches[-1:]
+        self.batches = self.batches[:-1]
+        self.lr_shape = self.batches[0].low_res.shape[1:]
+        self.hr_shape = self.batches[0].high_res.shape[1:]
+        self.shapes = (self.batches[0].low_res.shape, self.batches[0].high_res.shape)
+        self.stopped = False
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    def stop(self):
+        self.stopped = True
+
+
+def test_train_loop_history_checkpoint_and_reload(cuda):
+    """Loss goes down, history columns, checkpoints, save -> load identity
+    (tests/training/test_train_gan.py:109-246)."""
+    from sup3r_b200.models import Sup3rGan
+    Sup3rGan.seed(0)
+    loss = {"MeanAbsoluteError": {}, "MeanSquaredError": {}, "term_weights": [0.5, 0.5]}
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=2),
+                 C.discriminator(3, "same", (16,)), learning_rate=2e-3, loss=loss)
+    bh = SyntheticBatchHandler()
+    with tempfile.TemporaryDirectory() as td:
+        m.train(bh, input_resolution={"spatial": "30km", "temporal": "60min"}, n_epoch=4,
+                weight_gen_advers=0.0, train_gen=True, train_disc=False, checkpoint_int=1,
+                out_dir=os.path.join(td, "test_{epoch}"))
+        assert bh.stopped and len(m.history) == 4
+        assert all(m.history["gen_train_frac"] == 1) and all(m.history["disc_train_frac"] == 0)
+        tl = m.history["train_loss_gen"].values
+        assert tl[-1] < tl[0] and np.sum(np.diff(tl)) < 0
+        assert np.sum(np.diff(m.history["val_loss_gen"].values)) < 0
+        for col in ["train_mean_absolute_error", "train_mean_squared_error",
+                    "val_mean_absolute_error", "OptmGen/learning_rate", "OptmDisc/learning_rate",
+                    "elapsed_time", "weight_gen_advers", "total_batches"]:
+            assert col in m.history, col
+        assert any(c.startswith("OptmGen/Adam/v") for c in m.history.columns)
+        assert "test_0" in os.listdir(td) and "test_3" in os.listdir(td)
+        files = os.listdir(os.path.join(td, "test_3"))
+        for f in ["model_gen.pkl", "model_disc.pkl", "history.csv", "model_params.json"]:
+            assert f in files
+        assert m.meta["s_enhance"] == 2 and m.meta["t_enhance"] == 2
+        assert m.output_resolution == {"spatial": "15km", "temporal": "30min"}
+        out_dir = os.path.join(td, "st_gan")
+        m.save(out_dir)
+        loaded = Sup3rGan.load(out_dir)
+        x = bh.batches[0].low_res
+        a = m.generate(x, precision="fp32")
+        b = loaded.generate(x, precision="fp32")
+        assert np.array_equal(a, b)
+        assert loaded.meta["lr_features"] == ["u", "v"]
+        assert len(loaded.history) == 4
+        # a new input shape is accepted (test_train_gan.py:231-245)
+        assert loaded.generate(np.ones((1, 7, 9, 5, 2), np.float32)).shape == (1, 14, 18, 10, 2)
+        fresh = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1),
+                         C.discriminator(3, "same", (16,)))
+        with pytest.raises(RuntimeError):  # test_train_gan.py:389-422
+            fresh.train(SyntheticBatchHandler(), {"spatial": "30km", "temporal": "61min"}, 1,
+                        out_dir=os.path.join(td, "bad_{epoch}"))
+
+
+def test_disc_training_schedule_and_optimizer_update(cuda):
+    from sup3r_b200.models import Sup3rGan
+    Sup3rGan.seed(0)
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1),
+                 C.discriminator(3, "same", (16,)), learning_rate=1e-4, learning_rate_disc=4e-4)
+    assert m.optimizer.learning_rate == 1e-4 and m.optimizer_disc.learning_rate == 4e-4
+    m.update_optimizer(option="generator", learning_rate=2)
+    assert m.optimizer.learning_rate == 2 and m.optimizer_disc.learning_rate == 4e-4
+    m.update_optimizer(option="all", learning_rate=1e-3)
+    assert m.optimizer.learning_rate == 1e-3 and m.optimizer_disc.learning_rate == 1e-3
+    bh = SyntheticBatchHandler(n_batches=3, batch=2)
+    with tempfile.TemporaryDirectory() as td:
+        m.train(bh, {"spatial": "30km", "temporal": "60min"}, n_epoch=2, weight_gen_advers=1e-2,
+                train_gen=True, train_disc=True, disc_loss_bounds=(0.0, 100.0),
+                out_dir=os.path.join(td, "gan_{epoch}"), adaptive_update_fraction=0.05)
+        assert all(m.history["disc_train_frac"] == 1) and all(m.history["gen_train_frac"] == 1)
+        assert np.isfinite(m.history["train_loss_disc"].values).all()
+        assert "train_loss_gen_advers" in m.history
+
+
+def _fwp_model(s=2, t=2, f=2, n_blocks=2):
+    return make_model(C.spatiotemporal_generator(f, s, (t,) if t > 1 else (), n_blocks=n_blocks),
+                      C.discriminator(3, "same", (8,)), (1, 8, 8, 6, f),
+                      meta={"lr_features": ["u", "v"][:f], "hr_out_features": ["u", "v"][:f],
+                            "s_enhance": s, "t_enhance": t})
+
+
+def test_forward_pass_single_chunk_equals_generate(cuda):
+    """tests/forward_pass/test_forward_pass.py:500-558"""
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m = _fwp_model()
+    data = np.random.default_rng(0).standard_normal((12, 12, 10, 2)).astype(np.float32)
+    strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(data, ["u", "v"]),
+                                fwp_chunk_shape=(12, 12, 10), spatial_pad=0, temporal_pad=0)
+    assert strat.n_chunks == 1
+    out = ForwardPass.run(strat, 0)[0]
+    direct = m.generate(data[None])[0]
+    assert out.shape == (24, 24, 20, 2) and np.array_equal(out, direct)
+
+
+def test_forward_pass_chunked_close_to_unchunked(cuda):
+    """Chunked == unchunked when the halo covers the receptive field (reference:
+    test_forward_pass.py:411-497, mean |err| < 1e-6 with pad 20)."""
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m = _fwp_model(n_blocks=1)
+    data = np.random.default_rng(1).standard_normal((16, 16, 16, 2)).astype(np.float32)
+    handler = ArrayInputHandler(data, ["u", "v"])
+    m.precision = "fp32"
+    whole = m.generate(data[None])[0]
+    strat = ForwardPassStrategy(model=m, input_handler=handler, fwp_chunk_shape=(8, 8, 8),
+                                spatial_pad=8, temporal_pad=8, pass_workers=1)
+    assert strat.n_chunks == 8
+    outs = ForwardPass.run(strat, 0)
+    full = np.zeros_like(whole)
+    sl = strat.fwp_slicer
+    for idx, o in outs.items():
+        s_idx, t_idx = sl.get_chunk_indices(idx)
+        hs = sl.s_hr_slices[s_idx]
+        ts = sl.get_hr_slices(sl.t_lr_slices, sl.t_enhance)[t_idx]
+        full[hs[0], hs[1], ts] = o
+    assert np.abs(full - whole).mean() < 1e-6
+    # batched driver (equal-shape chunks stacked on the obs axis) gives the same chunks
+    strat2 = ForwardPassStrategy(model=m, input_handler=handler, fwp_chunk_shape=(8, 8, 8),
+                                 spatial_pad=8, temporal_pad=8, pass_workers=4)
+    outs2 = ForwardPass.run(strat2, 0)
+    for idx in outs:
+        assert np.allclose(outs[idx], outs2[idx], atol=1e-5)
+
+
+def test_forward_pass_failures_and_incremental(cuda):
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m = _fwp_model(n_blocks=1)
+    data = np.random.default_rng(2).standard_normal((8, 8, 8, 2)).astype(np.float32)
+    bad = data.copy()
+    bad[0, 0, 0, 1] = np.nan
+    strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(bad, ["u", "v"]),
+                                fwp_chunk_shape=(8, 8, 8))
+    with pytest.raises(RuntimeError):
+        ForwardPass.run(strat, 0)
+    assert ForwardPass._output_check(np.ones((4, 4, 4, 2)), allowed_const=None)
+    assert not ForwardPass._output_check(np.ones((4, 4, 4, 2)), allowed_const=[1])
+    assert not ForwardPass._output_check(np.ones((4, 4, 4, 2)), allowed_const=True)
+    with tempfile.TemporaryDirectory() as td:
+        pat = os.path.join(td, "out_{file_id}.npy")
+        strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(data, ["u", "v"]),
+                                    fwp_chunk_shape=(4, 4, 8), spatial_pad=1, out_pattern=pat,
+                                    max_nodes=2)
+        assert strat.n_chunks == 4 and len(strat.node_chunks) == 2
+        ForwardPass.run(strat, 0)
+        assert strat.node_finished(0) and not strat.node_finished(1)
+        assert os.path.exists(strat.out_files[0]) and not os.path.exists(strat.out_files[3])
+        ForwardPass.run(strat, 1)
+        assert all(strat.chunk_finished(i) for i in range(4))
+        assert np.load(strat.out_files[0]).shape == (8, 8, 16, 2)
+
+
+def test_multi_step_gan_chain(cuda):
+    """MultiStepGan.generate == model2.generate(model1.generate(x)) with the 4-D -> 5-D
+    transpose (tests/forward_pass/test_multi_step.py:20-58, 131-170)."""
+    from sup3r_b200.models import MultiStepGan
+    m1 = make_model(C.spatial_generator(2, (2,), n_blocks=1), C.discriminator(2, "same", (8,)),
+                    (4, 6, 6, 2), meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"],
+                                        "s_enhance": 2, "t_enhance": 1})
+    m2 = make_model(C.spatiotemporal_generator(2, 1, (2,), n_blocks=1, head_filters=16),
+                    C.discriminator(3, "same", (8,)), (1, 12, 12, 4, 2), seed=3,
+                    meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"],
+                          "s_enhance": 1, "t_enhance": 2})
+    ms = MultiStepGan([m1, m2])
+    assert ms.s_enhance == 2 and ms.t_enhance == 2 and ms.s_enhancements == [2, 1]
+    x = np.random.default_rng(4).standard_normal((4, 6, 6, 2)).astype(np.float32)
+    out = ms.generate(x)
+    step1 = m1.generate(x)
+    step2 = m2.generate(np.transpose(step1, (1, 2, 0, 3))[None])
+    assert out.shape == (1, 12, 12, 8, 2) and np.array_equal(out, step2)

@@ -1,0 +1,131 @@
+"""Pins for the CPU oracle (numpy restatement, oracle/layers_ref.py).
+
+The convolution arithmetic of the reference lives in TensorFlow / phygnn, which are not
+importable here, and the reference tests hold no golden outputs for it: parity is UNPINNED for
+conv arithmetic.  What can be pinned is pinned here: (1) the reference's own shape tables
+(tests/training/test_load_configs.py), (2) an independent float64 implementation of every layer
+(torch CPU ops, oracle/torch_ref.py) on seeded inputs, (3) the algebraic identities the fused
+kernels rely on (pad-3/conv/crop-2 == reflect-1 conv; Conv2DTranspose == flipped conv),
+(4) TensorFlow's documented conventions for SAME padding and depth_to_space on hand-computed
+examples."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as L
+from oracle.torch_ref import TorchRefNet
+from sup3r_b200 import configs as C
+
+
+def build(hl, in_shape, seed=0):
+    layers = L.build_layers(hl)
+    L.build_weights(layers, in_shape, seed=seed)
+    return layers
+
+
+CASES = [
+    ("st_5x_12x", C.spatiotemporal_generator(4, 5, (2, 2, 3), head_filters=200), (1, 5, 6, 4, 4), None),
+    ("st_3x_4x", C.spatiotemporal_generator(2, 3, (2, 2)), (2, 5, 5, 4, 2), None),
+    ("s_2x", C.spatial_generator(2, (2,)), (3, 7, 8, 2), None),
+    ("s_10x", C.spatial_generator(2, (2, 5), n_blocks=2), (1, 6, 6, 2), None),
+    ("cc_trh_d2t", C.sup3rcc_temporal_d2t_generator(2, 24, 12, n_blocks=2), (1, 5, 5, 4, 2), None),
+    ("cc_wind_exo", C.sup3rcc_spatial_generator(6, 5, 4, exo="topography"), (2, 6, 6, 6),
+     ("topography", (2, 30, 30, 1))),
+    ("disc_st_same", C.discriminator(3, "same", (64, 32)), (2, 9, 9, 10, 3), None),
+    ("disc_s_valid", C.discriminator(2, "valid", (32,)), (1, 64, 64, 2), None),
+]
+
+
+@pytest.mark.parametrize("name,hl,shape,exo", CASES, ids=[c[0] for c in CASES])
+def test_numpy_oracle_agrees_with_torch_restatement(name, hl, shape, exo):
+    rng = np.random.default_rng(3)
+    layers = build(hl, shape)
+    x = rng.standard_normal(shape)
+    exo_d = {exo[0]: rng.standard_normal(exo[1])} if exo else None
+    y = L.run_layers(layers, x.astype(np.float64), exo_d)
+    net = TorchRefNet(hl, L.get_weights(layers), dtype=torch.float64)
+    yt = net(torch.tensor(x), exo_d).numpy()
+    assert y.shape == yt.shape
+    assert np.abs(y - yt).max() <= 1e-9 * max(np.abs(yt).max(), 1.0)
+
+
+def test_shape_tables_of_reference_tests():
+    """tests/training/test_load_configs.py: (n, 7, 7, [4], f) ones -> enhanced shapes."""
+    for s, t, f, tm in [(3, 4, 2, (2, 2)), (2, 12, 14, (2, 2, 3)), (4, 24, 3, (2, 2, 2, 3))]:
+        hl = C.spatiotemporal_generator(f, s, tm)
+        layers = L.build_layers(hl)
+        shp = (1, 7, 7, 4, f)
+        for lyr in layers:
+            shp = L.out_shape(lyr, shp)
+        assert shp == (1, 7 * s, 7 * s, 4 * t, f)
+    layers = build(C.spatial_generator(2, (2,)), (4, 10, 10, 2))
+    y = L.run_layers(layers, np.ones((4, 10, 10, 2), np.float32))
+    assert y.shape == (4, 20, 20, 2) and y.dtype == np.float32
+
+
+def test_fusion_identities():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 6, 7, 5, 3))
+    w = rng.standard_normal((3, 3, 3, 3, 4))
+    b = rng.standard_normal(4)
+    lit = L.crop_nd(L.conv_nd(L.tf_pad(x, [[0, 0], [3, 3], [3, 3], [3, 3], [0, 0]], "REFLECT"),
+                              w, b), 2)
+    fused = L.conv_nd(L.tf_pad(x, [[0, 0], [1, 1], [1, 1], [1, 1], [0, 0]], "REFLECT"), w, b)
+    assert np.abs(lit - fused).max() < 1e-12
+    x2 = rng.standard_normal((2, 7, 8, 5))
+    wt = rng.standard_normal((3, 3, 6, 5))
+    lit = L.crop_nd(L.conv_transpose_nd(L.tf_pad(x2, [[0, 0], [3, 3], [3, 3], [0, 0]], "REFLECT"),
+                                        wt), 4)
+    wf = wt[::-1, ::-1].transpose(0, 1, 3, 2)
+    fused = L.conv_nd(L.tf_pad(x2, [[0, 0], [1, 1], [1, 1], [0, 0]], "REFLECT"), wf)
+    assert np.abs(lit - fused).max() < 1e-12
+
+
+def test_tf_conventions_hand_computed():
+    # SAME padding, stride 2: in 5, k 3 -> out 3, total pad 2 -> (1, 1); in 6 -> out 3, total 1
+    # -> (0, 1) (the odd element goes AFTER)
+    assert L.same_pads(5, 3, 2) == (1, 1) and L.same_pads(6, 3, 2) == (0, 1)
+    assert L.same_pads(7, 3, 1) == (1, 1)
+    # depth_to_space DCR: out[h*r+i, w*r+j, c] = in[h, w, (i*r+j)*C' + c]
+    x = np.arange(8, dtype=np.float32).reshape(1, 1, 1, 8)
+    y = L.depth_to_space(x, 2)
+    assert y.shape == (1, 2, 2, 2)
+    assert y[0, 0, 0].tolist() == [0, 1] and y[0, 0, 1].tolist() == [2, 3]
+    assert y[0, 1, 0].tolist() == [4, 5] and y[0, 1, 1].tolist() == [6, 7]
+    # depth_to_time = row-major reshape then roll
+    x = np.arange(12, dtype=np.float32).reshape(1, 1, 1, 2, 6)
+    y = L.spatiotemporal_expansion(x, 1, 3, "depth_to_time", 1)
+    assert y.shape == (1, 1, 1, 6, 2)
+    assert y[0, 0, 0, :, 0].tolist() == [10, 0, 2, 4, 6, 8]
+    # REFLECT excludes the edge, SYMMETRIC repeats it
+    a = np.arange(4.0).reshape(1, 4, 1)
+    assert L.tf_pad(a, [[0, 0], [2, 1], [0, 0]], "REFLECT")[0, :, 0].tolist() == [2, 1, 0, 1, 2, 3, 2]
+    assert L.tf_pad(a, [[0, 0], [2, 1], [0, 0]], "SYMMETRIC")[0, :, 0].tolist() == [1, 0, 0, 1, 2, 3, 3]
+    with pytest.raises(ValueError):
+        L.tf_pad(a, [[0, 0], [4, 0], [0, 0]], "REFLECT")
+
+
+def test_skip_connection_cache_semantics():
+    s = L.SkipConnection("a")
+    x = np.ones((1, 2, 2, 1))
+    assert s(x) is x
+    assert np.all(s(2 * x) == 3)
+    assert s(x) is x  # cache cleared after the add
+
+
+def test_loss_identities():
+    """LowResLoss-style identity of tests/utilities/test_loss_metrics.py:174-260 on the numpy
+    side: coarsening then MSE equals MSE of coarsened tensors; relativistic loss symmetric."""
+    from oracle.torch_ref import disc_loss
+    from sup3r_b200.utilities import spatial_coarsening, temporal_coarsening
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((2, 8, 8, 6, 2)), rng.standard_normal((2, 8, 8, 6, 2))
+    ca = temporal_coarsening(spatial_coarsening(a, 2), 3, "average")
+    cb = temporal_coarsening(spatial_coarsening(b, 2), 3, "average")
+    assert ca.shape == (2, 4, 4, 2, 2)
+    assert np.isclose(((ca - cb) ** 2).mean(),
+                      ((temporal_coarsening(spatial_coarsening(a - b, 2), 3, "average")) ** 2).mean())
+    t, g = torch.randn(5, 1), torch.randn(5, 1)
+    assert disc_loss(t, g) > 0
+    c = torch.full((5, 1), 0.7)
+    assert torch.isclose(disc_loss(c, c), torch.log(torch.tensor(2.0)))
