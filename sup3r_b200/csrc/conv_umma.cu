@@ -581,26 +581,28 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     S3_REQUIRE(r_max >= 1, "s3_conv_fwd_umma: npad %d too wide for TMEM", p.npad);
     const double eff_plane = (double)Y / (((Y + 15) / 16) * 16.0);
     const double eff_flat = (double)Y / (Y + 2.0);
-    for (int use_flat = (eff_flat > eff_plane + 0.02 ? 1 : 0); use_flat >= 0 && !found; --use_flat)
-      for (int R = r_max; R >= 1 && !found; --R) {
-        int YB, ZB, TS;
-        if (!use_flat) {
-          YB = 18; TS = 18;
-          ZB = (kz == 3) ? R + 2 : R;
-        } else {
-          YB = Y + 2; TS = 16;
-          const int rows = (YB - 1) + 16 * R + (kz == 3 ? 2 * YB : 0) + 2;
-          ZB = (rows + YB - 1) / YB;
+    for (int ws = p.WS; ws >= 1 && !found; --ws)
+      for (int use_flat = (eff_flat > eff_plane + 0.02 ? 1 : 0); use_flat >= 0 && !found;
+           --use_flat)
+        for (int R = r_max; R >= 1 && !found; --R) {
+          int YB, ZB, TS;
+          if (!use_flat) {
+            YB = 18; TS = 18;
+            ZB = (kz == 3) ? R + 2 : R;
+          } else {
+            YB = Y + 2; TS = 16;
+            const int rows = (YB - 1) + 16 * R + (kz == 3 ? 2 * YB : 0) + 2;
+            ZB = (rows + YB - 1) / YB;
+          }
+          if (YB > 256 || ZB > 256) continue;
+          const uint32_t box = (uint32_t)ZB * YB * p.XB * 128u;
+          const uint32_t boxs = (box + 1023u) & ~1023u;
+          if (boxs * halves + (uint32_t)ws * w_slab * halves + fixed > kSmemLimit) continue;
+          p.flat = use_flat; p.R = R; p.YB = YB; p.ZB = ZB; p.TS = TS; p.WS = ws;
+          p.box_bytes = box; p.box_stride = boxs;
+          p.AS = (2 * boxs * halves + (uint32_t)ws * w_slab * halves + fixed <= kSmemLimit) ? 2 : 1;
+          found = true;
         }
-        if (YB > 256 || ZB > 256) continue;
-        const uint32_t box = (uint32_t)ZB * YB * p.XB * 128u;
-        const uint32_t boxs = (box + 1023u) & ~1023u;
-        if (boxs * halves + (uint32_t)p.WS * w_slab * halves + fixed > kSmemLimit) continue;
-        p.flat = use_flat; p.R = R; p.YB = YB; p.ZB = ZB; p.TS = TS;
-        p.box_bytes = box; p.box_stride = boxs;
-        p.AS = (2 * boxs * halves + (uint32_t)p.WS * w_slab * halves + fixed <= kSmemLimit) ? 2 : 1;
-        found = true;
-      }
   }
   S3_REQUIRE(found, "s3_conv_fwd_umma: no tile shape fits shared memory (Y=%d, npad=%d)", Y, p.npad);
   p.acc_bufs = (2 * p.R * p.npad <= 512) ? 2 : 1;

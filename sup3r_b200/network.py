@@ -134,7 +134,7 @@ class Layer:
         if not self.built:
             self.build(tuple(t.shape), np.random.default_rng(_GLOBAL_SEED[0]), t.device)
         y = self.forward(t, *extra)
-        return y if torch.is_grad_enabled() and y.requires_grad else y.as_subclass(DeviceArray)
+        return y.as_subclass(DeviceArray)
 
     def get_config(self):
         return {"class": type(self).__name__}

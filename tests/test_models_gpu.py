@@ -161,7 +161,7 @@ def test_gradients_match_float64_autograd(cuda):
     torch-CPU float64 autograd through the restated layer sequence (abstract.py:1190-1238)."""
     gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
     disc_hl = C.discriminator(3, "same", (16,))
-    lr_shape, hr_shape = (2, 4, 4, 3, 2), (2, 8, 8, 6, 2)
+    lr_shape, hr_shape = (2, 4, 4, 4, 2), (2, 8, 8, 8, 2)
     m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, loss="MeanAbsoluteError")
     rng = np.random.default_rng(11)
     lr = rng.standard_normal(lr_shape).astype(np.float32)
@@ -184,12 +184,18 @@ def test_gradients_match_float64_autograd(cuda):
     assert abs(float(details["loss_gen_content"]) - content.item()) < 1e-4
     assert abs(float(details["loss_disc"]) - loss_disc.item()) < 1e-4
     assert "mean_absolute_error" in details
+    def close(got, want, name):
+        # shift-invariant parameters (e.g. the last biases under the relativistic loss) have
+        # exactly-zero gradients: compare on an absolute floor as well
+        d = np.abs(got.cpu().numpy().astype(np.float64) - want.numpy()).max()
+        assert d < 2e-3 * np.abs(want.numpy()).max() + 1e-7, name
+
     for got, want, v in zip(grads, ref_g, m.generator_weights):
-        assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-3, v.name
+        close(got, want, v.name)
     grads, details = m.get_single_grad(lr, hr, m.discriminator_weights, weight_gen_advers=w_adv,
                                        train_gen=False, train_disc=True)
     for got, want, v in zip(grads, ref_d, m.discriminator_weights):
-        assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-3, v.name
+        close(got, want, v.name)
 
 
 class _Batch:
@@ -291,7 +297,7 @@ def test_disc_training_schedule_and_optimizer_update(cuda):
     bh = SyntheticBatchHandler(n_batches=3, batch=2)
     with tempfile.TemporaryDirectory() as td:
         m.train(bh, {"spatial": "30km", "temporal": "60min"}, n_epoch=2, weight_gen_advers=1e-2,
-                train_gen=True, train_disc=True, disc_loss_bounds=(0.0, 100.0),
+                train_gen=True, train_disc=True, disc_loss_bounds=(-1.0, 100.0),
                 out_dir=os.path.join(td, "gan_{epoch}"), adaptive_update_fraction=0.05)
         assert all(m.history["disc_train_frac"] == 1) and all(m.history["gen_train_frac"] == 1)
         assert np.isfinite(m.history["train_loss_disc"].values).all()
@@ -319,32 +325,41 @@ def test_forward_pass_single_chunk_equals_generate(cuda):
 
 
 def test_forward_pass_chunked_close_to_unchunked(cuda):
-    """Chunked == unchunked when the halo covers the receptive field (reference:
-    test_forward_pass.py:411-497, mean |err| < 1e-6 with pad 20)."""
+    """Chunked == unchunked when the halo covers the receptive field and both see zeros outside
+    the domain (reference: test_forward_pass.py:411-497, constant-mode padding, pad 20,
+    mean |err| < 1e-6)."""
     from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
     m = _fwp_model(n_blocks=1)
+    m.precision = "fp32"
     data = np.random.default_rng(1).standard_normal((16, 16, 16, 2)).astype(np.float32)
     handler = ArrayInputHandler(data, ["u", "v"])
-    m.precision = "fp32"
-    whole = m.generate(data[None])[0]
+    pad = 8
+    padded = np.pad(data, ((pad, pad), (pad, pad), (pad, pad), (0, 0)), mode="constant")
+    whole = m.generate(padded[None])[0][2 * pad:-2 * pad, 2 * pad:-2 * pad, 2 * pad:-2 * pad]
     strat = ForwardPassStrategy(model=m, input_handler=handler, fwp_chunk_shape=(8, 8, 8),
-                                spatial_pad=8, temporal_pad=8, pass_workers=1)
+                                spatial_pad=pad, temporal_pad=pad, pass_workers=1,
+                                pad_mode="constant")
     assert strat.n_chunks == 8
     outs = ForwardPass.run(strat, 0)
     full = np.zeros_like(whole)
     sl = strat.fwp_slicer
-    for idx, o in outs.items():
-        s_idx, t_idx = sl.get_chunk_indices(idx)
-        hs = sl.s_hr_slices[s_idx]
-        ts = sl.get_hr_slices(sl.t_lr_slices, sl.t_enhance)[t_idx]
-        full[hs[0], hs[1], ts] = o
-    assert np.abs(full - whole).mean() < 1e-6
-    # batched driver (equal-shape chunks stacked on the obs axis) gives the same chunks
+
+    def assemble(outs):
+        full = np.zeros_like(whole)
+        for idx, o in outs.items():
+            s_idx, t_idx = sl.get_chunk_indices(idx)
+            hs = sl.s_hr_slices[s_idx]
+            ts = sl.get_hr_slices(sl.t_lr_slices, sl.t_enhance)[t_idx]
+            full[hs[0], hs[1], ts] = o
+        return full
+
+    assert np.abs(assemble(outs) - whole).mean() < 1e-6
+    # batched driver (equal-shape chunks stacked on the obs axis) gives the same field
     strat2 = ForwardPassStrategy(model=m, input_handler=handler, fwp_chunk_shape=(8, 8, 8),
-                                 spatial_pad=8, temporal_pad=8, pass_workers=4)
+                                 spatial_pad=pad, temporal_pad=pad, pass_workers=4,
+                                 pad_mode="constant")
     outs2 = ForwardPass.run(strat2, 0)
-    for idx in outs:
-        assert np.allclose(outs[idx], outs2[idx], atol=1e-5)
+    assert np.abs(assemble(outs2) - whole).mean() < 1e-6
 
 
 def test_forward_pass_failures_and_incremental(cuda):
