@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::s3::cuda_fail(e__, #expr);        \
   } while (0)
 
-#define S3_LAUNCH_CHECK(name) S3_CUDA(cudaPeekAtLastError())
+#define S3_LAUNCH_CHECK(name) S3_CUDA(cudaGetLastError())
 
 inline cudaStream_t as_stream(s3_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();

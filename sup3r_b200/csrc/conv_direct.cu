@@ -268,6 +268,8 @@ conv_wgrad_kernel(const ConvGeom g, const float* __restrict__ x, const float* __
 }
 
 int launch_colsum(const float* x, long long rows, int cols, float* out, cudaStream_t st);
+int try_conv_small(const ConvGeom& g, const float* x, const float* w, const Epilogue& ep,
+                   cudaStream_t st);
 
 }  // namespace s3
 
@@ -286,6 +288,9 @@ extern "C" int s3_conv_fwd_f32(const s3_conv_desc* d, const float* x, const floa
   Epilogue ep{bias, residual, post_scale, post_shift, y, y_hi, y_lo, 0};
   const long long M = (long long)g.n * g.od[0] * g.od[1] * g.od[2];
   cudaStream_t st = as_stream(stream);
+  const int small = try_conv_small(g, x, w, ep, st);
+  if (small < 0) return small;
+  if (small == 1) return S3_OK;
   if (g.cout > 16) {
     dim3 grid((unsigned)((M + 127) / 128), (g.cout + 63) / 64);
     conv_direct_kernel<128, 64, 8, 8, 4, MODE_FWD><<<grid, 256, 0, st>>>(g, x, w, ep, nullptr);

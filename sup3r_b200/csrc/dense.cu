@@ -103,7 +103,7 @@ int launch_colsum(const float* x, long long rows, int cols, float* out, cudaStre
   if (bx > cap) bx = cap;
   dim3 grid((unsigned)bx, (cols + 31) / 32);
   colsum_kernel<<<grid, 256, 0, st>>>(x, rows, cols, out);
-  S3_CUDA(cudaPeekAtLastError());
+  S3_CUDA(cudaGetLastError());
   return S3_OK;
 }
 
@@ -122,7 +122,7 @@ static int launch_gemm(const float* A, const float* B, float* C, int M, int N, i
   dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
   sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, kps,
                                                       splits > 1 ? 1 : 0);
-  S3_CUDA(cudaPeekAtLastError());
+  S3_CUDA(cudaGetLastError());
   return S3_OK;
 }
 

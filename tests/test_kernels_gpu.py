@@ -86,6 +86,30 @@ def test_fused_reflect_conv_equals_pad_conv_crop(cuda, ndim, shape, cout):
     assert rel_err(y, ref) < TOL
 
 
+@pytest.mark.parametrize("cin,cout,shape,mode", [(8, 4, (1, 9, 13, 70), 1), (4, 2, (2, 4, 8, 32), 1),
+                                                 (12, 6, (1, 5, 9, 33), 0), (3, 1, (1, 6, 6, 6), 1),
+                                                 (32, 2, (1, 4, 8, 40), 1), (18, 14, (1, 4, 5, 6), 1)])
+def test_small_channel_conv_matches_oracle(cuda, cin, cout, shape, mode):
+    """The narrow-layer kernel (conv_small.cu) incl. tile-edge masking, residual and affine;
+    (18 -> 14 falls back to the generic kernel)."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(21)
+    x = rng_arr(rng, shape + (cin,))
+    w = rng_arr(rng, (3, 3, 3, cin, cout), 0.1)
+    b = rng_arr(rng, (cout,), 0.1)
+    res = rng_arr(rng, shape + (cout,))
+    sc, sh = rng_arr(rng, (cout,)), rng_arr(rng, (cout,))
+    pads = [[0, 0]] + [[1, 1]] * 3 + [[0, 0]]
+    xp = L.tf_pad(x.astype(np.float64), pads, "REFLECT" if mode == 1 else "CONSTANT")
+    ref = L.conv_nd(xp, w.astype(np.float64), b.astype(np.float64))
+    ref = (np.where(ref >= 0, ref, 0.2 * ref) + res) * sc + sh
+    spec = ops.ConvSpec(3, cin, cout, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=mode,
+                        act=2, alpha=0.2)
+    y = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec, residual=dev(res, cuda),
+                     post_scale=dev(sc, cuda), post_shift=dev(sh, cuda)).cpu().numpy()
+    assert y.shape == ref.shape and rel_err(y, ref) < TOL
+
+
 def test_conv_transpose_as_flipped_conv(cuda):
     """Conv2DTranspose(valid, stride 1) == zero-pad-2 conv with the flipped, swapped kernel."""
     from sup3r_b200 import ops
