@@ -82,6 +82,7 @@ typedef struct s3_umma_tuning {
   int32_t box_y;            /* smem y extent of one activation plane (zcat kernel; >= 18) */
   int32_t max_ctas;         /* 0 = SM count */
   int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
+  void* trace;              /* optional device buffer of 16 int64: role timings of CTA 0 */
 } s3_umma_tuning;
 
 int s3_init(int device);

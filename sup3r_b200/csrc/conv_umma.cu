@@ -4,435 +4,15 @@
 // [-> LeakyReLU] [-> SpatioTemporalExpansion] [-> SkipConnection add]  layer runs
 // (sup3r/configs/spatiotemporal/gen_*.json, executed by sup3r/models/abstract.py:1081-1092).
 //
-// Data layout in HBM
-//   activations : 16-bit (bf16 | fp16), channels-last, padded by one voxel on every convolved
-//                 dim with the REFLECT halo already materialised by the producing kernel:
-//                 [planes][Y+2][X+2][64], planes = N*(Z+2) (3-D) or N (2-D).  One voxel = 128 B
-//                 = one SWIZZLE_128B row, so any (dz,dy,dx)-shifted window of a smem-resident
-//                 box is a legal K-major UMMA operand: 8 consecutive x voxels form a core
-//                 group, consecutive y rows are SBO = box_x*128 B apart.
-//   weights     : [taps][Npad][64] 16-bit (Cout rows, Cin contiguous), Npad = Cout up to x16.
-//   split mode  : activations and weights also carry a "lo" tensor (x - bf16(x)); the kernel
-//                 accumulates hi*hi + lo*hi + hi*lo in fp32 (~16 mantissa bits).
-//
-// Kernel (persistent, one CTA per SM, 192 threads)
-//   warp 0   : TMA producer  - one 4-D box load of the activation halo box per work item,
-//              one 3-D load of the [Npad][64] weight slab per tap through a WS-deep ring
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=Npad, K=16);
-//              R output tiles (128 voxels each) share every weight slab -> weight traffic / R
-//   warps 2-5: epilogue - tcgen05.ld accumulators, bias / activation / residual / affine,
-//              scatter (depth_to_space, nearest repeat, ...) to fp32 and/or the next layer's
-//              16-bit padded+mirrored tensor.  Accumulators are double buffered in TMEM so
-//              the epilogue of item i overlaps the MMAs of item i+1.
-#include <cuda.h>
-
+// This file: host side (work-item shape selection, TMA descriptors, kernel choice).  Kernels:
+// conv_umma_zcat.cu (narrow 3-D outputs) and conv_umma_tile.cu (wide / 2-D / split precision);
+// data layouts are described in conv_umma_common.cuh and DESIGN.md section 3.
 #include <cstring>
 
-#include "common.cuh"
-#include "ptx.cuh"
-#include "umma_epilogue.cuh"
+#include "conv_umma_common.cuh"
 
 namespace s3 {
 
-struct UmmaParams {
-  ConvGeom g;
-  Epilogue ep;
-  int kz, ntaps, npad, split, fmt;
-  int R, TS, XB, YB, ZB, WS, AS, acc_bufs;
-  int flat;           // 0: plane mode (16-row y blocks), 1: flat mode (full padded height)
-  int nxb, nyb;       // x blocks of 8, y blocks of 16 (plane mode)
-  int groups_per_b;   // plane groups (plane mode) / flat items (flat mode) per batch entry
-  int nb;             // batch entries looped as separate tensors (3-D: n; 2-D: 1)
-  int planes;         // output planes per batch entry (3-D: Z; 2-D: N)
-  int plane_pitch;    // padded planes per batch entry (3-D: Z+2; 2-D: 0)
-  int n_items;
-  uint32_t box_bytes, box_stride, w_bytes;  // per operand half (stride = 1 KiB aligned)
-  uint32_t idesc;
-  DebugRec* dbg;
-};
-
-struct ItemCoord {
-  int xb, y0, b, pl0, row0;
-};
-
-__device__ __forceinline__ ItemCoord decode_item(const UmmaParams& p, int item) {
-  ItemCoord c;
-  c.xb = item % p.nxb;
-  int rest = item / p.nxb;
-  if (!p.flat) {
-    int yb = rest % p.nyb;
-    int pg = rest / p.nyb;
-    c.b = pg / p.groups_per_b;
-    c.pl0 = (pg % p.groups_per_b) * p.R;
-    c.y0 = yb * 16;
-    c.row0 = 0;
-  } else {
-    c.b = rest / p.groups_per_b;
-    int f0 = (rest % p.groups_per_b) * p.R * 16;
-    c.pl0 = f0 / p.YB;
-    c.row0 = f0 % p.YB;
-    c.y0 = 0;
-  }
-  return c;
-}
-
-constexpr int kThreads = 192;
-constexpr int kMaxWS = 8;
-constexpr int kMaxPlanes = 10;
-
-// barrier slot indices (8 B each) inside the barrier block
-constexpr int B_AFULL = 0;                        // [2 stages][kMaxPlanes]
-constexpr int B_AEMPTY = B_AFULL + 2 * kMaxPlanes;
-constexpr int B_WFULL = B_AEMPTY + 2 * kMaxPlanes;
-constexpr int B_WEMPTY = B_WFULL + kMaxWS;
-constexpr int B_ACCFULL = B_WEMPTY + kMaxWS;
-constexpr int B_ACCEMPTY = B_ACCFULL + 2;
-constexpr int B_TMEMPTR = B_ACCEMPTY + 2;
-constexpr int B_COUNT = B_TMEMPTR + 1;
-static_assert(B_COUNT * 8 <= 1024, "barrier block overflows its 1 KiB");
-
-struct SmemMap {
-  uint32_t a_base, w_base, bar_base, a_stage_bytes, w_slab, w_stage_bytes;
-  float* sbias;  // [npad] bias staged in shared memory (1 KiB after the barrier block)
-};
-
-__device__ __forceinline__ SmemMap carve(const UmmaParams& p, const uint8_t* smem_raw) {
-  SmemMap m;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int halves = p.split ? 2 : 1;
-  m.a_stage_bytes = p.box_stride * halves;
-  m.w_slab = (p.w_bytes + 1023u) & ~1023u;
-  m.w_stage_bytes = m.w_slab * halves;
-  m.a_base = base;
-  m.w_base = m.a_base + m.a_stage_bytes * p.AS;
-  m.bar_base = m.w_base + m.w_stage_bytes * p.WS;
-  m.sbias = reinterpret_cast<float*>(const_cast<uint8_t*>(smem_raw) +
-                                     (m.bar_base + 1024u - smem_u32(smem_raw)));
-  return m;
-}
-
-__device__ __forceinline__ uint32_t setup_cta(const UmmaParams& p, const SmemMap& m,
-                                              const CUtensorMap* a_hi, const CUtensorMap* a_lo,
-                                              const CUtensorMap* w_hi, const CUtensorMap* w_lo) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * kMaxPlanes; ++i) {
-      mbar_init(m.bar_base + 8u * (B_AFULL + i), 1);
-      mbar_init(m.bar_base + 8u * (B_AEMPTY + i), 1);
-    }
-    for (int i = 0; i < kMaxWS; ++i) {
-      mbar_init(m.bar_base + 8u * (B_WFULL + i), 1);
-      mbar_init(m.bar_base + 8u * (B_WEMPTY + i), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(m.bar_base + 8u * (B_ACCFULL + i), 1);
-      mbar_init(m.bar_base + 8u * (B_ACCEMPTY + i), 4);
-    }
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < p.npad; i += blockDim.x)
-    m.sbias[i] = (p.ep.bias && i < p.g.cout) ? p.ep.bias[i] : 0.f;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(a_hi);
-    tma_prefetch_desc(w_hi);
-    if (p.split) {
-      tma_prefetch_desc(a_lo);
-      tma_prefetch_desc(w_lo);
-    }
-  }
-  if (warp == 1) {
-    tmem_alloc(m.bar_base + 8u * B_TMEMPTR, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(m.bar_base + 8u * B_TMEMPTR));
-  return tmem_base;
-}
-
-// One accumulator tile (128 voxels of one plane / flat row range) through the lean epilogue.
-__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const SmemMap& sm,
-                                              const ItemCoord& c, int fr0, uint32_t t_addr,
-                                              int warp, int lane) {
-  const ConvGeom& g = p.g;
-  const int q = warp & 3;
-  const int mrow = q * 32 + lane;
-  const int grp = mrow >> 3, xl = mrow & 7;
-  const int fr = fr0 + grp;
-  const int zq = fr / p.YB, yq = fr - zq * p.YB;
-  const int plane = c.pl0 + zq;
-  RowPlan rp;
-  rp.y = c.y0 + yq;
-  rp.x = c.xb * 8 + xl;
-  rp.valid = yq <= p.YB - 3 && rp.y < g.in[1] && rp.x < g.in[2] && plane < p.planes;
-  if (g.ndim == 3) { rp.b = c.b; rp.z = plane; } else { rp.b = plane; rp.z = 0; }
-  rp.conv_vox = (((size_t)rp.b * g.in[0] + rp.z) * g.in[1] + rp.y) * g.in[2] + rp.x;
-  plan_plain(g, p.ep, rp);
-  if (g.cout <= 64)
-    epilogue_row<true>(g, p.ep, sm.sbias, t_addr + ((uint32_t)(q * 32) << 16), rp);
-  else
-    epilogue_row<false>(g, p.ep, sm.sbias, t_addr + ((uint32_t)(q * 32) << 16), rp);
-}
-
-// ============================================================================ kernel "tile"
-// Every output tile accumulates all taps itself (N = npad).  Used for 2-D convolutions and
-// for wide outputs (npad > 80) where one MMA already has N >= 128.
-__global__ void __launch_bounds__(kThreads, 1)
-conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
-                      const __grid_constant__ CUtensorMap tm_a_lo,
-                      const __grid_constant__ CUtensorMap tm_w_hi,
-                      const __grid_constant__ CUtensorMap tm_w_lo, const UmmaParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemMap sm = carve(p, smem_raw);
-  auto bar = [&](int i) { return sm.bar_base + 8u * i; };
-  const int halves = p.split ? 2 : 1;
-  const uint32_t a_tx_bytes = p.box_bytes * halves;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup_cta(p, sm, &tm_a_hi, &tm_a_lo, &tm_w_hi, &tm_w_lo);
-
-  if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer (warp-uniform)
-    int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const ItemCoord c = decode_item(p, item);
-      mbar_wait(bar(B_AEMPTY + as), aph ^ 1, p.dbg, 1, as, it);
-      if (elect_one()) {
-        mbar_expect_tx(bar(B_AFULL + as), a_tx_bytes);
-        const int plane = c.b * p.plane_pitch + c.pl0;
-        tma_load_4d(sm.a_base + as * sm.a_stage_bytes, &tm_a_hi, bar(B_AFULL + as), 0, c.xb * 8,
-                    c.y0, plane);
-        if (p.split)
-          tma_load_4d(sm.a_base + as * sm.a_stage_bytes + p.box_stride, &tm_a_lo,
-                      bar(B_AFULL + as), 0, c.xb * 8, c.y0, plane);
-      }
-      __syncwarp();
-      if (++as == p.AS) { as = 0; aph ^= 1; }
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        mbar_wait(bar(B_WEMPTY + ws), wph ^ 1, p.dbg, 2, ws, it * 100 + tap);
-        if (elect_one()) {
-          mbar_expect_tx(bar(B_WFULL + ws), p.w_bytes * halves);
-          tma_load_3d(sm.w_base + ws * sm.w_stage_bytes, &tm_w_hi, bar(B_WFULL + ws), 0, 0, tap);
-          if (p.split)
-            tma_load_3d(sm.w_base + ws * sm.w_stage_bytes + sm.w_slab, &tm_w_lo,
-                        bar(B_WFULL + ws), 0, 0, tap);
-        }
-        __syncwarp();
-        if (++ws == p.WS) { ws = 0; wph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (warp-uniform, elected issue)
-    int as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0, it = 0;
-    const uint32_t hi_a = sdesc_hi_sw128((uint32_t)p.XB * 128u);
-    const uint32_t hi_b = sdesc_hi_sw128(1024u);
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const ItemCoord c = decode_item(p, item);
-      mbar_wait(bar(B_ACCEMPTY + ab), abph ^ 1, p.dbg, 3, ab, it);
-      mbar_wait(bar(B_AFULL + as), aph, p.dbg, 4, as, it);
-      tc_fence_after();
-      const uint32_t a_hi = sm.a_base + as * sm.a_stage_bytes;
-      const uint32_t d_base = tmem_base + (uint32_t)(ab * p.R * p.npad);
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int dx = tap % 3, dy = (tap / 3) % 3, dz = tap / 9;
-        mbar_wait(bar(B_WFULL + ws), wph, p.dbg, 5, ws, it * 100 + tap);
-        tc_fence_after();
-        const uint32_t wl = sdesc_lo(sm.w_base + ws * sm.w_stage_bytes);
-        const uint32_t wl_lo = sdesc_lo(sm.w_base + ws * sm.w_stage_bytes + sm.w_slab);
-        if (elect_one()) {
-          for (int r = 0; r < p.R; ++r) {
-            const uint32_t row = (uint32_t)(c.row0 + r * p.TS + dz * p.YB + dy);
-            const uint32_t al = sdesc_lo(a_hi + (row * p.XB + dx) * 128u);
-            const uint32_t al_lo = sdesc_lo(a_hi + p.box_stride + (row * p.XB + dx) * 128u);
-            const uint32_t d_addr = d_base + (uint32_t)(r * p.npad);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = mk_desc(al + 2u * kk, hi_a);
-              const uint64_t db = mk_desc(wl + 2u * kk, hi_b);
-              if (tap == 0 && kk == 0) umma_f16_new(d_addr, da, db, p.idesc);
-              else umma_f16_acc(d_addr, da, db, p.idesc);
-              if (p.split) {
-                umma_f16_acc(d_addr, mk_desc(al_lo + 2u * kk, hi_a), db, p.idesc);
-                umma_f16_acc(d_addr, da, mk_desc(wl_lo + 2u * kk, hi_b), p.idesc);
-              }
-            }
-          }
-          umma_commit(bar(B_WEMPTY + ws));
-          if (tap == p.ntaps - 1) {
-            umma_commit(bar(B_AEMPTY + as));
-            umma_commit(bar(B_ACCFULL + ab));
-          }
-        }
-        __syncwarp();
-        if (++ws == p.WS) { ws = 0; wph ^= 1; }
-      }
-      if (++as == p.AS) { as = 0; aph ^= 1; }
-      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
-    }
-  } else {
-    int ab = 0, abph = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const ItemCoord c = decode_item(p, item);
-      mbar_wait(bar(B_ACCFULL + ab), abph, p.dbg, 6, ab, it);
-      tc_fence_after();
-      for (int r = 0; r < p.R; ++r)
-        epilogue_tile(p, sm, c, c.row0 + r * p.TS, tmem_base + (uint32_t)((ab * p.R + r) * p.npad),
-                      warp, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + ab));
-      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-// ============================================================================ kernel "zcat"
-// 3-D convolutions with a narrow output (3*npad <= 256).  An SS-mode tcgen05.mma with M = 128
-// costs max(64, N/2) cycles (measured on B200: the A operand streams from shared memory at
-// 64 B/cycle), so N = 64 would cap the tensor pipe at 50 %.  Here the weight slab of one
-// (dy, dx) holds the three dz taps stacked along N ([3*npad][64]); one MMA on INPUT plane ip
-// then feeds three OUTPUT planes at once: block j of the result belongs to output plane
-// ip - j.  The accumulators of an item's R output planes sit at descending TMEM columns so the
-// three blocks land in consecutive columns: col(O_r) = base + npad * (R - 1 - r).
-// Loop order: (dy, dx) slab outer (each slab is fetched once per item), input planes inner.
-__global__ void __launch_bounds__(kThreads, 1)
-conv_umma_zcat_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
-                      const __grid_constant__ CUtensorMap tm_a_lo,
-                      const __grid_constant__ CUtensorMap tm_w_hi,
-                      const __grid_constant__ CUtensorMap tm_w_lo, const UmmaParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemMap sm = carve(p, smem_raw);
-  auto bar = [&](int i) { return sm.bar_base + 8u * i; };
-  const int halves = p.split ? 2 : 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup_cta(p, sm, &tm_a_hi, &tm_a_lo, &tm_w_hi, &tm_w_lo);
-  const int NP = p.ZB;                                   // input planes per item (R + 2)
-  const uint32_t plane_bytes = (uint32_t)p.YB * p.XB * 128u;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer (warp-uniform)
-    int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
-    auto load_slab = [&](int s) {
-      mbar_wait(bar(B_WEMPTY + ws), wph ^ 1, p.dbg, 2, ws, it * 100 + s);
-      if (elect_one()) {
-        mbar_expect_tx(bar(B_WFULL + ws), p.w_bytes * halves);
-        tma_load_3d(sm.w_base + ws * sm.w_stage_bytes, &tm_w_hi, bar(B_WFULL + ws), 0, 0, s);
-        if (p.split)
-          tma_load_3d(sm.w_base + ws * sm.w_stage_bytes + sm.w_slab, &tm_w_lo, bar(B_WFULL + ws),
-                      0, 0, s);
-      }
-      __syncwarp();
-      if (++ws == p.WS) { ws = 0; wph ^= 1; }
-    };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const ItemCoord c = decode_item(p, item);
-      load_slab(0);
-      const int plane0 = c.b * p.plane_pitch + c.pl0;
-      for (int ip = 0; ip < NP; ++ip) {
-        const int bi = as * kMaxPlanes + ip;
-        mbar_wait(bar(B_AEMPTY + bi), aph ^ 1, p.dbg, 1, bi, it);
-        if (elect_one()) {
-          mbar_expect_tx(bar(B_AFULL + bi), plane_bytes * halves);
-          const uint32_t dst = sm.a_base + as * sm.a_stage_bytes + ip * plane_bytes;
-          tma_load_4d(dst, &tm_a_hi, bar(B_AFULL + bi), 0, c.xb * 8, c.y0, plane0 + ip);
-          if (p.split)
-            tma_load_4d(dst + p.box_stride, &tm_a_lo, bar(B_AFULL + bi), 0, c.xb * 8, c.y0,
-                        plane0 + ip);
-        }
-        __syncwarp();
-      }
-      if (++as == p.AS) { as = 0; aph ^= 1; }
-      for (int s = 1; s < 9; ++s) load_slab(s);
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (warp-uniform, elected issue)
-    int as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0, it = 0;
-    const int R = p.R, npad = p.npad;
-    const uint32_t fmtb = p.fmt == 0 ? 1u : 0u;
-    const uint32_t hi_a = sdesc_hi_sw128((uint32_t)p.XB * 128u);
-    const uint32_t hi_b = sdesc_hi_sw128(1024u);
-    const uint32_t id1 = make_idesc_f16((uint32_t)npad, fmtb);
-    const uint32_t id2 = make_idesc_f16((uint32_t)(2 * npad), fmtb);
-    const uint32_t id3 = make_idesc_f16((uint32_t)(3 * npad), fmtb);
-    const uint32_t blk_lo = ((uint32_t)npad * 128u) >> 4;   // one weight block in desc units
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      mbar_wait(bar(B_ACCEMPTY + ab), abph ^ 1, p.dbg, 3, ab, it);
-      tc_fence_after();
-      const uint32_t a_stage = sm.a_base + as * sm.a_stage_bytes;
-      const uint32_t acc0 = tmem_base + (uint32_t)(ab * R * npad);
-      for (int s = 0; s < 9; ++s) {
-        const int dy = s / 3, dx = s - 3 * dy;
-        mbar_wait(bar(B_WFULL + ws), wph, p.dbg, 5, ws, it * 100 + s);
-        tc_fence_after();
-        const uint32_t wl = sdesc_lo(sm.w_base + ws * sm.w_stage_bytes);
-        const uint32_t al0 = sdesc_lo(a_stage + ((uint32_t)(dy * p.XB + dx)) * 128u);
-        for (int ip = 0; ip < NP; ++ip) {
-          if (s == 0) {
-            mbar_wait(bar(B_AFULL + as * kMaxPlanes + ip), aph, p.dbg, 4, ip, it);
-            tc_fence_after();
-          }
-          const int jlo = ip - (R - 1) > 0 ? ip - (R - 1) : 0;
-          const int jhi = ip < 2 ? ip : 2;
-          const int nblk = jhi - jlo + 1;
-          const uint32_t dcol = acc0 + (uint32_t)(npad * (R - 1 - (ip - jlo)));
-          const uint32_t al = al0 + ((ip * plane_bytes) >> 4);
-          const uint32_t bl = wl + (uint32_t)jlo * blk_lo;
-          const uint32_t idn = nblk == 3 ? id3 : (nblk == 2 ? id2 : id1);
-          if (elect_one()) {
-            if (s == 0 && jlo == 0) {
-              // block 0 (output plane ip) starts a new accumulation; the others continue
-              umma_f16_new(dcol, mk_desc(al, hi_a), mk_desc(wl, hi_b), id1);
-              if (nblk > 1)
-                umma_f16_acc(dcol + npad, mk_desc(al, hi_a), mk_desc(wl + blk_lo, hi_b),
-                             nblk == 3 ? id2 : id1);
-#pragma unroll
-              for (int kk = 1; kk < 4; ++kk)
-                umma_f16_acc(dcol, mk_desc(al + 2u * kk, hi_a), mk_desc(bl + 2u * kk, hi_b), idn);
-            } else {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16_acc(dcol, mk_desc(al + 2u * kk, hi_a), mk_desc(bl + 2u * kk, hi_b), idn);
-            }
-            if (s == 8) umma_commit(bar(B_AEMPTY + as * kMaxPlanes + ip));
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          umma_commit(bar(B_WEMPTY + ws));
-          if (s == 8) umma_commit(bar(B_ACCFULL + ab));
-        }
-        __syncwarp();
-        if (++ws == p.WS) { ws = 0; wph ^= 1; }
-      }
-      if (++as == p.AS) { as = 0; aph ^= 1; }
-      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
-    }
-  } else {
-    int ab = 0, abph = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const ItemCoord c = decode_item(p, item);
-      mbar_wait(bar(B_ACCFULL + ab), abph, p.dbg, 6, ab, it);
-      tc_fence_after();
-      for (int r = 0; r < p.R; ++r)
-        epilogue_tile(p, sm, c, r * p.YB,
-                      tmem_base + (uint32_t)(ab * p.R * p.npad + p.npad * (p.R - 1 - r)), warp,
-                      lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + ab));
-      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -617,6 +197,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   p.idesc = make_idesc_f16((uint32_t)p.npad, (uint32_t)(t.fmt == 0 ? 1 : 0));
   p.dbg = debug_rec();
+  p.trace = reinterpret_cast<long long*>(t.trace);
 
   CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
   const uint64_t total_planes = kz == 3 ? (uint64_t)g.n * (g.in[0] + 2) : (uint64_t)g.n;
@@ -633,22 +214,27 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     if ((rc = encode_map(&tm_w_lo, w_lo, t.fmt, 3, wdims, wbox))) return rc;
   }
   const uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
-    S3_CUDA(cudaFuncSetAttribute(conv_umma_tile_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    S3_CUDA(cudaFuncSetAttribute(conv_umma_zcat_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    attr_set = true;
-  }
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
+  // epilogue specialisation: fast paths only when their preconditions hold for EVERY row
+  int epi = EPI_GENERIC;
+  const bool aligned = (g.cstride % 8 == 0) && (g.coff % 8 == 0);
+  const bool plain = g.r == 1 && g.m == 1 && g.rep[0] == 1 && g.rep[1] == 1 && g.rep[2] <= 3;
+  const bool roomy = g.fd[1] >= 4 && g.fd[2] >= 4 && (g.ndim == 2 || g.fd[0] >= 4);
+  if (plain && aligned && roomy && g.cout % 16 == 0 && !post_scale) {
+    epi = EPI_PLAIN;
+  } else if ((g.r > 1 || g.m > 1) && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !y_hi && y &&
+             (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && g.cout % g.cmap == 0 &&
+             g.cstride % 4 == 0 && g.coff % 4 == 0) {
+    epi = EPI_D2S;
+  }
   if (zcat)
-    conv_umma_zcat_kernel<<<ctas, kThreads, smem, as_stream(stream)>>>(tm_a_hi, tm_a_lo, tm_w_hi,
-                                                                       tm_w_lo, p);
+    rc = launch_umma_zcat(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
+                          as_stream(stream));
   else
-    conv_umma_tile_kernel<<<ctas, kThreads, smem, as_stream(stream)>>>(tm_a_hi, tm_a_lo, tm_w_hi,
-                                                                       tm_w_lo, p);
-  S3_LAUNCH_CHECK("conv_umma_kernel");
+    rc = launch_umma_tile(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
+                          as_stream(stream));
+  if (rc) return rc;
+
   return S3_OK;
 }

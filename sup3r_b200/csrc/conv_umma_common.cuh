@@ -1,0 +1,162 @@
+// Shared pieces of the tcgen05 convolution kernels: parameters, work-item decoding, shared
+// memory carve-up, CTA set-up and the per-tile epilogue driver.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "umma_epilogue.cuh"
+
+namespace s3 {
+
+struct UmmaParams {
+  ConvGeom g;
+  Epilogue ep;
+  int kz, ntaps, npad, split, fmt;
+  int R, TS, XB, YB, ZB, WS, AS, acc_bufs;
+  int flat;           // 0: plane mode (16-row y blocks), 1: flat mode (full padded height)
+  int nxb, nyb;       // x blocks of 8, y blocks of 16 (plane mode)
+  int groups_per_b;   // plane groups (plane mode) / flat items (flat mode) per batch entry
+  int nb;             // batch entries looped as separate tensors (3-D: n; 2-D: 1)
+  int planes;         // output planes per batch entry (3-D: Z; 2-D: N)
+  int plane_pitch;    // padded planes per batch entry (3-D: Z+2; 2-D: 0)
+  int n_items;
+  uint32_t box_bytes, box_stride, w_bytes;  // per operand half (stride = 1 KiB aligned)
+  uint32_t idesc;
+  DebugRec* dbg;
+  long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
+};
+
+struct ItemCoord {
+  int xb, y0, b, pl0, row0;
+};
+
+__device__ __forceinline__ ItemCoord decode_item(const UmmaParams& p, int item) {
+  ItemCoord c;
+  c.xb = item % p.nxb;
+  int rest = item / p.nxb;
+  if (!p.flat) {
+    int yb = rest % p.nyb;
+    int pg = rest / p.nyb;
+    c.b = pg / p.groups_per_b;
+    c.pl0 = (pg % p.groups_per_b) * p.R;
+    c.y0 = yb * 16;
+    c.row0 = 0;
+  } else {
+    c.b = rest / p.groups_per_b;
+    int f0 = (rest % p.groups_per_b) * p.R * 16;
+    c.pl0 = f0 / p.YB;
+    c.row0 = f0 % p.YB;
+    c.y0 = 0;
+  }
+  return c;
+}
+
+constexpr int kThreads = 192;
+constexpr int kMaxWS = 8;
+constexpr int kMaxPlanes = 10;
+
+// barrier slot indices (8 B each) inside the barrier block
+constexpr int B_AFULL = 0;                        // [2 stages][kMaxPlanes]
+constexpr int B_AEMPTY = B_AFULL + 2 * kMaxPlanes;
+constexpr int B_WFULL = B_AEMPTY + 2 * kMaxPlanes;
+constexpr int B_WEMPTY = B_WFULL + kMaxWS;
+constexpr int B_ACCFULL = B_WEMPTY + kMaxWS;
+constexpr int B_ACCEMPTY = B_ACCFULL + 2;
+constexpr int B_TMEMPTR = B_ACCEMPTY + 2;
+constexpr int B_COUNT = B_TMEMPTR + 1;
+static_assert(B_COUNT * 8 <= 1024, "barrier block overflows its 1 KiB");
+
+struct SmemMap {
+  uint32_t a_base, w_base, bar_base, a_stage_bytes, w_slab, w_stage_bytes;
+  float* sbias;  // [npad] bias staged in shared memory (1 KiB after the barrier block)
+};
+
+__device__ __forceinline__ SmemMap carve(const UmmaParams& p, const uint8_t* smem_raw) {
+  SmemMap m;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int halves = p.split ? 2 : 1;
+  m.a_stage_bytes = p.box_stride * halves;
+  m.w_slab = (p.w_bytes + 1023u) & ~1023u;
+  m.w_stage_bytes = m.w_slab * halves;
+  m.a_base = base;
+  m.w_base = m.a_base + m.a_stage_bytes * p.AS;
+  m.bar_base = m.w_base + m.w_stage_bytes * p.WS;
+  m.sbias = reinterpret_cast<float*>(const_cast<uint8_t*>(smem_raw) +
+                                     (m.bar_base + 1024u - smem_u32(smem_raw)));
+  return m;
+}
+
+__device__ __forceinline__ uint32_t setup_cta(const UmmaParams& p, const SmemMap& m,
+                                              const CUtensorMap* a_hi, const CUtensorMap* a_lo,
+                                              const CUtensorMap* w_hi, const CUtensorMap* w_lo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kMaxPlanes; ++i) {
+      mbar_init(m.bar_base + 8u * (B_AFULL + i), 1);
+      mbar_init(m.bar_base + 8u * (B_AEMPTY + i), 1);
+    }
+    for (int i = 0; i < kMaxWS; ++i) {
+      mbar_init(m.bar_base + 8u * (B_WFULL + i), 1);
+      mbar_init(m.bar_base + 8u * (B_WEMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(m.bar_base + 8u * (B_ACCFULL + i), 1);
+      mbar_init(m.bar_base + 8u * (B_ACCEMPTY + i), 4);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.npad; i += blockDim.x)
+    m.sbias[i] = (p.ep.bias && i < p.g.cout) ? p.ep.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(a_hi);
+    tma_prefetch_desc(w_hi);
+    if (p.split) {
+      tma_prefetch_desc(a_lo);
+      tma_prefetch_desc(w_lo);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(m.bar_base + 8u * B_TMEMPTR, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(m.bar_base + 8u * B_TMEMPTR));
+  return tmem_base;
+}
+
+// One accumulator tile (128 voxels of one plane / flat row range) through the lean epilogue.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const SmemMap& sm,
+                                              const ItemCoord& c, int fr0, uint32_t t_addr,
+                                              int warp, int lane) {
+  const ConvGeom& g = p.g;
+  const int q = warp & 3;
+  const int mrow = q * 32 + lane;
+  const int grp = mrow >> 3, xl = mrow & 7;
+  const int fr = fr0 + grp;
+  const int zq = fr / p.YB, yq = fr - zq * p.YB;
+  const int plane = c.pl0 + zq;
+  RowPlan rp;
+  rp.y = c.y0 + yq;
+  rp.x = c.xb * 8 + xl;
+  rp.valid = yq <= p.YB - 3 && rp.y < g.in[1] && rp.x < g.in[2] && plane < p.planes;
+  if (g.ndim == 3) { rp.b = c.b; rp.z = plane; } else { rp.b = plane; rp.z = 0; }
+  rp.conv_vox = (((size_t)rp.b * g.in[0] + rp.z) * g.in[1] + rp.y) * g.in[2] + rp.x;
+  if (EPI != EPI_D2S) plan_plain(g, p.ep, rp);
+  epilogue_row<EPI>(g, p.ep, sm.sbias, t_addr + ((uint32_t)(q * 32) << 16), rp);
+}
+
+
+// launchers implemented in conv_umma_zcat.cu / conv_umma_tile.cu
+int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                     const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
+                     uint32_t smem, cudaStream_t st);
+int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                     const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
+                     uint32_t smem, cudaStream_t st);
+
+}  // namespace s3

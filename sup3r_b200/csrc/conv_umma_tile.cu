@@ -1,0 +1,147 @@
+// tcgen05 convolution, "tile" scheme: every 128-voxel output tile accumulates all taps itself
+// (N = npad).  Used for wide outputs (npad > 80, e.g. the 64 -> 200 head with the fused
+// depth_to_space scatter), 2-D convolutions and the split-precision (bf16x3) mode.
+#include "conv_umma_common.cuh"
+
+namespace s3 {
+
+// ============================================================================ kernel "tile"
+// Every output tile accumulates all taps itself (N = npad).  Used for 2-D convolutions and
+// for wide outputs (npad > 80) where one MMA already has N >= 128.
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+                      const __grid_constant__ CUtensorMap tm_a_lo,
+                      const __grid_constant__ CUtensorMap tm_w_hi,
+                      const __grid_constant__ CUtensorMap tm_w_lo, const UmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemMap sm = carve(p, smem_raw);
+  auto bar = [&](int i) { return sm.bar_base + 8u * i; };
+  const int halves = p.split ? 2 : 1;
+  const uint32_t a_tx_bytes = p.box_bytes * halves;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_base = setup_cta(p, sm, &tm_a_hi, &tm_a_lo, &tm_w_hi, &tm_w_lo);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (warp-uniform)
+    int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const ItemCoord c = decode_item(p, item);
+      mbar_wait(bar(B_AEMPTY + as), aph ^ 1, p.dbg, 1, as, it);
+      if (elect_one()) {
+        mbar_expect_tx(bar(B_AFULL + as), a_tx_bytes);
+        const int plane = c.b * p.plane_pitch + c.pl0;
+        tma_load_4d(sm.a_base + as * sm.a_stage_bytes, &tm_a_hi, bar(B_AFULL + as), 0, c.xb * 8,
+                    c.y0, plane);
+        if (p.split)
+          tma_load_4d(sm.a_base + as * sm.a_stage_bytes + p.box_stride, &tm_a_lo,
+                      bar(B_AFULL + as), 0, c.xb * 8, c.y0, plane);
+      }
+      __syncwarp();
+      if (++as == p.AS) { as = 0; aph ^= 1; }
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        mbar_wait(bar(B_WEMPTY + ws), wph ^ 1, p.dbg, 2, ws, it * 100 + tap);
+        if (elect_one()) {
+          mbar_expect_tx(bar(B_WFULL + ws), p.w_bytes * halves);
+          tma_load_3d(sm.w_base + ws * sm.w_stage_bytes, &tm_w_hi, bar(B_WFULL + ws), 0, 0, tap);
+          if (p.split)
+            tma_load_3d(sm.w_base + ws * sm.w_stage_bytes + sm.w_slab, &tm_w_lo,
+                        bar(B_WFULL + ws), 0, 0, tap);
+        }
+        __syncwarp();
+        if (++ws == p.WS) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (warp-uniform, elected issue)
+    int as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0, it = 0;
+    const uint32_t hi_a = sdesc_hi_sw128((uint32_t)p.XB * 128u);
+    const uint32_t hi_b = sdesc_hi_sw128(1024u);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const ItemCoord c = decode_item(p, item);
+      mbar_wait(bar(B_ACCEMPTY + ab), abph ^ 1, p.dbg, 3, ab, it);
+      mbar_wait(bar(B_AFULL + as), aph, p.dbg, 4, as, it);
+      tc_fence_after();
+      const uint32_t a_hi = sm.a_base + as * sm.a_stage_bytes;
+      const uint32_t d_base = tmem_base + (uint32_t)(ab * p.R * p.npad);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int dx = tap % 3, dy = (tap / 3) % 3, dz = tap / 9;
+        mbar_wait(bar(B_WFULL + ws), wph, p.dbg, 5, ws, it * 100 + tap);
+        tc_fence_after();
+        const uint32_t wl = sdesc_lo(sm.w_base + ws * sm.w_stage_bytes);
+        const uint32_t wl_lo = sdesc_lo(sm.w_base + ws * sm.w_stage_bytes + sm.w_slab);
+        if (elect_one()) {
+          for (int r = 0; r < p.R; ++r) {
+            const uint32_t row = (uint32_t)(c.row0 + r * p.TS + dz * p.YB + dy);
+            const uint32_t al = sdesc_lo(a_hi + (row * p.XB + dx) * 128u);
+            const uint32_t al_lo = sdesc_lo(a_hi + p.box_stride + (row * p.XB + dx) * 128u);
+            const uint32_t d_addr = d_base + (uint32_t)(r * p.npad);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = mk_desc(al + 2u * kk, hi_a);
+              const uint64_t db = mk_desc(wl + 2u * kk, hi_b);
+              if (tap == 0 && kk == 0) umma_f16_new(d_addr, da, db, p.idesc);
+              else umma_f16_acc(d_addr, da, db, p.idesc);
+              if (p.split) {
+                umma_f16_acc(d_addr, mk_desc(al_lo + 2u * kk, hi_a), db, p.idesc);
+                umma_f16_acc(d_addr, da, mk_desc(wl_lo + 2u * kk, hi_b), p.idesc);
+              }
+            }
+          }
+          umma_commit(bar(B_WEMPTY + ws));
+          if (tap == p.ntaps - 1) {
+            umma_commit(bar(B_AEMPTY + as));
+            umma_commit(bar(B_ACCFULL + ab));
+          }
+        }
+        __syncwarp();
+        if (++ws == p.WS) { ws = 0; wph ^= 1; }
+      }
+      if (++as == p.AS) { as = 0; aph ^= 1; }
+      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
+    }
+  } else {
+    int ab = 0, abph = 0, it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const ItemCoord c = decode_item(p, item);
+      mbar_wait(bar(B_ACCFULL + ab), abph, p.dbg, 6, ab, it);
+      tc_fence_after();
+      for (int r = 0; r < p.R; ++r)
+        epilogue_tile<EPI>(p, sm, c, c.row0 + r * p.TS, tmem_base + (uint32_t)((ab * p.R + r) * p.npad),
+                      warp, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + ab));
+      if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+
+template <int EPI>
+static int launch_tile_t(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                         const CUtensorMap& w_hi, const CUtensorMap& w_lo, int ctas, uint32_t smem,
+                         cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    S3_CUDA(cudaFuncSetAttribute(conv_umma_tile_kernel<EPI>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr = true;
+  }
+  conv_umma_tile_kernel<EPI><<<ctas, kThreads, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  S3_CUDA(cudaGetLastError());
+  return S3_OK;
+}
+
+int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                     const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
+                     uint32_t smem, cudaStream_t st) {
+  if (epi == EPI_PLAIN) return launch_tile_t<EPI_PLAIN>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
+  if (epi == EPI_D2S) return launch_tile_t<EPI_D2S>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
+  return launch_tile_t<EPI_GENERIC>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
+}
+
+}  // namespace s3

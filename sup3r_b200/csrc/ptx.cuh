@@ -63,9 +63,9 @@ struct DebugRec {
 #define S3_WAIT_TIMEOUT_CYCLES (4000000000LL)  // ~2 s at 1.9 GHz
 #endif
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRec* dbg,
-                                          unsigned code, unsigned index, unsigned iter) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path kept out of line so that every inlined wait is only a try_wait + branch
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, DebugRec* dbg,
+                                            unsigned code, unsigned index, unsigned iter) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > S3_WAIT_TIMEOUT_CYCLES) {
@@ -82,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRe
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRec* dbg,
+                                          unsigned code, unsigned index, unsigned iter) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, dbg, code, index, iter);
 }
 
 // --------------------------------------------------------------------- TMA

@@ -9,6 +9,10 @@
 
 namespace s3 {
 
+// epilogue specialisations (one per kernel instantiation keeps the SASS small: the generic
+// scatter is ~10x the code of the fast paths and would thrash the instruction cache)
+enum { EPI_PLAIN = 0, EPI_D2S = 1, EPI_GENERIC = 2 };
+
 struct RowPlan {
   bool valid, slow;
   int b, z, y, x;
@@ -64,18 +68,125 @@ __device__ __forceinline__ void store16x2(uint16_t* base, long long off, const u
 // Process all column chunks of one accumulator row.  t_addr: TMEM address of column 0 of this
 // warp's lane quarter.  sbias: bias staged in shared memory (zeros when absent).
 // All 32 lanes must call (LDTM is warp-collective).
-template <bool kPrefetchResidual>
+// Hot path: plain mapping, cout == 64.  All four TMEM chunks and the residual row are in
+// flight before anything is consumed (one TMEM wait, one DRAM/L2 round trip per tile).
+__device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Epilogue& ep,
+                                                     const float* sbias, uint32_t t_addr,
+                                                     const RowPlan& rp) {
+  float4 rpre[16];
+  const bool has_res = ep.residual != nullptr;
+  if (rp.valid && has_res) {
+    const float4* rr = reinterpret_cast<const float4*>(ep.residual + rp.conv_vox * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) rpre[q] = __ldg(rr + q);
+  }
+  uint32_t raw[64];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc)
+    tmem_ld16(t_addr + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[cc * 16]));
+  tmem_ld_wait();
+  if (!rp.valid) return;
+  const int rep = g.rep[2];
+  const int fmt = ep.fmt;
+  uint16_t* yh = reinterpret_cast<uint16_t*>(ep.y_hi);
+  uint16_t* yl = reinterpret_cast<uint16_t*>(ep.y_lo);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bv = *reinterpret_cast<const float4*>(sbias + cc * 16 + 4 * q);
+      v[4 * q] = __uint_as_float(raw[cc * 16 + 4 * q]) + bv.x;
+      v[4 * q + 1] = __uint_as_float(raw[cc * 16 + 4 * q + 1]) + bv.y;
+      v[4 * q + 2] = __uint_as_float(raw[cc * 16 + 4 * q + 2]) + bv.z;
+      v[4 * q + 3] = __uint_as_float(raw[cc * 16 + 4 * q + 3]) + bv.w;
+    }
+    if (g.act == S3_ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
+    } else if (g.act == S3_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (g.act != S3_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+    }
+    if (has_res) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 r4 = rpre[cc * 4 + q];
+        v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+      }
+    }
+    uint4 h0, h1, l0, l1;
+    if (yh) {
+      h0.x = pack2(v[0], v[1], fmt);   h0.y = pack2(v[2], v[3], fmt);
+      h0.z = pack2(v[4], v[5], fmt);   h0.w = pack2(v[6], v[7], fmt);
+      h1.x = pack2(v[8], v[9], fmt);   h1.y = pack2(v[10], v[11], fmt);
+      h1.z = pack2(v[12], v[13], fmt); h1.w = pack2(v[14], v[15], fmt);
+      if (yl) {
+        float e[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) e[j] = v[j] - from16(to16(v[j], fmt), fmt);
+        l0.x = pack2(e[0], e[1], fmt);   l0.y = pack2(e[2], e[3], fmt);
+        l0.z = pack2(e[4], e[5], fmt);   l0.w = pack2(e[6], e[7], fmt);
+        l1.x = pack2(e[8], e[9], fmt);   l1.y = pack2(e[10], e[11], fmt);
+        l1.z = pack2(e[12], e[13], fmt); l1.w = pack2(e[14], e[15], fmt);
+      }
+    }
+#pragma unroll 1
+    for (int rx = 0; rx < rep; ++rx) {
+      if (ep.y) {
+        float4* dst = reinterpret_cast<float4*>(ep.y + rp.base32 + (size_t)rx * 64 + cc * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (yh) {
+        const int ox = rp.x * rep + rx;
+        const long long mx = ox == 1 ? -128LL : (ox == g.fd[2] - 2 ? 128LL : 0LL);
+        const long long o0 = (long long)rp.base16 + (long long)rx * 64 + cc * 16;
+        store16x2(yh, o0, h0, h1);
+        if (yl) store16x2(yl, o0, l0, l1);
+        if ((rp.mz | rp.my | mx) != 0) {
+#pragma unroll 1
+          for (int combo = 1; combo < 8; ++combo) {
+            const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+            if ((a && rp.mz == 0) || (bq && rp.my == 0) || (cq && mx == 0)) continue;
+            const long long o = o0 + (a ? rp.mz : 0) + (bq ? rp.my : 0) + (cq ? mx : 0);
+            store16x2(yh, o, h0, h1);
+            if (yl) store16x2(yl, o, l0, l1);
+          }
+        }
+      }
+    }
+  }
+}
+
+//   EPI_PLAIN  : host guarantees plain mapping, cout % 16 == 0, aligned strides, extents >= 4
+//                (no "slow" rows), nearest repeat along x only (<= 3 copies)
+//   EPI_D2S    : host guarantees depth_to_space / depth_to_time with cmap in {4, 8, 16},
+//                cout % cmap == 0, f32 destination only, no repeat
+//   EPI_GENERIC: anything
+template <int EPI>
 __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& ep,
                                              const float* sbias, uint32_t t_addr, RowPlan& rp) {
-  const bool mapped = (g.r != 1 || g.m != 1);
-  const bool vec32 = (g.cstride % 4 == 0) && (g.coff % 4 == 0);
-  const bool vec16 = (g.cstride % 8 == 0) && (g.coff % 8 == 0);
-  const bool fast_plain = !mapped && !rp.slow && vec32 && vec16;
+  if (EPI == EPI_PLAIN && g.cout == 64 && g.cstride == 64 && g.coff == 0 && !ep.post_scale) {
+    epilogue_row_plain64(g, ep, sbias, t_addr, rp);
+    return;
+  }
+  constexpr bool kPrefetchResidual = false;
+  const bool mapped = EPI == EPI_PLAIN ? false : (EPI == EPI_D2S ? true : (g.r != 1 || g.m != 1));
+  const bool vec32 = EPI != EPI_GENERIC ? true : ((g.cstride % 4 == 0) && (g.coff % 4 == 0));
+  const bool vec16 = EPI != EPI_GENERIC ? true : ((g.cstride % 8 == 0) && (g.coff % 8 == 0));
+  const bool fast_plain = EPI == EPI_PLAIN ? true
+                                           : (EPI == EPI_D2S ? false
+                                                             : (!mapped && !rp.slow && vec32 && vec16));
 
   // residual row prefetch (cout <= 64): 16 x LDG.128 in flight before the first TMEM load
   float4 rpre[kPrefetchResidual ? 16 : 1];
   if (kPrefetchResidual) {
-    if (rp.valid && ep.residual) {
+    if (rp.valid && ep.residual && g.cout <= 64) {
       const float4* rr = reinterpret_cast<const float4*>(ep.residual + rp.conv_vox * g.cout);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
@@ -93,7 +204,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-    if (len == 16) {
+    if (EPI == EPI_PLAIN || len == 16) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * q);
@@ -110,7 +221,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
         for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
       }
       if (ep.residual) {
-        if (kPrefetchResidual) {
+        if (kPrefetchResidual && g.cout <= 64) {
           // select the prefetched quad for this chunk with static indices
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
@@ -136,13 +247,13 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
         for (int j = 0; j < 16; ++j)
           v[j] = v[j] * ep.post_scale[c0 + j] + (ep.post_shift ? ep.post_shift[c0 + j] : 0.f);
       }
-    } else {
+    } else if (EPI != EPI_PLAIN) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         v[j] = j < len ? finish(g, ep, v[j], c0 + j, rp.conv_vox) : 0.f;
     }
 
-    if (fast_plain && len == 16) {
+    if (fast_plain && (EPI == EPI_PLAIN || len == 16)) {
       // ---- fast path: the 16-channel run goes to every destination row
       uint4 h0, h1, l0, l1;
       if (ep.y_hi) {
@@ -176,18 +287,23 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
           const long long o0 = (long long)rp.base16 + (long long)rx * g.cstride + c0;
           uint16_t* yh = reinterpret_cast<uint16_t*>(ep.y_hi);
           uint16_t* yl = reinterpret_cast<uint16_t*>(ep.y_lo);
-#pragma unroll
-          for (int combo = 0; combo < 8; ++combo) {
-            const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
-            if ((a && rp.mz == 0) || (bq && rp.my == 0) || (cq && mx == 0)) continue;
-            const long long o = o0 + (a ? rp.mz : 0) + (bq ? rp.my : 0) + (cq ? mx : 0);
-            store16x2(yh, o, h0, h1);
-            if (ep.y_lo) store16x2(yl, o, l0, l1);
+          store16x2(yh, o0, h0, h1);
+          if (ep.y_lo) store16x2(yl, o0, l0, l1);
+          if ((rp.mz | rp.my | mx) != 0) {
+#pragma unroll 1
+            for (int combo = 1; combo < 8; ++combo) {
+              const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+              if ((a && rp.mz == 0) || (bq && rp.my == 0) || (cq && mx == 0)) continue;
+              const long long o = o0 + (a ? rp.mz : 0) + (bq ? rp.my : 0) + (cq ? mx : 0);
+              store16x2(yh, o, h0, h1);
+              if (ep.y_lo) store16x2(yl, o, l0, l1);
+            }
           }
         }
       }
-    } else if (mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !ep.y_hi && ep.y &&
-               (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && len % g.cmap == 0) {
+    } else if (EPI == EPI_D2S ||
+               (EPI == EPI_GENERIC && mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !ep.y_hi &&
+                ep.y && (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && len % g.cmap == 0)) {
       // ---- depth_to_space / depth_to_time fast path: runs of cmap channels, f32 only
       const int nrun = len / g.cmap;
       for (int s = 0; s < nrun; ++s) {
@@ -224,7 +340,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
           }
         }
       }
-    } else {
+    } else if (EPI == EPI_GENERIC) {
       // ---- generic scatter (rare shapes): element runs through store_run
       int j = 0;
       while (j < len) {
