@@ -83,6 +83,9 @@ typedef struct s3_umma_tuning {
   int32_t max_ctas;         /* 0 = SM count */
   int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
   void* trace;              /* optional device buffer of 16 int64: role timings of CTA 0 */
+  int32_t scheme;           /* 3-D narrow convs: 0 = plane-ring pipeline ("zring"), 1 = per-item
+                               halo boxes ("zcat", the round-1 baseline kept for A/B runs) */
+  int32_t ring_slots;       /* zring: activation plane slots in shared memory (0 = as many as fit) */
 } s3_umma_tuning;
 
 int s3_init(int device);

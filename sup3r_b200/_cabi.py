@@ -34,7 +34,8 @@ class ConvDesc(C.Structure):
 class UmmaTuning(C.Structure):
     """``s3_umma_tuning``"""
     _fields_ = [("tiles", C.c_int32), ("w_stages", C.c_int32), ("box_x", C.c_int32),
-                ("box_y", C.c_int32), ("max_ctas", C.c_int32), ("fmt", C.c_int32), ("trace", C.c_void_p)]
+                ("box_y", C.c_int32), ("max_ctas", C.c_int32), ("fmt", C.c_int32), ("trace", C.c_void_p),
+                ("scheme", C.c_int32), ("ring_slots", C.c_int32)]
 
 
 _P = C.c_void_p

@@ -135,7 +135,26 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   const uint32_t fixed = 3072u;  // alignment slack + barrier block + staged bias
 
   bool found = false;
-  if (zcat) {
+  const bool zring = zcat && t.scheme == 0;
+  if (zring) {
+    // plane-ring pipeline: P plane slots (18 x XB voxels each) + a WS-deep slab ring
+    int R = t.tiles > 0 ? t.tiles : 4;
+    if (2 * R * p.npad > 512) R = 512 / (2 * p.npad);
+    if (R > p.planes) R = p.planes;
+    if (R < 1) R = 1;
+    const int ws = t.w_stages > 0 ? t.w_stages : 2;
+    S3_REQUIRE(ws >= 2 && ws <= 4, "s3_conv_fwd_umma: zring needs w_stages in [2, 4]");
+    const uint32_t plane = 18u * (uint32_t)p.XB * 128u;
+    int P = (int)((kSmemLimit - fixed - 1024u - (uint32_t)ws * w_slab) / plane);
+    if (P > 8) P = 8;
+    if (t.ring_slots > 0 && t.ring_slots < P) P = t.ring_slots;
+    if (R + 2 > P) R = P - 2;
+    S3_REQUIRE(R >= 1, "s3_conv_fwd_umma: zring does not fit shared memory (npad %d)", p.npad);
+    p.flat = 0; p.R = R; p.YB = 18; p.ZB = 1; p.TS = 18; p.WS = ws; p.AS = P;
+    p.dbg_flags = t.box_y;   // zring: box_y carries experiment flags (see kernel)
+    p.box_bytes = plane; p.box_stride = plane;
+    found = true;
+  } else if (zcat) {
     int r_max = t.tiles > 0 ? t.tiles : 4;
     if (2 * r_max * p.npad > 512) r_max = 512 / (2 * p.npad);
     if (r_max > p.planes) r_max = p.planes;
@@ -213,7 +232,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     if ((rc = encode_map(&tm_a_lo, x_lo, t.fmt, 4, adims, abox))) return rc;
     if ((rc = encode_map(&tm_w_lo, w_lo, t.fmt, 3, wdims, wbox))) return rc;
   }
-  const uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
+  uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
+  if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed;
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
   // epilogue specialisation: fast paths only when their preconditions hold for EVERY row
@@ -228,7 +248,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
              g.cstride % 4 == 0 && g.coff % 4 == 0) {
     epi = EPI_D2S;
   }
-  if (zcat)
+  if (zring)
+    rc = launch_umma_zring(p, tm_a_hi, tm_w_hi, epi, ctas, smem, as_stream(stream));
+  else if (zcat)
     rc = launch_umma_zcat(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
                           as_stream(stream));
   else

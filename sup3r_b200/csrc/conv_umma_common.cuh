@@ -25,6 +25,7 @@ struct UmmaParams {
   uint32_t idesc;
   DebugRec* dbg;
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
+  int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
 };
 
 struct ItemCoord {
@@ -155,6 +156,8 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const SmemMap
 int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st);
+int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w, int epi,
+                      int ctas, uint32_t smem, cudaStream_t st);
 int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st);

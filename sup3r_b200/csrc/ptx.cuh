@@ -89,6 +89,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRe
   mbar_wait_slow(bar, parity, dbg, code, index, iter);
 }
 
+// fully inlined variant for kernels that re-partition registers with setmaxnreg (ptxas cannot
+// allocate across an ABI call there)
+__device__ __forceinline__ void mbar_wait_inl(uint32_t bar, uint32_t parity, DebugRec* dbg,
+                                              unsigned code, unsigned index, unsigned iter) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > S3_WAIT_TIMEOUT_CYCLES) {
+      if (dbg) {
+        dbg->code = code;
+        dbg->index = index;
+        dbg->parity = parity;
+        dbg->block = blockIdx.x;
+        dbg->iter = iter;
+        __threadfence_system();
+        dbg->flag = 0xDEADu;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -27,7 +27,9 @@ y = torch.empty(ops._shape_from(n, od, oc, 3), device=dev)
 y_hi = torch.empty(ops.pad16_shape(n, od, oc, 3), device=dev, dtype=torch.bfloat16)
 y_lo = torch.empty_like(y_hi) if split else None
 kw = dict(out=y) if variant == "f32out" else dict(want_f32=False, out_hi=y_hi, out_lo=y_lo)
-t = UmmaTuning(tiles=tiles, w_stages=ws)
+scheme = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+flags = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+t = UmmaTuning(tiles=tiles, w_stages=ws, scheme=scheme, box_y=flags)
 for _ in range(iters):
     ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims, tune=t, **kw)
 torch.cuda.synchronize()

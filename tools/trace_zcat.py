@@ -6,6 +6,8 @@ sys.path.insert(0, ROOT)
 from sup3r_b200 import ops
 from sup3r_b200._cabi import UmmaTuning
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+scheme = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda:0")
 dims = (16, 16, 288)
 x = torch.randn((n, *dims, 64), device=dev)
@@ -20,12 +22,12 @@ res = torch.randn_like(y)
 for name, kw in [("pad16", dict(want_f32=False, out_hi=y_hi)), ("f32", dict(out=y)),
                  ("res_f32_pad16", dict(out=y, out_hi=y_hi, residual=res))]:
     trace = torch.zeros(16, dtype=torch.int64, device=dev)
-    t = UmmaTuning(trace=trace.data_ptr())
+    t = UmmaTuning(trace=trace.data_ptr(), scheme=scheme, box_y=flags)
     for _ in range(3):
         ops.conv_fwd_umma(x_hi, None, w_hi, None, b, spec, n, dims, tune=t, **kw)
     torch.cuda.synchronize()
     tr = trace.cpu().tolist()
     items = max(tr[5], 1)
-    print(f"{name}: items/CTA {tr[5]}  MMA-warp total {tr[0]} cyc ({tr[0]/items:.0f}/item): wait acc_empty {tr[1]/items:.0f}, "
+    print(f"scheme {scheme} flags {flags} {name}: items/CTA {tr[5]}  MMA-warp total {tr[0]} cyc ({tr[0]/items:.0f}/item): wait acc_empty {tr[1]/items:.0f}, "
           f"wait weights {tr[2]/items:.0f}, wait planes {tr[3]/items:.0f}, issue loop {tr[4]/items:.0f} | "
           f"epilogue warp: wait acc_full {tr[8]/items:.0f}, work {tr[9]/items:.0f} (per item)")
