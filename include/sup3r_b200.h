@@ -115,11 +115,14 @@ int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, fl
 
 /* ---- tcgen05 implicit-GEMM convolution (cin == 64, 3x3[x3], stride 1, reflect-1) ---------
  * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single-pass bf16, else the
- * 3-pass split-precision product hi*hi + lo*hi + hi*lo).  w_hi/w_lo: from s3_pack_weights_umma. */
+ * 3-pass split-precision product hi*hi + lo*hi + hi*lo).  w_hi/w_lo: from s3_pack_weights_umma.
+ * The SkipConnection addend is either `residual` (f32, output layout) or the pair res_hi/res_lo
+ * (16-bit padded layout of y_hi; value = hi + lo; res_lo may be NULL). */
 int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi,
                      const void* w_lo, const float* bias, const float* residual,
-                     const float* post_scale, const float* post_shift, float* y, void* y_hi,
-                     void* y_lo, const s3_umma_tuning* tune, s3_stream stream);
+                     const void* res_hi, const void* res_lo, const float* post_scale,
+                     const float* post_shift, float* y, void* y_hi, void* y_lo,
+                     const s3_umma_tuning* tune, s3_stream stream);
 /* rows of the packed weight tensor per tap (cout rounded up to a multiple of 16) */
 int s3_umma_npad(int cout);
 /* Weight layout the tcgen05 kernel expects for a conv with this rank / cout:

@@ -54,7 +54,7 @@ SIGNATURES = {
     "s3_conv_dgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "s3_conv_wgrad_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "s3_conv_wgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
-    "s3_conv_fwd_umma": (_I, [C.POINTER(ConvDesc)] + [_P] * 11 + [C.POINTER(UmmaTuning), _P]),
+    "s3_conv_fwd_umma": (_I, [C.POINTER(ConvDesc)] + [_P] * 13 + [C.POINTER(UmmaTuning), _P]),
     "s3_umma_npad": (_I, [_I]),
     "s3_umma_weight_layout": (_I, [_I, _I, _I]),
     "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P]),

@@ -61,6 +61,8 @@ struct Epilogue {
   void* y_hi;        // 16-bit padded mirrored destination (nullable)
   void* y_lo;        // residual half of the split (nullable)
   int fmt;           // 0 bf16, 1 fp16
+  const void* res_hi;  // residual as a 16-bit padded pair (hi + lo), same layout as y_hi
+  const void* res_lo;
 };
 
 // ------------------------------------------------------------------------ device side

@@ -85,9 +85,10 @@ extern "C" int s3_umma_weight_layout(int ndim, int cout, int split) {
 
 extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const void* x_lo,
                                 const void* w_hi, const void* w_lo, const float* bias,
-                                const float* residual, const float* post_scale,
-                                const float* post_shift, float* y, void* y_hi, void* y_lo,
-                                const s3_umma_tuning* tune, s3_stream stream) {
+                                const float* residual, const void* res_hi, const void* res_lo,
+                                const float* post_scale, const float* post_shift, float* y,
+                                void* y_hi, void* y_lo, const s3_umma_tuning* tune,
+                                s3_stream stream) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   int rc = make_geom(d, &p.g);
@@ -113,7 +114,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   s3_umma_tuning t;
   memset(&t, 0, sizeof(t));
   if (tune) t = *tune;
-  p.ep = Epilogue{bias, residual, post_scale, post_shift, y, y_hi, y_lo, t.fmt};
+  S3_REQUIRE(!(residual && res_hi), "s3_conv_fwd_umma: give the residual as f32 OR as a 16-bit pair");
+  S3_REQUIRE(!(res_lo && !res_hi), "s3_conv_fwd_umma: res_lo without res_hi");
+  p.ep = Epilogue{bias, residual, post_scale, post_shift, y, y_hi, y_lo, t.fmt, res_hi, res_lo};
   p.kz = kz;
   p.ntaps = kz * 9;
   p.npad = s3_umma_npad(g.cout);
@@ -145,13 +148,24 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     const int ws = t.w_stages > 0 ? t.w_stages : 2;
     S3_REQUIRE(ws >= 2 && ws <= 4, "s3_conv_fwd_umma: zring needs w_stages in [2, 4]");
     const uint32_t plane = 18u * (uint32_t)p.XB * 128u;
-    int P = (int)((kSmemLimit - fixed - 1024u - (uint32_t)ws * w_slab) / plane);
+    // coalescing 16-bit epilogue: 8 warps x 2 KiB staging (see conv_umma_zring.cu)
+    const bool v2_shape = g.cout == 64 && g.cstride == 64 && g.coff == 0 && g.r == 1 && g.m == 1 &&
+                          g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.fd[0] >= 4 && g.fd[1] >= 4 &&
+                          g.fd[2] >= 4 && !post_scale;
+    p.epi_v2 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
+                p.planes >= 4) ? 1 : 0;
+    S3_REQUIRE(!res_hi || p.epi_v2, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
+               "64-channel 16-bit-output configuration");
+    const uint32_t stage_bytes = p.epi_v2 ? 16384u : 0u;
+    int P = (int)((kSmemLimit - fixed - 1024u - stage_bytes - (uint32_t)ws * w_slab) / plane);
     if (P > 8) P = 8;
     if (t.ring_slots > 0 && t.ring_slots < P) P = t.ring_slots;
     if (R + 2 > P) R = P - 2;
     S3_REQUIRE(R >= 1, "s3_conv_fwd_umma: zring does not fit shared memory (npad %d)", p.npad);
     p.flat = 0; p.R = R; p.YB = 18; p.ZB = 1; p.TS = 18; p.WS = ws; p.AS = P;
     p.dbg_flags = t.box_y;   // zring: box_y carries experiment flags (see kernel)
+    p.ring_fast = (R == 4 && p.planes % 4 == 0 && p.npad == 64 && p.XB == 10 && P == 7 && ws == 2 &&
+                   !(p.dbg_flags & 16)) ? 1 : 0;
     p.box_bytes = plane; p.box_stride = plane;
     found = true;
   } else if (zcat) {
@@ -233,7 +247,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     if ((rc = encode_map(&tm_w_lo, w_lo, t.fmt, 3, wdims, wbox))) return rc;
   }
   uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
-  if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed;
+  if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed +
+                    (p.epi_v2 ? 16384u : 0u);
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
   // epilogue specialisation: fast paths only when their preconditions hold for EVERY row

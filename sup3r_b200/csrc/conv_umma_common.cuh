@@ -26,6 +26,8 @@ struct UmmaParams {
   DebugRec* dbg;
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
   int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
+  int epi_v2;         // zring: coalescing 16-bit epilogue (conv_umma_zring.cu)
+  int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
 };
 
 struct ItemCoord {

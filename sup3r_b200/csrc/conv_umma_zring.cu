@@ -69,7 +69,7 @@ __device__ __forceinline__ RingItem ring_decode(const UmmaParams& p, int i, int 
 // written with back-to-back 16-byte stores (full 128-B lines per voxel).
 __device__ __forceinline__ void ring_epilogue_row64(const ConvGeom& g, const Epilogue& ep,
                                                     const float* sbias, uint32_t t_addr,
-                                                    const RowPlan& rp) {
+                                                    const RowPlan& rp, int dbg = 0) {
   float4 rpre[16];
   const bool has_res = ep.residual != nullptr;
   if (rp.valid && has_res) {
@@ -78,11 +78,17 @@ __device__ __forceinline__ void ring_epilogue_row64(const ConvGeom& g, const Epi
     for (int q = 0; q < 16; ++q) rpre[q] = __ldg(rr + q);
   }
   uint32_t raw[64];
+  if (dbg & 64) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) raw[j] = t_addr + j;
+  } else {
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc)
     tmem_ld16(t_addr + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[cc * 16]));
   tmem_ld_wait();
+  }
   if (!rp.valid) return;
+  if ((dbg & 32) && raw[5] != 0x7fffffffu) return;
   float v[64];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -167,6 +173,177 @@ __device__ __forceinline__ void ring_epilogue_row64(const ConvGeom& g, const Epi
   }
 }
 
+// ------------------------------------------------------------------- coalescing epilogue
+// Measured (role trace, B200): global loads / stores issued thread-per-row (32 different
+// 128-B lines per warp instruction) slow the concurrently running MMA stream almost 1:1 with
+// their L1 wavefront count -- the SS-mode tcgen05.mma already uses ~85 % of the shared-memory
+// bandwidth and the LSU shares that data path.  This epilogue therefore moves every global
+// access to a row-coalesced mapping (8 lanes x 16 B = one 128-B voxel row, 4 rows = 512
+// contiguous bytes per instruction) through a 2 KiB per-warp staging buffer with a 16-byte
+// XOR swizzle (conflict-free for both the thread-per-row and the coalesced side).
+//   * output: 16-bit padded rows (hi [+ lo = rounding residue]) incl. the REFLECT halo mirrors;
+//   * residual: 16-bit hi + lo pair of the skip tensor (same padded layout), prefetched into
+//     registers before the accumulator is waited for.
+// One call = one warp = 32 accumulator rows = 4 y rows x 8 x voxels of one output plane.
+struct TileGeom {
+  long long sy, sz;      // byte strides of the padded 16-bit tensor along y / z
+  long long base;        // byte offset of voxel (y0, x0) of this plane (interior position)
+  long long mz;          // z mirror delta in bytes (0 = none), warp-uniform
+  int y0, x0;
+};
+
+__device__ __forceinline__ uint32_t stage_off(int r, int k) {
+  return (uint32_t)(r * 128 + ((k ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void unpack_add8(float* v, const uint4& u, int fmt) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] += from16((uint16_t)(w[j] & 0xffffu), fmt);
+    v[2 * j + 1] += from16((uint16_t)(w[j] >> 16), fmt);
+  }
+}
+
+template <bool kRes>
+__device__ __forceinline__ void ring_epilogue_warp_v2(const ConvGeom& g, const Epilogue& ep,
+                                                      const float* sbias, uint32_t t_addr,
+                                                      const TileGeom& tg, uint8_t* stage,
+                                                      int lane) {
+  const int fmt = ep.fmt;
+  const int FY = g.fd[1], FX = g.fd[2];
+  const int lr = lane >> 3, lk = lane & 7;      // coalesced side: row within a group of 4, chunk
+  const int half_of_lane = lane >> 4, rrow = lane & 15;   // thread-per-row side
+  const bool has_lo = ep.y_lo != nullptr;
+  // coalesced side: (h, i) -> m = 16 h + 4 i + lr, y = y0 + (m >> 3), x = x0 + (m & 7);
+  // byte offset of this lane's 16-byte chunk of row m = rowoff + (m >> 3) * sy + (m & 7) * 128
+  const long long lane_off = tg.base + (long long)(lr & 1 ? 0 : 0) + lk * 16;
+  auto row_off = [&](int h, int i) -> long long {
+    const int m = 16 * h + 4 * i + lr;
+    return lane_off + (long long)(m >> 3) * tg.sy + (long long)(m & 7) * 128;
+  };
+  auto row_ok = [&](int h, int i) -> bool {
+    const int m = 16 * h + 4 * i + lr;
+    return tg.y0 + (m >> 3) < FY && tg.x0 + (m & 7) < FX;
+  };
+
+  // ---- residual: rolling register prefetch, two (operand, half) rounds in flight
+  uint4 rres[2][4];
+  const bool res_has_lo = kRes && ep.res_lo != nullptr;
+  auto res_load = [&](int op, int h, uint4 (&dst)[4]) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(op == 0 ? ep.res_hi : ep.res_lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = row_ok(h, i) ? __ldg(reinterpret_cast<const uint4*>(src + row_off(h, i)))
+                            : make_uint4(0, 0, 0, 0);
+  };
+  if (kRes) {
+    res_load(0, 0, rres[0]);
+    res_load(0, 1, rres[1]);
+  }
+
+  // ---- accumulator row -> registers, bias, activation
+  float v[64];
+  {
+    uint32_t raw[64];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      tmem_ld16(t_addr + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[cc * 16]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * q);
+      v[4 * q] = __uint_as_float(raw[4 * q]) + bv.x;
+      v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bv.y;
+      v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bv.z;
+      v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bv.w;
+    }
+  }
+  if (g.act == S3_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
+  } else if (g.act == S3_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (g.act != S3_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+  }
+
+  // ---- residual: coalesced registers -> staging -> own row (rounds: hi h0, hi h1, lo h0, lo h1)
+  if (kRes) {
+#pragma unroll
+    for (int rnd = 0; rnd < 4; ++rnd) {
+      const int op = rnd >> 1, h = rnd & 1;
+      if (op == 0 || res_has_lo) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(stage + stage_off(4 * i + lr, lk)) = rres[rnd & 1][i];
+        __syncwarp();
+        if (rnd < 2 && res_has_lo) res_load(1, h, rres[rnd & 1]);   // next use: round rnd + 2
+        if (half_of_lane == h) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(stage + stage_off(rrow, k));
+            unpack_add8(&v[8 * k], u, fmt);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- outputs: own row -> staging -> coalesced stores (+ halo mirrors)
+#pragma unroll
+  for (int op = 0; op < 2; ++op) {
+    if (op == 0 || has_lo) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(op == 0 ? ep.y_hi : ep.y_lo);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (half_of_lane == h) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = v[8 * k + j];
+            a[j] = op == 0 ? x : x - from16(to16(x, fmt), fmt);
+          }
+          uint4 hk;
+          hk.x = pack2(a[0], a[1], fmt);
+          hk.y = pack2(a[2], a[3], fmt);
+          hk.z = pack2(a[4], a[5], fmt);
+          hk.w = pack2(a[6], a[7], fmt);
+          *reinterpret_cast<uint4*>(stage + stage_off(rrow, k)) = hk;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (row_ok(h, i)) {
+          const int m = 16 * h + 4 * i + lr;
+          const int y = tg.y0 + (m >> 3), x = tg.x0 + (m & 7);
+          const uint4 u = *reinterpret_cast<const uint4*>(stage + stage_off(4 * i + lr, lk));
+          const long long off = row_off(h, i);
+          const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
+          const long long mx = x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL);
+          *reinterpret_cast<uint4*>(dst + off) = u;
+          if ((tg.mz | my | mx) != 0) {
+#pragma unroll 1
+            for (int combo = 1; combo < 8; ++combo) {
+              const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+              if ((a && tg.mz == 0) || (bq && my == 0) || (cq && mx == 0)) continue;
+              *reinterpret_cast<uint4*>(dst + off + (a ? tg.mz : 0) + (bq ? my : 0) + (cq ? mx : 0)) = u;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void ring_epilogue_tile(const UmmaParams& p, const float* sbias,
                                                    const RingItem& c, int r, uint32_t t_addr,
@@ -184,7 +361,7 @@ __device__ __forceinline__ void ring_epilogue_tile(const UmmaParams& p, const fl
   plan_plain(g, p.ep, rp);
   const uint32_t ta = t_addr + ((uint32_t)(q * 32) << 16);
   if (EPI == EPI_PLAIN && g.cout == 64 && g.cstride == 64 && g.coff == 0)
-    ring_epilogue_row64(g, p.ep, sbias, ta, rp);
+    ring_epilogue_row64(g, p.ep, sbias, ta, rp, p.dbg_flags);
   else
     epilogue_row<EPI>(g, p.ep, sbias, ta, rp);
 }
@@ -232,6 +409,129 @@ __device__ __forceinline__ void ring_issue_slab_fast_sw(int slot0, uint32_t a_ta
     case 4: ring_issue_slab_fast<4, kLast>(a_tap, wl, hi_a, hi_b, acc0, id1, id2, id3, keep_tail, pempty0); break;
     case 5: ring_issue_slab_fast<5, kLast>(a_tap, wl, hi_a, hi_b, acc0, id1, id2, id3, keep_tail, pempty0); break;
     default: ring_issue_slab_fast<6, kLast>(a_tap, wl, hi_a, hi_b, acc0, id1, id2, id3, keep_tail, pempty0); break;
+  }
+}
+
+// bounded spin without clock reads (one try_wait + branch on the hot path)
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t n = 0; !mbar_try_wait(bar, parity); ++n)
+    if (n > (1u << 26)) __trap();
+}
+
+// MMA role for the hot configuration (every item has R = 4 output planes, npad = 64, 18 x 10
+// voxel planes, 7 ring slots, 2 weight slots).  Measured on B200 (tools/microbench/mma_rate4.cu
+// and the role trace): the tcgen05 queue only holds ~2 MMAs beyond the executing one, so every
+// stretch of issue-side code between two MMAs that is longer than ~2 MMA durations is a tensor
+// pipe bubble (the per-slab loop overhead of the generic role, ~430-580 cycles, cost ~20 %).
+// Here one elected thread issues an entire item (9 slabs x 6 planes x 4 k-steps) as straight
+// line code; the barrier waits for the NEXT slab / item are taken before the last MMA group of
+// the current slab (a N = 192 group, 4 x 96 cycles), so that the first MMA of the next slab
+// follows the last one of this slab back to back.
+__device__ __forceinline__ void ring_mma_fast(const UmmaParams& p, uint32_t bar_base,
+                                              uint32_t a_base, uint32_t w_base, uint32_t w_slab,
+                                              uint32_t tmem_base, int i0, int i1, int lane) {
+  constexpr int kR = 4, kP = 7;
+  constexpr uint32_t kPlaneLo = (18u * 10u * 128u) >> 4, kBlkLo = (64u * 128u) >> 4;
+  // plane order inside a slab: slab 0 ascending (each accumulator block is zero-initialised by
+  // its dz = 0 contribution); other slabs end with a N = 192 group; the last slab releases the
+  // planes the producer needs first (0, 1, 2) early
+  constexpr int kOrdMid[6] = {0, 1, 4, 5, 2, 3};
+  constexpr int kOrdLast[6] = {0, 1, 2, 4, 5, 3};
+  auto bar = [&](int i) { return bar_base + 8u * i; };
+  const uint32_t fmtb = p.fmt == 0 ? 1u : 0u;
+  const uint32_t hi_a = sdesc_hi_sw128(1280u), hi_b = sdesc_hi_sw128(1024u);
+  const uint32_t id1 = make_idesc_f16(64u, fmtb), id2 = make_idesc_f16(128u, fmtb),
+                 id3 = make_idesc_f16(192u, fmtb);
+  const uint32_t a_lo0 = sdesc_lo(a_base);
+  const uint32_t w_lo0 = sdesc_lo(w_base), w_lo1 = sdesc_lo(w_base + w_slab);
+  int g = 0;   // weight slabs consumed so far: slot g & 1, parity (g >> 1) & 1
+  int ab = 0, abph = 0, slot0 = 0;
+  uint32_t pf_phase = 0;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+  const long long t_all0 = tr ? clock64() : 0;
+  for (int i = i0; i < i1; ++i) {
+    const RingItem c = ring_decode(p, i, i0, i1);
+    const bool has_next = i + 1 < i1;
+    const uint32_t acc0 = tmem_base + (uint32_t)(ab * kR * 64);
+    const uint32_t next_acc_par = (uint32_t)((ab == 1 ? abph ^ 1 : abph) ^ 1);
+    uint32_t al[kR + 2], pfb[kR + 2], pfp[kR + 2], peb[kR + 2];
+#pragma unroll
+    for (int ip = 0; ip < kR + 2; ++ip) {
+      int slot = slot0 + ip;
+      if (slot >= kP) slot -= kP;
+      al[ip] = a_lo0 + (uint32_t)slot * kPlaneLo;
+      pfb[ip] = bar(RB_PFULL + slot);
+      peb[ip] = bar(RB_PEMPTY + slot);
+      pfp[ip] = (pf_phase >> slot) & 1u;
+      if (!(c.cont && ip < 2)) pf_phase ^= 1u << slot;
+    }
+    if (elect_one()) {
+      if (i == i0) {
+        mbar_wait_lean(bar(RB_ACCEMPTY + ab), (uint32_t)(abph ^ 1));
+        mbar_wait_lean(bar(RB_WFULL + 0), 0u);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        const int gs = g + s;
+        const uint32_t wl = (gs & 1) ? w_lo1 : w_lo0;
+        const uint32_t tap = (uint32_t)((s / 3) * 80 + (s % 3) * 8);
+#pragma unroll
+        for (int q = 0; q < kR + 2; ++q) {
+          const int ip = s == 0 ? q : (s == 8 ? kOrdLast[q] : kOrdMid[q]);
+          const int jlo = ip - (kR - 1) > 0 ? ip - (kR - 1) : 0;
+          const int jhi = ip < 2 ? ip : 2;
+          const int nblk = jhi - jlo + 1;
+          const uint32_t dcol = acc0 + (uint32_t)(64 * (kR - 1 - (ip - jlo)));
+          const uint32_t idn = nblk == 3 ? id3 : (nblk == 2 ? id2 : id1);
+          const uint32_t a0 = al[ip] + tap;
+          const uint32_t b0 = wl + (uint32_t)jlo * kBlkLo;
+          if (q == kR + 1) {
+            // operands of the next slab / item before the last group of this slab goes out
+            if (s < 8) {
+              mbar_wait_lean(bar(RB_WFULL + ((gs + 1) & 1)), (uint32_t)(((gs + 1) >> 1) & 1));
+            } else if (has_next) {
+              mbar_wait_lean(bar(RB_ACCEMPTY + (ab ^ 1)), next_acc_par);
+              mbar_wait_lean(bar(RB_WFULL + ((gs + 1) & 1)), (uint32_t)(((gs + 1) >> 1) & 1));
+              tc_fence_after();
+            }
+          }
+          if (s == 0) {
+            if (!(c.cont && ip < 2)) mbar_wait_lean(pfb[ip], pfp[ip]);
+            if (jlo == 0) {
+              umma_f16_new(dcol, mk_desc(a0, hi_a), mk_desc(wl, hi_b), id1);
+              if (nblk > 1)
+                umma_f16_acc(dcol + 64u, mk_desc(a0, hi_a), mk_desc(wl + kBlkLo, hi_b),
+                             nblk == 3 ? id2 : id1);
+#pragma unroll
+              for (int kk = 1; kk < 4; ++kk)
+                umma_f16_acc(dcol, mk_desc(a0 + 2u * kk, hi_a), mk_desc(b0 + 2u * kk, hi_b), idn);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_acc(dcol, mk_desc(a0 + 2u * kk, hi_a), mk_desc(b0 + 2u * kk, hi_b), idn);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_acc(dcol, mk_desc(a0 + 2u * kk, hi_a), mk_desc(b0 + 2u * kk, hi_b), idn);
+          }
+          if (s == 8 && !(c.next_cont && ip >= kR)) umma_commit(peb[ip]);
+        }
+        umma_commit(bar(RB_WEMPTY + (gs & 1)));
+        if (s == 8) umma_commit(bar(RB_ACCFULL + ab));
+      }
+    }
+    __syncwarp();
+    g += 9;
+    slot0 += c.next_cont ? kR : kR + 2;
+    while (slot0 >= kP) slot0 -= kP;
+    if (++ab == 2) { ab = 0; abph ^= 1; }
+  }
+  if (tr) {
+    p.trace[0] = clock64() - t_all0; p.trace[1] = 0; p.trace[2] = 0; p.trace[3] = 0;
+    p.trace[4] = 0; p.trace[5] = i1 - i0;
   }
 }
 
@@ -331,6 +631,8 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
         }
         for (int s = 1; s < 9; ++s) load_slab(s, i - i0);
       }
+    } else if (warp == 1 && kR == 4 && p.ring_fast) {
+      ring_mma_fast(p, bar_base, a_base, w_base, w_slab, tmem_base, i0, i1, lane);
     } else if (warp == 1) {
       // ---------------------------------------------- MMA issuer (warp-uniform, elected issue)
       int ws = 0, wph = 0, ab = 0, abph = 0;
@@ -453,11 +755,33 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       long long c1 = tr ? clock64() : 0;
       if (tr) t_wait += c1 - c0;
       tc_fence_after();
-      if (!(p.dbg_flags & 8))
-      for (int r = wg; r < c.ri; r += 2)
-        ring_epilogue_tile<EPI>(p, sbias, c, r,
-                                tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)), q,
-                                lane);
+      if (EPI == EPI_V2) {
+        if (!(p.dbg_flags & 8)) {
+        const ConvGeom& g = p.g;
+        uint8_t* stage = smem_raw + (bar_base + 2048u - smem_u32(smem_raw)) + (warp - 4) * 2048;
+        TileGeom tg;
+        tg.sy = (long long)(g.fd[2] + 2) * 128;
+        tg.sz = (long long)(g.fd[1] + 2) * tg.sy;
+        tg.y0 = c.yb * 16 + q * 4;
+        tg.x0 = c.xb * 8;
+        for (int r = wg; r < c.ri; r += 2) {
+          const int z = c.pl0 + r;
+          tg.base = ((((long long)c.b * (g.fd[0] + 2) + z + 1) * (g.fd[1] + 2) + tg.y0 + 1) *
+                         (g.fd[2] + 2) + tg.x0 + 1) * 128;
+          tg.mz = z == 1 ? -2 * tg.sz : (z == g.fd[0] - 2 ? 2 * tg.sz : 0);
+          const uint32_t ta = tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)) +
+                              ((uint32_t)(q * 32) << 16);
+          if (p.ep.res_hi)
+            ring_epilogue_warp_v2<true>(g, p.ep, sbias, ta, tg, stage, lane);
+          else
+            ring_epilogue_warp_v2<false>(g, p.ep, sbias, ta, tg, stage, lane);
+        }
+        }
+      } else if (!(p.dbg_flags & 8)) {
+        for (int r = wg; r < c.ri; r += 2)
+          ring_epilogue_tile<EPI == EPI_V2 ? EPI_PLAIN : EPI>(
+              p, sbias, c, r, tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)), q, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(RB_ACCEMPTY + ab));
@@ -487,6 +811,7 @@ static int launch_zring_t(const UmmaParams& p, const CUtensorMap& a, const CUten
 
 int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w, int epi,
                       int ctas, uint32_t smem, cudaStream_t st) {
+  if (p.epi_v2 && p.R == 4) return launch_zring_t<4, EPI_V2>(p, a, w, ctas, smem, st);
   if (epi == EPI_PLAIN && p.R == 4) return launch_zring_t<4, EPI_PLAIN>(p, a, w, ctas, smem, st);
   if (epi == EPI_PLAIN) return launch_zring_t<0, EPI_PLAIN>(p, a, w, ctas, smem, st);
   return launch_zring_t<0, EPI_GENERIC>(p, a, w, ctas, smem, st);

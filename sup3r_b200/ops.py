@@ -214,7 +214,7 @@ def unpack_act_pad16(hi, lo, ndim, fmt=0):
 
 def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residual=None,
                   post_scale=None, post_shift=None, out=None, want_f32=True, want_pad16=False,
-                  tune=None, out_hi=None, out_lo=None):
+                  tune=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, want_lo=False):
     """tcgen05 convolution on padded 16-bit activations.  ``dims`` = unpadded (z, y, x)."""
     ensure_device(x_hi)
     _, od, oc = spec.out_dims(n, dims)
@@ -226,13 +226,14 @@ def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residua
     if want_pad16 and y_hi is None:
         y_hi = torch.empty(pad16_shape(n, od, cs, spec.ndim), device=x_hi.device,
                            dtype=x_hi.dtype)
-        if x_lo is not None:
+        if x_lo is not None or want_lo:
             y_lo = torch.empty_like(y_hi)
     t = tune if tune is not None else UmmaTuning()
     bias, residual = _f32(bias), _f32(residual)
     post_scale, post_shift = _f32(post_scale), _f32(post_shift)
     _cabi.call("s3_conv_fwd_umma", C.byref(spec.desc(n, dims)), _p(x_hi), _p(x_lo), _p(w_hi),
-               _p(w_lo), _p(bias), _p(residual), _p(post_scale), _p(post_shift), _p(y), _p(y_hi),
+               _p(w_lo), _p(bias), _p(residual), _p(res_hi), _p(res_lo), _p(post_scale),
+               _p(post_shift), _p(y), _p(y_hi),
                _p(y_lo), C.byref(t), _s())
     _count()
     return y, y_hi, y_lo

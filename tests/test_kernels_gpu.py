@@ -368,3 +368,69 @@ def test_stats_and_channel_check(cuda):
     cc = ops.channel_check(dev(x, cuda)).cpu().numpy()
     assert cc[2, 0] == cc[2, 1] == 1.5 and cc[3, 2] == 1 and cc[0, 2] == 0
     assert cc[0, 0] == x[..., 0].min() and cc[1, 1] == x[..., 1].max()
+
+
+# ----------------------------------------------------------------------------- tcgen05 conv
+def _bf16_exact(a):
+    return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+UMMA_CASES = [
+    # n, (z, y, x), variant
+    (1, (16, 16, 24), "pad16"),          # hot shape: ring kernel, straight-line MMA role, v2 epilogue
+    (2, (8, 16, 40), "pad16_lo"),
+    (1, (16, 16, 24), "res16"),
+    (2, (4, 13, 21), "res16"),           # ragged y / x tiles
+    (1, (12, 20, 9), "res16_nolo"),
+    (1, (6, 9, 17), "pad16"),            # planes % 4 != 0 -> generic MMA role
+    (1, (16, 16, 24), "f32"),            # fp32 destination (thread-per-row epilogue)
+    (1, (8, 16, 24), "res_f32"),
+]
+
+
+@pytest.mark.parametrize("n,dims,variant", UMMA_CASES)
+def test_umma_conv_matches_direct(cuda, n, dims, variant):
+    """tcgen05 64->64 3x3x3 reflect conv (+bias, LeakyReLU, SkipConnection add) against the fp32
+    direct kernel on bf16-exact operands: products are exact, only the fp32 summation order
+    differs.  16-bit outputs are compared INCLUDING the REFLECT halo the epilogue writes."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(hash((n, dims, variant)) % (2 ** 31))
+    x = _bf16_exact(rng_arr(rng, (n, *dims, 64)))
+    w = _bf16_exact(rng_arr(rng, (3, 3, 3, 64, 64), 0.05))
+    b = rng_arr(rng, (64,), 0.1)
+    res = rng_arr(rng, (n, *dims, 64))
+    xd, wd, bd, rd = dev(x, cuda), dev(w, cuda), dev(b, cuda), dev(res, cuda)
+    has_res = variant.startswith("res")
+    spec = ops.ConvSpec(3, 64, 64, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
+                        act=0 if has_res else 2, alpha=0.2)
+    x_hi, _ = ops.pack_act_pad16(xd)
+    w_hi, _ = ops.pack_weights_umma(wd, ndim=3)
+    r_hi, r_lo = ops.pack_act_pad16(rd, split=True)
+    if variant == "res16_nolo":
+        r_lo = None
+    if has_res:   # the addend the kernel sees
+        rd_eff = ops.unpack_act_pad16(r_hi, r_lo, 3) if variant != "res_f32" else rd
+    ref = ops.conv_fwd(xd, wd, bd, spec, residual=rd_eff if has_res else None)
+    if variant in ("f32", "res_f32"):
+        y, _, _ = ops.conv_fwd_umma(x_hi, None, w_hi, None, bd, spec, n, dims,
+                                    residual=rd if has_res else None)
+        assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+        return
+    want_lo = variant in ("pad16_lo", "res16")
+    _, y_hi, y_lo = ops.conv_fwd_umma(x_hi, None, w_hi, None, bd, spec, n, dims, want_f32=False,
+                                      want_pad16=True, want_lo=want_lo,
+                                      res_hi=r_hi if has_res else None,
+                                      res_lo=r_lo if has_res else None)
+    ref_hi, ref_lo = ops.pack_act_pad16(ref, split=True)
+    scale = float(ref.abs().max())
+    # hi: bf16 rounding of an fp32 sum that may differ in the last bits -> allow one bf16 ulp
+    dh = (y_hi.float() - ref_hi.float()).abs().max().item()
+    assert dh <= scale * 2.0 ** -7, dh
+    frac_equal = (y_hi == ref_hi).float().mean().item()
+    assert frac_equal > 0.999, frac_equal
+    if want_lo:
+        got = ops.unpack_act_pad16(y_hi, y_lo, 3)
+        assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 5e-5
+        full = y_hi.float() + y_lo.float()
+        full_ref = ref_hi.float() + ref_lo.float()
+        assert (full - full_ref).abs().max().item() <= scale * 1e-4   # halos of hi + lo too
