@@ -59,6 +59,33 @@ static int encode_map(CUtensorMap* tm, const void* base, int fmt, int rank, cons
   return S3_OK;
 }
 
+static int encode_map_strided(CUtensorMap* tm, const void* base, int fmt, int rank,
+                              const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return S3_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i < rank - 1) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(tm, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (strided) failed with %d (rank %d)", (int)r, rank);
+    return S3_ERR_CUDA;
+  }
+  return S3_OK;
+}
+
 static DebugRec* debug_rec() {
   static DebugRec* host = nullptr;
   static DebugRec* dev = nullptr;
@@ -153,7 +180,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
                           g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.fd[0] >= 4 && g.fd[1] >= 4 &&
                           g.fd[2] >= 4 && !post_scale;
     p.epi_v2 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
-                p.planes >= 4) ? 1 : 0;
+                p.planes >= 4) ? ((t.box_y & 128) ? 1 : 2) : 0;
     S3_REQUIRE(!res_hi || p.epi_v2, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
                "64-channel 16-bit-output configuration");
     const uint32_t stage_bytes = p.epi_v2 ? 16384u : 0u;
@@ -263,8 +290,27 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
              g.cstride % 4 == 0 && g.coff % 4 == 0) {
     epi = EPI_D2S;
   }
-  if (zring)
-    rc = launch_umma_zring(p, tm_a_hi, tm_w_hi, epi, ctas, smem, as_stream(stream));
+  if (zring) {
+    CUtensorMap em[4];
+    memset(em, 0, sizeof(em));
+    if (p.epi_v2 == 2) {
+      // interior views (x + 1, y + 1) of the padded tensors: tile coordinates are plain voxel
+      // indices, ragged tiles are clipped by the map extents
+      const uint64_t edims[4] = {64, (uint64_t)g.fd[2], (uint64_t)g.fd[1], total_planes};
+      const uint64_t estr[3] = {128, (uint64_t)(g.fd[2] + 2) * 128,
+                                (uint64_t)(g.fd[1] + 2) * (g.fd[2] + 2) * 128};
+      const uint32_t ebox[4] = {64, 8, 2, 1};
+      const size_t shift = ((size_t)(g.fd[2] + 2) + 1) * 128;
+      const void* ptrs[4] = {res_hi, res_lo, y_hi, y_lo};
+      for (int i = 0; i < 4; ++i) {
+        if (!ptrs[i]) continue;
+        if ((rc = encode_map_strided(&em[i], static_cast<const uint8_t*>(ptrs[i]) + shift, t.fmt, 4,
+                                     edims, estr, ebox)))
+          return rc;
+      }
+    }
+    rc = launch_umma_zring(p, tm_a_hi, tm_w_hi, em, epi, ctas, smem, as_stream(stream));
+  }
   else if (zcat)
     rc = launch_umma_zcat(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
                           as_stream(stream));

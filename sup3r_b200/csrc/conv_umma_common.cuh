@@ -26,7 +26,7 @@ struct UmmaParams {
   DebugRec* dbg;
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
   int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
-  int epi_v2;         // zring: coalescing 16-bit epilogue (conv_umma_zring.cu)
+  int epi_v2;         // zring 16-bit epilogue: 0 thread-per-row, 1 LSU-coalescing, 2 TMA tile I/O
   int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
 };
 
@@ -158,8 +158,9 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const SmemMap
 int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st);
-int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w, int epi,
-                      int ctas, uint32_t smem, cudaStream_t st);
+int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w,
+                      const CUtensorMap* epi_maps /* res_hi, res_lo, y_hi, y_lo or NULL */,
+                      int epi, int ctas, uint32_t smem, cudaStream_t st);
 int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st);

@@ -29,6 +29,11 @@ constexpr int RB_WEMPTY = RB_WFULL + kRingMaxWS;
 constexpr int RB_ACCFULL = RB_WEMPTY + kRingMaxWS;
 constexpr int RB_ACCEMPTY = RB_ACCFULL + 2;
 constexpr int RB_TMEMPTR = RB_ACCEMPTY + 2;
+constexpr int RB_EPILD = RB_TMEMPTR + 2;     // 8 per-warp residual load barriers (TMA epilogue)
+
+struct EpiMaps {
+  CUtensorMap res_hi, res_lo, y_hi, y_lo;   // interior views, box 64 x 8 x 2 x 1 (TMA epilogue)
+};
 
 template <int N>
 __device__ __forceinline__ void reg_dec() {
@@ -37,6 +42,13 @@ __device__ __forceinline__ void reg_dec() {
 template <int N>
 __device__ __forceinline__ void reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// bounded spin without clock reads (one try_wait + branch on the hot path)
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t n = 0; !mbar_try_wait(bar, parity); ++n)
+    if (n > (1u << 26)) __trap();
 }
 
 struct RingItem {
@@ -344,6 +356,155 @@ __device__ __forceinline__ void ring_epilogue_warp_v2(const ConvGeom& g, const E
   }
 }
 
+// ------------------------------------------------------------------------- TMA epilogue
+// Same job as ring_epilogue_warp_v2, but every bulk transfer goes through the TMA unit, whose
+// shared-memory traffic was measured NOT to slow the MMA stream (the plane / weight loads are
+// free), unlike LSU wavefronts (~2 MMA cycles lost per wavefront).  Per warp: one 2 KiB
+// SWIZZLE_128B staging box = 2 y rows x 8 x voxels x 64 channels; the 32 accumulator rows of the
+// warp go through it in two halves.  Residual halves are TMA-loaded (mbarrier), output halves
+// TMA-stored (bulk group), incl. the z mirror (same box, plane +-2).  The y / x REFLECT mirrors
+// (rows y = 1, FY-2 / voxels x = 1, FX-2 only) are stored from registers.
+struct EpiTma {
+  const CUtensorMap* res[2];   // hi, lo (interior view of the padded 16-bit tensor)
+  const CUtensorMap* out[2];
+  uint32_t stage_s;            // shared address of this warp's staging box (1 KiB aligned)
+  uint8_t* stage;              // generic pointer to the same
+  uint32_t bar;                // this warp's load barrier
+  uint32_t phase;
+  bool trace;                  // role timing (CTA 0, first epilogue warp)
+  long long t_load, t_store;
+};
+
+template <bool kRes>
+__device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const Epilogue& ep,
+                                                      const float* sbias, uint32_t t_addr,
+                                                      const TileGeom& tg, int plane_coord,
+                                                      int mz_planes, EpiTma& et, int lane) {
+  const int fmt = ep.fmt;
+  const int FY = g.fd[1], FX = g.fd[2];
+  const int h_of_lane = lane >> 4, rrow = lane & 15;
+  const int yl = lane >> 3, xl = lane & 7;
+  const int y = tg.y0 + yl, x = tg.x0 + xl;
+  const bool row_valid = y < FY && x < FX;
+  const bool has_lo = ep.y_lo != nullptr;
+  const bool res_has_lo = kRes && ep.res_lo != nullptr;
+
+  auto issue_res = [&](int op, int h) {
+    if (lane == 0) {
+      mbar_expect_tx(et.bar, 2048u);
+      tma_load_4d(et.stage_s, et.res[op], et.bar, 0, tg.x0, tg.y0 + 2 * h, plane_coord);
+    }
+  };
+  if (kRes) issue_res(0, 0);
+
+  float v[64];
+  {
+    uint32_t raw[64];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      tmem_ld16(t_addr + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[cc * 16]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * q);
+      v[4 * q] = __uint_as_float(raw[4 * q]) + bv.x;
+      v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bv.y;
+      v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bv.z;
+      v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bv.w;
+    }
+  }
+  if (g.act == S3_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
+  } else if (g.act == S3_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (g.act != S3_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+  }
+
+  if (kRes) {
+    const int n_rounds = res_has_lo ? 4 : 2;
+#pragma unroll
+    for (int rnd = 0; rnd < 4; ++rnd) {
+      if (rnd < n_rounds) {
+        const int h = rnd & 1;
+        const long long tl0 = et.trace ? clock64() : 0;
+        mbar_wait_lean(et.bar, et.phase);
+        if (et.trace) et.t_load += clock64() - tl0;
+        et.phase ^= 1u;
+        if (h_of_lane == h) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(et.stage + stage_off(rrow, k));
+            unpack_add8(&v[8 * k], u, fmt);
+          }
+        }
+        __syncwarp();
+        if (rnd + 1 < n_rounds) issue_res((rnd + 1) >> 1, (rnd + 1) & 1);
+      }
+    }
+  }
+
+  const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * 128;
+  const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
+  const long long mx = x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL);
+  const long long mzb = (long long)mz_planes * tg.sz;
+#pragma unroll
+  for (int op = 0; op < 2; ++op) {
+    if (op == 0 || has_lo) {
+      uint4 hrow[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xv = v[8 * k + j];
+          a[j] = op == 0 ? xv : xv - from16(to16(xv, fmt), fmt);
+        }
+        hrow[k].x = pack2(a[0], a[1], fmt);
+        hrow[k].y = pack2(a[2], a[3], fmt);
+        hrow[k].z = pack2(a[4], a[5], fmt);
+        hrow[k].w = pack2(a[6], a[7], fmt);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h_of_lane == h) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(et.stage + stage_off(rrow, k)) = hrow[k];
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(et.out[op], et.stage_s, 0, tg.x0, tg.y0 + 2 * h, plane_coord);
+          if (mz_planes != 0)
+            tma_store_4d(et.out[op], et.stage_s, 0, tg.x0, tg.y0 + 2 * h, plane_coord + mz_planes);
+          tma_store_commit();
+          const long long ts0 = et.trace ? clock64() : 0;
+          tma_store_wait_read();
+          if (et.trace) et.t_store += clock64() - ts0;
+        }
+        __syncwarp();
+      }
+      // y / x halo mirrors of this row (and their z-mirrored copies)
+      if (row_valid && (my | mx) != 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(op == 0 ? ep.y_hi : ep.y_lo) + row_off;
+#pragma unroll 1
+        for (int combo = 1; combo < 8; ++combo) {
+          const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+          if (!(bq || cq)) continue;
+          if ((a && mzb == 0) || (bq && my == 0) || (cq && mx == 0)) continue;
+          uint4* d = reinterpret_cast<uint4*>(dst + (a ? mzb : 0) + (bq ? my : 0) + (cq ? mx : 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = hrow[k];
+        }
+      }
+    }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void ring_epilogue_tile(const UmmaParams& p, const float* sbias,
                                                    const RingItem& c, int r, uint32_t t_addr,
@@ -410,13 +571,6 @@ __device__ __forceinline__ void ring_issue_slab_fast_sw(int slot0, uint32_t a_ta
     case 5: ring_issue_slab_fast<5, kLast>(a_tap, wl, hi_a, hi_b, acc0, id1, id2, id3, keep_tail, pempty0); break;
     default: ring_issue_slab_fast<6, kLast>(a_tap, wl, hi_a, hi_b, acc0, id1, id2, id3, keep_tail, pempty0); break;
   }
-}
-
-// bounded spin without clock reads (one try_wait + branch on the hot path)
-__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  for (uint32_t n = 0; !mbar_try_wait(bar, parity); ++n)
-    if (n > (1u << 26)) __trap();
 }
 
 // MMA role for the hot configuration (every item has R = 4 output planes, npad = 64, 18 x 10
@@ -540,7 +694,8 @@ __device__ __forceinline__ void ring_mma_fast(const UmmaParams& p, uint32_t bar_
 template <int kR, int EPI>
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
-                       const __grid_constant__ CUtensorMap tm_w, const UmmaParams p) {
+                       const __grid_constant__ CUtensorMap tm_w,
+                       const __grid_constant__ EpiMaps em, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t plane_bytes = (uint32_t)p.YB * p.XB * 128u;
@@ -567,6 +722,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       mbar_init(bar(RB_ACCFULL + i), 1);
       mbar_init(bar(RB_ACCEMPTY + i), 8);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(bar(RB_EPILD + i), 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x)
@@ -746,6 +902,15 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     reg_inc<216>();
     const int wg = (warp - 4) >> 2, q = warp & 3;
     int ab = 0, abph = 0;
+    EpiTma et;
+    et.res[0] = &em.res_hi; et.res[1] = &em.res_lo;
+    et.out[0] = &em.y_hi; et.out[1] = &em.y_lo;
+    et.stage_s = bar_base + 2048u + (uint32_t)(warp - 4) * 2048u;
+    et.stage = smem_raw + (et.stage_s - smem_u32(smem_raw));
+    et.bar = bar(RB_EPILD + warp - 4);
+    et.phase = 0;
+    et.trace = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+    et.t_load = et.t_store = 0;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
     long long t_wait = 0, t_work = 0;
     for (int i = i0; i < i1; ++i) {
@@ -755,7 +920,30 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       long long c1 = tr ? clock64() : 0;
       if (tr) t_wait += c1 - c0;
       tc_fence_after();
-      if (EPI == EPI_V2) {
+      if (EPI == EPI_V3) {
+        if (!(p.dbg_flags & 8)) {
+          const ConvGeom& g = p.g;
+          TileGeom tg;
+          tg.sy = (long long)(g.fd[2] + 2) * 128;
+          tg.sz = (long long)(g.fd[1] + 2) * tg.sy;
+          tg.y0 = c.yb * 16 + q * 4;
+          tg.x0 = c.xb * 8;
+          tg.mz = 0;
+          for (int r = wg; r < c.ri; r += 2) {
+            const int z = c.pl0 + r;
+            const int plane_coord = c.b * (g.fd[0] + 2) + z + 1;
+            tg.base = (((long long)plane_coord * (g.fd[1] + 2) + tg.y0 + 1) * (g.fd[2] + 2) +
+                       tg.x0 + 1) * 128;
+            const int mzp = z == 1 ? -2 : (z == g.fd[0] - 2 ? 2 : 0);
+            const uint32_t ta = tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)) +
+                                ((uint32_t)(q * 32) << 16);
+            if (p.ep.res_hi)
+              ring_epilogue_warp_v3<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+            else
+              ring_epilogue_warp_v3<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+          }
+        }
+      } else if (EPI == EPI_V2) {
         if (!(p.dbg_flags & 8)) {
         const ConvGeom& g = p.g;
         uint8_t* stage = smem_raw + (bar_base + 2048u - smem_u32(smem_raw)) + (warp - 4) * 2048;
@@ -779,7 +967,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
         }
       } else if (!(p.dbg_flags & 8)) {
         for (int r = wg; r < c.ri; r += 2)
-          ring_epilogue_tile<EPI == EPI_V2 ? EPI_PLAIN : EPI>(
+          ring_epilogue_tile<(EPI == EPI_V2 || EPI == EPI_V3) ? EPI_PLAIN : EPI>(
               p, sbias, c, r, tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)), q, lane);
       }
       tc_fence_before();
@@ -788,7 +976,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       if (++ab == 2) { ab = 0; abph ^= 1; }
       if (tr) t_work += clock64() - c1;
     }
-    if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; }
+    if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; p.trace[10] = et.t_load; p.trace[11] = et.t_store; }
   }
   tc_fence_before();
   __syncthreads();
@@ -797,24 +985,31 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
 
 template <int kR, int EPI>
 static int launch_zring_t(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w,
-                          int ctas, uint32_t smem, cudaStream_t st) {
+                          const EpiMaps& em, int ctas, uint32_t smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     S3_CUDA(cudaFuncSetAttribute(conv_umma_zring_kernel<kR, EPI>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr = true;
   }
-  conv_umma_zring_kernel<kR, EPI><<<ctas, kRingThreads, smem, st>>>(a, w, p);
+  conv_umma_zring_kernel<kR, EPI><<<ctas, kRingThreads, smem, st>>>(a, w, em, p);
   S3_CUDA(cudaGetLastError());
   return S3_OK;
 }
 
-int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w, int epi,
-                      int ctas, uint32_t smem, cudaStream_t st) {
-  if (p.epi_v2 && p.R == 4) return launch_zring_t<4, EPI_V2>(p, a, w, ctas, smem, st);
-  if (epi == EPI_PLAIN && p.R == 4) return launch_zring_t<4, EPI_PLAIN>(p, a, w, ctas, smem, st);
-  if (epi == EPI_PLAIN) return launch_zring_t<0, EPI_PLAIN>(p, a, w, ctas, smem, st);
-  return launch_zring_t<0, EPI_GENERIC>(p, a, w, ctas, smem, st);
+int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w,
+                      const CUtensorMap* epi_maps, int epi, int ctas, uint32_t smem,
+                      cudaStream_t st) {
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (epi_maps) {
+    em.res_hi = epi_maps[0]; em.res_lo = epi_maps[1]; em.y_hi = epi_maps[2]; em.y_lo = epi_maps[3];
+  }
+  if (p.epi_v2 == 2 && p.R == 4) return launch_zring_t<4, EPI_V3>(p, a, w, em, ctas, smem, st);
+  if (p.epi_v2 == 1 && p.R == 4) return launch_zring_t<4, EPI_V2>(p, a, w, em, ctas, smem, st);
+  if (epi == EPI_PLAIN && p.R == 4) return launch_zring_t<4, EPI_PLAIN>(p, a, w, em, ctas, smem, st);
+  if (epi == EPI_PLAIN) return launch_zring_t<0, EPI_PLAIN>(p, a, w, em, ctas, smem, st);
+  return launch_zring_t<0, EPI_GENERIC>(p, a, w, em, ctas, smem, st);
 }
 
 }  // namespace s3

@@ -267,14 +267,14 @@ class Plan:
                         cur = self._run_conv(st, cur, skips, steps, si, split, ps, pf)
                         applied_post = applied_post or (last and ps is not None)
                     elif isinstance(st, SkipStep):
-                        t = cur.need_f32()
                         if st.store:
-                            skips[st.name] = t
+                            skips[st.name] = cur
                         else:
+                            t = cur.need_f32()
                             cache = skips.pop(st.name)
                             if tuple(cache.shape) != tuple(t.shape):
                                 raise RuntimeError(f'SkipConnection "{st.name}" shape mismatch')
-                            cur = Act(t.shape, f32=ops.add(t, cache))
+                            cur = Act(t.shape, f32=ops.add(t, cache.need_f32()))
                     else:
                         lyr = st.layer
                         t = cur.need_f32()
@@ -323,33 +323,52 @@ class Plan:
         n, dims, cin, ndim = ops.dims3(shp)
         _, od, oc = spec.out_dims(n, dims)
         out_shape = ops._shape_from(n, od, oc, ndim)
-        residual = None
+        res_act = None
         if st.skip_add is not None:
-            residual = skips.pop(st.skip_add)
-            if tuple(residual.shape) != tuple(out_shape):
+            res_act = skips.pop(st.skip_add)
+            if tuple(res_act.shape) != tuple(out_shape):
                 raise RuntimeError(f'SkipConnection "{st.skip_add}" shape mismatch: '
-                                   f"{tuple(residual.shape)} vs {tuple(out_shape)}")
+                                   f"{tuple(res_act.shape)} vs {tuple(out_shape)}")
         plain = st.r == 1 and st.m == 1 or (st.m > 1 and st.method == 0 and st.r == 1)
         want16 = plain and self._next_wants_pad16(steps, si, out_shape)
-        want32 = (not want16) or bool(st.skip_store) or si == len(steps) - 1
+        last = si == len(steps) - 1
+        # SkipConnection caches travel as a 16-bit (hi, lo) pair in the padded layout when the
+        # producer writes 16-bit output anyway: hi is the next convolution's operand, hi + lo
+        # (~16 mantissa bits) is the addend of the consuming convolution's epilogue
+        # (phygnn SkipConnection semantics, call site sup3r/models/abstract.py:1081-1092)
+        pair_skip = want16 and bool(st.skip_store) and not split
+        want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
         if _umma_ok(st, shp, self.precision):
             x_hi, x_lo = cur.need_pad16(split)
             w_hi, w_lo = self._packed(conv, split)
+            res16 = (res_act is not None and not split and not want32 and want16
+                     and self._ring16_ok(st, out_shape) and post_scale is None
+                     and res_act.hi is not None)
             y, y_hi, y_lo = ops.conv_fwd_umma(
-                x_hi, x_lo, w_hi, w_lo, bias, spec, n, dims, residual=residual,
+                x_hi, x_lo, w_hi, w_lo, bias, spec, n, dims,
+                residual=None if (res16 or res_act is None) else res_act.need_f32(),
+                res_hi=res_act.hi if res16 else None, res_lo=res_act.lo if res16 else None,
                 post_scale=post_scale, post_shift=post_shift, want_f32=want32,
-                want_pad16=want16)
+                want_pad16=want16, want_lo=pair_skip)
         else:
             x = cur.need_f32()
-            res = ops.conv_fwd(x, conv.conv_kernel().detach(), bias, spec, residual=residual,
+            res = ops.conv_fwd(x, conv.conv_kernel().detach(), bias, spec,
+                               residual=None if res_act is None else res_act.need_f32(),
                                post_scale=post_scale, post_shift=post_shift,
-                               want_pad16=want16, split=split, want_f32=want32)
+                               want_pad16=want16, split=split or pair_skip, want_f32=want32)
             y, y_hi, y_lo = res if want16 else (res, None, None)
         out = Act(out_shape, f32=y, hi=y_hi, lo=y_lo)
         for name in st.skip_store:
-            skips[name] = out.need_f32()
+            skips[name] = out
         return out
+
+    @staticmethod
+    def _ring16_ok(st, out_shape):
+        """Host mirror of the C side's conditions for the ring kernel's 16-bit tile epilogue
+        (s3_conv_fwd_umma: 3-D, 64 -> 64 channels, plain output map, extents >= 4)."""
+        return (len(out_shape) == 5 and out_shape[-1] == 64 and st.r == 1 and st.m == 1
+                and min(out_shape[1:-1]) >= 4)
 
     # -- training forward (autograd) -------------------------------------------------
     def forward_train(self, x, exo=None):

@@ -427,7 +427,7 @@ def test_umma_conv_matches_direct(cuda, n, dims, variant):
     dh = (y_hi.float() - ref_hi.float()).abs().max().item()
     assert dh <= scale * 2.0 ** -7, dh
     frac_equal = (y_hi == ref_hi).float().mean().item()
-    assert frac_equal > 0.999, frac_equal
+    assert frac_equal > 0.995, frac_equal
     if want_lo:
         got = ops.unpack_act_pad16(y_hi, y_lo, 3)
         assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 5e-5
