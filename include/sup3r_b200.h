@@ -103,6 +103,18 @@ int s3_conv_fwd_f32(const s3_conv_desc* d, const float* x, const float* w, const
                     const float* residual, const float* post_scale, const float* post_shift,
                     float* y, void* y_hi, void* y_lo, s3_stream stream);
 
+/* Narrow 3-D convolution (3x3x3, stride 1, pad 1, cin <= 8, cout <= 8, plain output map) on
+ * the warp-level tensor cores: x and w are rounded to bf16, products accumulate in fp32.  The
+ * single-pass "bf16" precision mode uses it for the generators' high-resolution output
+ * convolution (last FlexiblePadding -> Conv3D -> Cropping3D of
+ * sup3r/configs/spatiotemporal/gen_*.json); same operands / epilogue as s3_conv_fwd_f32.
+ * Input: x (f32) or x_bf16 (unpadded (n, z, y, x, 8) bf16, e.g. the 16-bit depth_to_space
+ * destination of s3_conv_fwd_umma) -- exactly one of the two. */
+int s3_conv_fwd_small_bf16(const s3_conv_desc* d, const float* x, const void* x_bf16,
+                           const float* w, const float* bias, const float* residual,
+                           const float* post_scale, const float* post_shift, float* y,
+                           s3_stream stream);
+
 /* Adjoint of the convolution w.r.t. its input: dy in conv-output geometry -> dx (n,z,y,x,cin).
  * Stands in for tape.gradient through keras Conv* (abstract.py:1230-1238). */
 int s3_conv_dgrad_f32(const s3_conv_desc* d, const float* dy, const float* w, float* dx,
@@ -117,7 +129,9 @@ int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, fl
  * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single-pass bf16, else the
  * 3-pass split-precision product hi*hi + lo*hi + hi*lo).  w_hi/w_lo: from s3_pack_weights_umma.
  * The SkipConnection addend is either `residual` (f32, output layout) or the pair res_hi/res_lo
- * (16-bit padded layout of y_hi; value = hi + lo; res_lo may be NULL). */
+ * (16-bit padded layout of y_hi; value = hi + lo; res_lo may be NULL).
+ * y_hi: padded+mirrored 16-bit destination for plain output maps; for depth_to_space /
+ * depth_to_time maps (8-channel runs) an UNPADDED 16-bit tensor of the mapped geometry. */
 int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi,
                      const void* w_lo, const float* bias, const float* residual,
                      const void* res_hi, const void* res_lo, const float* post_scale,

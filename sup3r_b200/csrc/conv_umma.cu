@@ -61,7 +61,7 @@ static int encode_map(CUtensorMap* tm, const void* base, int fmt, int rank, cons
 
 static int encode_map_strided(CUtensorMap* tm, const void* base, int fmt, int rank,
                               const uint64_t* dims, const uint64_t* strides_bytes,
-                              const uint32_t* box) {
+                              const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -77,7 +77,7 @@ static int encode_map_strided(CUtensorMap* tm, const void* base, int fmt, int ra
   }
   CUresult r = enc(tm, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (strided) failed with %d (rank %d)", (int)r, rank);
@@ -135,8 +135,14 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   S3_REQUIRE(g.in[1] >= 2 && g.in[2] >= 2 && (kz == 1 || g.in[0] >= 2),
              "s3_conv_fwd_umma: reflect-1 needs extents >= 2");
-  if (y_hi) S3_REQUIRE(g.fd[1] >= 2 && g.fd[2] >= 2, "s3_conv_fwd_umma: padded output too small");
-  if (y_hi) S3_REQUIRE(g.r == 1 && g.m == 1, "s3_conv_fwd_umma: 16-bit output needs a plain map");
+  const bool mapped16 = y_hi && (g.r > 1 || g.m > 1);   // unpadded 16-bit mapped destination
+  if (y_hi && !mapped16)
+    S3_REQUIRE(g.fd[1] >= 2 && g.fd[2] >= 2, "s3_conv_fwd_umma: padded output too small");
+  if (mapped16)
+    S3_REQUIRE(!y_lo && g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.cmap == 8 && g.cout % 8 == 0 &&
+                   g.cstride % 8 == 0 && g.coff % 8 == 0 && !post_scale && !residual && !res_hi,
+               "s3_conv_fwd_umma: a 16-bit depth_to_space destination needs 8-channel runs, "
+               "aligned strides and no lo / residual / affine");
 
   s3_umma_tuning t;
   memset(&t, 0, sizeof(t));
@@ -183,7 +189,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
                 p.planes >= 4) ? ((t.box_y & 128) ? 1 : 2) : 0;
     S3_REQUIRE(!res_hi || p.epi_v2, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
                "64-channel 16-bit-output configuration");
-    const uint32_t stage_bytes = p.epi_v2 ? 16384u : 0u;
+    // residual layers keep two transfers per warp in flight (costs one plane slot: P = 6)
+    p.epi_bufs = (p.epi_v2 == 2 && res_hi && !(t.box_y & 256)) ? 2 : 1;
+    const uint32_t stage_bytes = p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u;
     int P = (int)((kSmemLimit - fixed - 1024u - stage_bytes - (uint32_t)ws * w_slab) / plane);
     if (P > 8) P = 8;
     if (t.ring_slots > 0 && t.ring_slots < P) P = t.ring_slots;
@@ -191,7 +199,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     S3_REQUIRE(R >= 1, "s3_conv_fwd_umma: zring does not fit shared memory (npad %d)", p.npad);
     p.flat = 0; p.R = R; p.YB = 18; p.ZB = 1; p.TS = 18; p.WS = ws; p.AS = P;
     p.dbg_flags = t.box_y;   // zring: box_y carries experiment flags (see kernel)
-    p.ring_fast = (R == 4 && p.planes % 4 == 0 && p.npad == 64 && p.XB == 10 && P == 7 && ws == 2 &&
+    p.ring_fast = (R == 4 && p.planes % 4 == 0 && p.npad == 64 && p.XB == 10 && (P == 7 || P == 6) && ws == 2 &&
                    !(p.dbg_flags & 16)) ? 1 : 0;
     p.box_bytes = plane; p.box_stride = plane;
     found = true;
@@ -275,7 +283,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
   if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed +
-                    (p.epi_v2 ? 16384u : 0u);
+                    (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u);
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
   // epilogue specialisation: fast paths only when their preconditions hold for EVERY row
@@ -285,7 +293,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   const bool roomy = g.fd[1] >= 4 && g.fd[2] >= 4 && (g.ndim == 2 || g.fd[0] >= 4);
   if (plain && aligned && roomy && g.cout % 16 == 0 && !post_scale) {
     epi = EPI_PLAIN;
-  } else if ((g.r > 1 || g.m > 1) && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !y_hi && y &&
+  } else if ((g.r > 1 || g.m > 1) && g.rep[0] * g.rep[1] * g.rep[2] == 1 && (y || mapped16) &&
+             (!y_hi || mapped16) &&
              (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && g.cout % g.cmap == 0 &&
              g.cstride % 4 == 0 && g.coff % 4 == 0) {
     epi = EPI_D2S;
@@ -299,13 +308,13 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
       const uint64_t edims[4] = {64, (uint64_t)g.fd[2], (uint64_t)g.fd[1], total_planes};
       const uint64_t estr[3] = {128, (uint64_t)(g.fd[2] + 2) * 128,
                                 (uint64_t)(g.fd[1] + 2) * (g.fd[2] + 2) * 128};
-      const uint32_t ebox[4] = {64, 8, 2, 1};
+      const uint32_t ebox[4] = {32, 8, 4, 1};   // one warp's 32 rows x 32 channels, SWIZZLE_64B
       const size_t shift = ((size_t)(g.fd[2] + 2) + 1) * 128;
       const void* ptrs[4] = {res_hi, res_lo, y_hi, y_lo};
       for (int i = 0; i < 4; ++i) {
         if (!ptrs[i]) continue;
         if ((rc = encode_map_strided(&em[i], static_cast<const uint8_t*>(ptrs[i]) + shift, t.fmt, 4,
-                                     edims, estr, ebox)))
+                                     edims, estr, ebox, CU_TENSOR_MAP_SWIZZLE_64B)))
           return rc;
       }
     }

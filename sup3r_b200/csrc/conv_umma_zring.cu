@@ -29,7 +29,7 @@ constexpr int RB_WEMPTY = RB_WFULL + kRingMaxWS;
 constexpr int RB_ACCFULL = RB_WEMPTY + kRingMaxWS;
 constexpr int RB_ACCEMPTY = RB_ACCFULL + 2;
 constexpr int RB_TMEMPTR = RB_ACCEMPTY + 2;
-constexpr int RB_EPILD = RB_TMEMPTR + 2;     // 8 per-warp residual load barriers (TMA epilogue)
+constexpr int RB_EPILD = RB_TMEMPTR + 2;     // 2 x 8 per-warp residual load barriers (TMA epilogue)
 
 struct EpiMaps {
   CUtensorMap res_hi, res_lo, y_hi, y_lo;   // interior views, box 64 x 8 x 2 x 1 (TMA epilogue)
@@ -367,13 +367,23 @@ __device__ __forceinline__ void ring_epilogue_warp_v2(const ConvGeom& g, const E
 struct EpiTma {
   const CUtensorMap* res[2];   // hi, lo (interior view of the padded 16-bit tensor)
   const CUtensorMap* out[2];
-  uint32_t stage_s;            // shared address of this warp's staging box (1 KiB aligned)
-  uint8_t* stage;              // generic pointer to the same
-  uint32_t bar;                // this warp's load barrier
-  uint32_t phase;
+  uint32_t stage_s0, stage_s1; // shared addresses of this warp's staging boxes (1 KiB aligned)
+  uint8_t *stage0, *stage1;    // generic pointers to the same
+  uint32_t bar0, bar1;         // load barrier of each box
+  uint32_t phase0, phase1;     // (scalars, not arrays: a runtime box index must not force the
+                               //  struct into local memory)
+  int nb;                      // boxes in use: 1, or 2 (residual layers: two transfers in flight)
   bool trace;                  // role timing (CTA 0, first epilogue warp)
   long long t_load, t_store;
+  long long t_ph[4];           // tmem load, bias + act, residual, output
+  int dbg;
 };
+
+// staging box: [32 rows (4 y x 8 x)][32 channels = 64 B], SWIZZLE_64B (16-byte chunk index XOR
+// bits 7..8 of the address): conflict-free for thread-per-row 16-byte accesses
+__device__ __forceinline__ uint32_t stage64_off(int row, int k) {
+  return (uint32_t)(row * 64 + ((k ^ ((row >> 1) & 3)) << 4));
+}
 
 template <bool kRes>
 __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const Epilogue& ep,
@@ -382,21 +392,38 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
                                                       int mz_planes, EpiTma& et, int lane) {
   const int fmt = ep.fmt;
   const int FY = g.fd[1], FX = g.fd[2];
-  const int h_of_lane = lane >> 4, rrow = lane & 15;
   const int yl = lane >> 3, xl = lane & 7;
   const int y = tg.y0 + yl, x = tg.x0 + xl;
   const bool row_valid = y < FY && x < FX;
   const bool has_lo = ep.y_lo != nullptr;
   const bool res_has_lo = kRes && ep.res_lo != nullptr;
+  const int nb = et.nb;
 
-  auto issue_res = [&](int op, int h) {
+  // the staging boxes may still be read by the previous tile's stores
+  if (lane == 0) {
+    const long long ts0 = et.trace ? clock64() : 0;
+    tma_store_wait_read();
+    if (et.trace) et.t_store += clock64() - ts0;
+  }
+  __syncwarp();
+
+  // round r of a 4-round sequence: operand r >> 1 (hi, lo), channel half r & 1, box r % nb
+  auto issue_res = [&](int r) {
     if (lane == 0) {
-      mbar_expect_tx(et.bar, 2048u);
-      tma_load_4d(et.stage_s, et.res[op], et.bar, 0, tg.x0, tg.y0 + 2 * h, plane_coord);
+      const int bi = nb == 2 ? (r & 1) : 0;
+      const uint32_t lb = bi ? et.bar1 : et.bar0;
+      mbar_expect_tx(lb, 2048u);
+      tma_load_4d(bi ? et.stage_s1 : et.stage_s0, (r >> 1) ? et.res[1] : et.res[0], lb,
+                  32 * (r & 1), tg.x0, tg.y0, plane_coord);
     }
   };
-  if (kRes) issue_res(0, 0);
+  const int n_res = kRes ? (res_has_lo ? 4 : 2) : 0;
+  if (kRes) {
+    issue_res(0);
+    if (nb == 2) issue_res(1);
+  }
 
+  const long long tp0 = et.trace ? clock64() : 0;
   float v[64];
   {
     uint32_t raw[64];
@@ -404,6 +431,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
     for (int cc = 0; cc < 4; ++cc)
       tmem_ld16(t_addr + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[cc * 16]));
     tmem_ld_wait();
+    if (et.trace) et.t_ph[0] += clock64() - tp0;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const float4 bv = *reinterpret_cast<const float4*>(sbias + 4 * q);
@@ -424,33 +452,36 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
     for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
   }
 
+  const long long tp1 = et.trace ? clock64() : 0;
+  if (et.trace) et.t_ph[1] += tp1 - tp0;
   if (kRes) {
-    const int n_rounds = res_has_lo ? 4 : 2;
 #pragma unroll
-    for (int rnd = 0; rnd < 4; ++rnd) {
-      if (rnd < n_rounds) {
-        const int h = rnd & 1;
+    for (int r = 0; r < 4; ++r) {
+      if (r < n_res) {
+        const int bi = nb == 2 ? (r & 1) : 0;
         const long long tl0 = et.trace ? clock64() : 0;
-        mbar_wait_lean(et.bar, et.phase);
+        mbar_wait_lean(bi ? et.bar1 : et.bar0, bi ? et.phase1 : et.phase0);
         if (et.trace) et.t_load += clock64() - tl0;
-        et.phase ^= 1u;
-        if (h_of_lane == h) {
+        if (bi) et.phase1 ^= 1u; else et.phase0 ^= 1u;
+        const uint8_t* sb = bi ? et.stage1 : et.stage0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint4 u = *reinterpret_cast<const uint4*>(et.stage + stage_off(rrow, k));
-            unpack_add8(&v[8 * k], u, fmt);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sb + stage64_off(lane, k));
+          unpack_add8(&v[32 * (r & 1) + 8 * k], u, fmt);
         }
         __syncwarp();
-        if (rnd + 1 < n_rounds) issue_res((rnd + 1) >> 1, (rnd + 1) & 1);
+        if (r + nb < n_res) issue_res(r + nb);
       }
     }
   }
 
+  const long long tp2 = et.trace ? clock64() : 0;
+  if (et.trace) et.t_ph[2] += tp2 - tp1;
   const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * 128;
   const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
   const long long mx = x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL);
   const long long mzb = (long long)mz_planes * tg.sz;
+  const int n_out = has_lo ? 4 : 2;
 #pragma unroll
   for (int op = 0; op < 2; ++op) {
     if (op == 0 || has_lo) {
@@ -469,27 +500,35 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
         hrow[k].w = pack2(a[6], a[7], fmt);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h_of_lane == h) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int r = 2 * op + c2;
+        const int bi = nb == 2 ? (r & 1) : 0;
+        // box reuse inside the tile: the store issued nb rounds ago must have read it
+        if (r >= nb) {
+          if (lane == 0) {
+            const long long ts0 = et.trace ? clock64() : 0;
+            if (nb == 2) tma_store_wait_read1(); else tma_store_wait_read();
+            if (et.trace) et.t_store += clock64() - ts0;
+          }
+          __syncwarp();
+        }
+        uint8_t* sb = bi ? et.stage1 : et.stage0;
+        const uint32_t sbs = bi ? et.stage_s1 : et.stage_s0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<uint4*>(et.stage + stage_off(rrow, k)) = hrow[k];
-        }
-        fence_proxy_async_smem();
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(sb + stage64_off(lane, k)) = hrow[4 * c2 + k];
+        if (!(et.dbg & 512)) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(et.out[op], et.stage_s, 0, tg.x0, tg.y0 + 2 * h, plane_coord);
+        if (lane == 0 && !(et.dbg & 2048)) {
+          tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord);
           if (mz_planes != 0)
-            tma_store_4d(et.out[op], et.stage_s, 0, tg.x0, tg.y0 + 2 * h, plane_coord + mz_planes);
+            tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes);
           tma_store_commit();
-          const long long ts0 = et.trace ? clock64() : 0;
-          tma_store_wait_read();
-          if (et.trace) et.t_store += clock64() - ts0;
         }
-        __syncwarp();
+        (void)n_out;
       }
       // y / x halo mirrors of this row (and their z-mirrored copies)
-      if (row_valid && (my | mx) != 0) {
+      if (row_valid && (my | mx) != 0 && !(et.dbg & 1024)) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(op == 0 ? ep.y_hi : ep.y_lo) + row_off;
 #pragma unroll 1
         for (int combo = 1; combo < 8; ++combo) {
@@ -503,6 +542,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
       }
     }
   }
+  if (et.trace) et.t_ph[3] += clock64() - tp2;
 }
 
 template <int EPI>
@@ -582,16 +622,18 @@ __device__ __forceinline__ void ring_issue_slab_fast_sw(int slot0, uint32_t a_ta
 // line code; the barrier waits for the NEXT slab / item are taken before the last MMA group of
 // the current slab (a N = 192 group, 4 x 96 cycles), so that the first MMA of the next slab
 // follows the last one of this slab back to back.
+template <int kP>
 __device__ __forceinline__ void ring_mma_fast(const UmmaParams& p, uint32_t bar_base,
                                               uint32_t a_base, uint32_t w_base, uint32_t w_slab,
                                               uint32_t tmem_base, int i0, int i1, int lane) {
-  constexpr int kR = 4, kP = 7;
+  constexpr int kR = 4;
   constexpr uint32_t kPlaneLo = (18u * 10u * 128u) >> 4, kBlkLo = (64u * 128u) >> 4;
   // plane order inside a slab: slab 0 ascending (each accumulator block is zero-initialised by
   // its dz = 0 contribution); other slabs end with a N = 192 group; the last slab releases the
   // planes the producer needs first (0, 1, 2) early
+  // (with 6 slots every slot is needed again by the next item: release 0..3 in order)
   constexpr int kOrdMid[6] = {0, 1, 4, 5, 2, 3};
-  constexpr int kOrdLast[6] = {0, 1, 2, 4, 5, 3};
+  constexpr int kOrdLast[6] = {0, 1, 2, kP == 6 ? 3 : 4, 5, kP == 6 ? 4 : 3};
   auto bar = [&](int i) { return bar_base + 8u * i; };
   const uint32_t fmtb = p.fmt == 0 ? 1u : 0u;
   const uint32_t hi_a = sdesc_hi_sw128(1280u), hi_b = sdesc_hi_sw128(1024u);
@@ -722,7 +764,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       mbar_init(bar(RB_ACCFULL + i), 1);
       mbar_init(bar(RB_ACCEMPTY + i), 8);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(bar(RB_EPILD + i), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(bar(RB_EPILD + i), 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x)
@@ -788,7 +830,8 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
         for (int s = 1; s < 9; ++s) load_slab(s, i - i0);
       }
     } else if (warp == 1 && kR == 4 && p.ring_fast) {
-      ring_mma_fast(p, bar_base, a_base, w_base, w_slab, tmem_base, i0, i1, lane);
+      if (P == 6) ring_mma_fast<6>(p, bar_base, a_base, w_base, w_slab, tmem_base, i0, i1, lane);
+      else ring_mma_fast<7>(p, bar_base, a_base, w_base, w_slab, tmem_base, i0, i1, lane);
     } else if (warp == 1) {
       // ---------------------------------------------- MMA issuer (warp-uniform, elected issue)
       int ws = 0, wph = 0, ab = 0, abph = 0;
@@ -905,12 +948,18 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     EpiTma et;
     et.res[0] = &em.res_hi; et.res[1] = &em.res_lo;
     et.out[0] = &em.y_hi; et.out[1] = &em.y_lo;
-    et.stage_s = bar_base + 2048u + (uint32_t)(warp - 4) * 2048u;
-    et.stage = smem_raw + (et.stage_s - smem_u32(smem_raw));
-    et.bar = bar(RB_EPILD + warp - 4);
-    et.phase = 0;
+    et.nb = p.epi_bufs;
+    et.stage_s0 = bar_base + 2048u + (uint32_t)((warp - 4) * et.nb) * 2048u;
+    et.stage_s1 = et.stage_s0 + 2048u;
+    et.stage0 = smem_raw + (et.stage_s0 - smem_u32(smem_raw));
+    et.stage1 = et.stage0 + 2048;
+    et.bar0 = bar(RB_EPILD + 2 * (warp - 4));
+    et.bar1 = et.bar0 + 8u;
+    et.phase0 = et.phase1 = 0;
     et.trace = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
     et.t_load = et.t_store = 0;
+    et.dbg = p.dbg_flags;
+    et.t_ph[0] = et.t_ph[1] = et.t_ph[2] = et.t_ph[3] = 0;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
     long long t_wait = 0, t_work = 0;
     for (int i = i0; i < i1; ++i) {
@@ -976,7 +1025,8 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       if (++ab == 2) { ab = 0; abph ^= 1; }
       if (tr) t_work += clock64() - c1;
     }
-    if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; p.trace[10] = et.t_load; p.trace[11] = et.t_store; }
+    if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; p.trace[10] = et.t_load; p.trace[11] = et.t_store;
+              for (int k = 0; k < 4; ++k) p.trace[12 + k] = et.t_ph[k]; }
   }
   tc_fence_before();
   __syncthreads();

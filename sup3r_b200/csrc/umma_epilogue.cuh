@@ -302,14 +302,53 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
         }
       }
     } else if (EPI == EPI_D2S ||
-               (EPI == EPI_GENERIC && mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 && !ep.y_hi &&
-                ep.y && (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && len % g.cmap == 0)) {
-      // ---- depth_to_space / depth_to_time fast path: runs of cmap channels, f32 only
+               (EPI == EPI_GENERIC && mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 &&
+                (ep.y || ep.y_hi) && (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) &&
+                len % g.cmap == 0)) {
+      // ---- depth_to_space / depth_to_time fast path: runs of cmap channels; f32 (ep.y) or an
+      // unpadded 16-bit mapped tensor (ep.y_hi; 8-channel runs of 8 consecutive x voxels form
+      // full 128-byte lines per warp instruction)
       const int nrun = len / g.cmap;
+      if (g.cmap == 8 && ep.y_hi && !ep.y) {
+        // hot case (5x spatial head -> bf16 high-resolution tensor): static register indices
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s < nrun) {
+            const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + s * 8);
+            const size_t doff = ((((size_t)rp.b * g.fd[0] + d.z) * g.fd[1] + d.y) * g.fd[2] + d.x) *
+                                    g.cstride + g.coff;
+            uint4 u;
+            u.x = pack2(v[8 * s], v[8 * s + 1], ep.fmt);
+            u.y = pack2(v[8 * s + 2], v[8 * s + 3], ep.fmt);
+            u.z = pack2(v[8 * s + 4], v[8 * s + 5], ep.fmt);
+            u.w = pack2(v[8 * s + 6], v[8 * s + 7], ep.fmt);
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.y_hi) + doff) = u;
+          }
+        }
+        continue;
+      }
       for (int s = 0; s < nrun; ++s) {
         const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + s * g.cmap);
-        float* dst = ep.y + ((((size_t)rp.b * g.fd[0] + d.z) * g.fd[1] + d.y) * g.fd[2] + d.x) *
+        const size_t doff = ((((size_t)rp.b * g.fd[0] + d.z) * g.fd[1] + d.y) * g.fd[2] + d.x) *
                                 g.cstride + g.coff;
+        if (ep.y_hi) {
+          uint16_t* d16 = reinterpret_cast<uint16_t*>(ep.y_hi) + doff;
+          const float* vs = v + s * g.cmap;   // (s * cmap is a multiple of 4: register select below)
+          if (g.cmap == 8) {
+            const int o = s * 8;
+            uint4 u;
+            u.x = pack2(o == 0 ? v[0] : v[8], o == 0 ? v[1] : v[9], ep.fmt);
+            u.y = pack2(o == 0 ? v[2] : v[10], o == 0 ? v[3] : v[11], ep.fmt);
+            u.z = pack2(o == 0 ? v[4] : v[12], o == 0 ? v[5] : v[13], ep.fmt);
+            u.w = pack2(o == 0 ? v[6] : v[14], o == 0 ? v[7] : v[15], ep.fmt);
+            *reinterpret_cast<uint4*>(d16) = u;
+          } else {
+            for (int k = 0; k < g.cmap; ++k) d16[k] = to16(v[(s * g.cmap + k) & 15], ep.fmt);
+          }
+          (void)vs;
+          if (!ep.y) continue;
+        }
+        float* dst = ep.y + doff;
         if (g.cmap == 4) {
           float4 o;
           if (s == 0) o = make_float4(v[0], v[1], v[2], v[3]);

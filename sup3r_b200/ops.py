@@ -143,6 +143,40 @@ def conv_fwd(x, w, bias, spec: ConvSpec, residual=None, post_scale=None, post_sh
     return (y, y_hi, y_lo) if want_pad16 else y
 
 
+def small_bf16_ok(spec: ConvSpec):
+    """Shapes s3_conv_fwd_small_bf16 covers (host mirror of the C side's check)."""
+    return (spec.ndim == 3 and spec.cin <= 8 and spec.cout <= 8 and tuple(spec.ksize) == (3, 3, 3)
+            and tuple(spec.stride) == (1, 1, 1) and tuple(spec.pad_lo) == (1, 1, 1)
+            and tuple(spec.pad_hi) == (1, 1, 1) and spec.d2s == 1 and spec.d2t == 1
+            and tuple(spec.out_repeat) == (1, 1, 1))
+
+
+def conv_fwd_small_bf16(x, w, bias, spec: ConvSpec, residual=None, post_scale=None,
+                        post_shift=None, out=None):
+    """Narrow 3x3x3 convolution on mma.sync tensor cores (bf16 operands, fp32 accumulate)."""
+    x16 = None
+    if x.dtype == torch.bfloat16:
+        x16, x = x.contiguous(), None
+        ensure_device(x16)
+        n, dims, c, ndim = dims3(x16.shape)
+    else:
+        x = _f32(x)
+        ensure_device(x)
+        n, dims, c, ndim = dims3(x.shape)
+    assert c == spec.cin and ndim == spec.ndim, (c, ndim, spec)
+    _, od, oc = spec.out_dims(n, dims)
+    cs = spec.out_cstride or oc
+    ref = x16 if x is None else x
+    y = out if out is not None else torch.empty(_shape_from(n, od, cs, ndim), device=ref.device,
+                                                dtype=torch.float32)
+    w, bias, residual = _f32(w), _f32(bias), _f32(residual)
+    post_scale, post_shift = _f32(post_scale), _f32(post_shift)
+    _cabi.call("s3_conv_fwd_small_bf16", C.byref(spec.desc(n, dims)), _p(x), _p(x16), _p(w),
+               _p(bias), _p(residual), _p(post_scale), _p(post_shift), _p(y), _s())
+    _count()
+    return y
+
+
 def conv_dgrad(dy, w, spec: ConvSpec, x_shape):
     dy = _f32(dy)
     ensure_device(dy)
@@ -214,7 +248,8 @@ def unpack_act_pad16(hi, lo, ndim, fmt=0):
 
 def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residual=None,
                   post_scale=None, post_shift=None, out=None, want_f32=True, want_pad16=False,
-                  tune=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, want_lo=False):
+                  tune=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, want_lo=False,
+                  want_map16=False):
     """tcgen05 convolution on padded 16-bit activations.  ``dims`` = unpadded (z, y, x)."""
     ensure_device(x_hi)
     _, od, oc = spec.out_dims(n, dims)
@@ -228,6 +263,8 @@ def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residua
                            dtype=x_hi.dtype)
         if x_lo is not None or want_lo:
             y_lo = torch.empty_like(y_hi)
+    if want_map16:   # unpadded 16-bit tensor of the mapped (depth_to_space) geometry
+        y_hi = torch.empty(_shape_from(n, od, cs, spec.ndim), device=x_hi.device, dtype=x_hi.dtype)
     t = tune if tune is not None else UmmaTuning()
     bias, residual = _f32(bias), _f32(residual)
     post_scale, post_shift = _f32(post_scale), _f32(post_shift)

@@ -181,20 +181,24 @@ def build_steps(layers):
 class Act:
     """An activation tensor held in f32 and / or padded 16-bit (hi, lo) form."""
 
-    __slots__ = ("f32", "hi", "lo", "shape")
+    __slots__ = ("f32", "hi", "lo", "shape", "b16")
 
-    def __init__(self, shape, f32=None, hi=None, lo=None):
+    def __init__(self, shape, f32=None, hi=None, lo=None, b16=None):
         self.shape = tuple(shape)
         self.f32, self.hi, self.lo = f32, hi, lo
+        self.b16 = b16          # unpadded 16-bit tensor (depth_to_space destination)
 
     def need_f32(self):
         if self.f32 is None:
-            self.f32 = ops.unpack_act_pad16(self.hi, self.lo, len(self.shape) - 2)
+            if self.b16 is not None:
+                self.f32 = self.b16.float()
+            else:
+                self.f32 = ops.unpack_act_pad16(self.hi, self.lo, len(self.shape) - 2)
         return self.f32
 
     def need_pad16(self, split):
         if self.hi is None or (split and self.lo is None):
-            self.hi, self.lo = ops.pack_act_pad16(self.f32, split=split)
+            self.hi, self.lo = ops.pack_act_pad16(self.need_f32(), split=split)
         return self.hi, (self.lo if split else None)
 
 
@@ -339,6 +343,11 @@ class Plan:
         pair_skip = want16 and bool(st.skip_store) and not split
         want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
+        # depth_to_space head feeding the narrow output convolution: hand the high-resolution
+        # tensor over as unpadded bf16 (8-channel voxels = 16 B) instead of f32
+        map16 = (self.precision == "bf16" and _umma_ok(st, shp, self.precision) and st.r > 1
+                 and st.m == 1 and oc == 8 and res_act is None and not st.skip_store and not last
+                 and post_scale is None and self._next_is_small_bf16(steps, si, out_shape))
         if _umma_ok(st, shp, self.precision):
             x_hi, x_lo = cur.need_pad16(split)
             w_hi, w_lo = self._packed(conv, split)
@@ -349,8 +358,20 @@ class Plan:
                 x_hi, x_lo, w_hi, w_lo, bias, spec, n, dims,
                 residual=None if (res16 or res_act is None) else res_act.need_f32(),
                 res_hi=res_act.hi if res16 else None, res_lo=res_act.lo if res16 else None,
-                post_scale=post_scale, post_shift=post_shift, want_f32=want32,
-                want_pad16=want16, want_lo=pair_skip)
+                post_scale=post_scale, post_shift=post_shift, want_f32=want32 and not map16,
+                want_pad16=want16, want_lo=pair_skip, want_map16=map16)
+            if map16:
+                out = Act(out_shape, b16=y_hi)
+                return out
+        elif (self.precision == "bf16" and not want16 and ops.small_bf16_ok(spec)
+              and spec.pad_mode == S3_PAD_REFLECT):
+            # narrow high-resolution output convolution: warp-level tensor cores, bf16 operands
+            y = ops.conv_fwd_small_bf16(
+                cur.b16 if (cur.b16 is not None and cur.f32 is None and shp[-1] == 8)
+                else cur.need_f32(), conv.conv_kernel().detach(), bias, spec,
+                residual=None if res_act is None else res_act.need_f32(),
+                post_scale=post_scale, post_shift=post_shift)
+            y_hi = y_lo = None
         else:
             x = cur.need_f32()
             res = ops.conv_fwd(x, conv.conv_kernel().detach(), bias, spec,
@@ -362,6 +383,18 @@ class Plan:
         for name in st.skip_store:
             skips[name] = out
         return out
+
+    def _next_is_small_bf16(self, steps, si, out_shape):
+        """Is the consumer of step si's output the narrow tensor-core convolution?"""
+        for nxt in steps[si + 1:]:
+            if not isinstance(nxt, FusedConv) or nxt.pads is None:
+                return False
+            if _umma_ok(nxt, out_shape, self.precision) or nxt.skip_add is not None:
+                return False
+            sp = nxt.spec(out_shape)
+            return (ops.small_bf16_ok(sp) and sp.pad_mode == S3_PAD_REFLECT and sp.cin == 8
+                    and nxt.r == 1 and nxt.m == 1)
+        return False
 
     @staticmethod
     def _ring16_ok(st, out_shape):

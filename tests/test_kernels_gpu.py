@@ -434,3 +434,53 @@ def test_umma_conv_matches_direct(cuda, n, dims, variant):
         full = y_hi.float() + y_lo.float()
         full_ref = ref_hi.float() + ref_lo.float()
         assert (full - full_ref).abs().max().item() <= scale * 1e-4   # halos of hi + lo too
+
+
+@pytest.mark.parametrize("cin,cout,shape,mode", [(8, 4, (1, 9, 21, 70), 1), (4, 2, (2, 4, 8, 32), 1),
+                                                   (8, 8, (1, 5, 17, 33), 0), (6, 3, (1, 6, 6, 40), 2)])
+def test_small_channel_mma_conv(cuda, cin, cout, shape, mode):
+    """Narrow 3x3x3 conv on mma.sync (bf16 operands) vs the fp32 direct kernel on bf16-exact
+    inputs: identical products, fp32 summation order differs."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(cin * 100 + cout)
+    x = _bf16_exact(rng_arr(rng, (*shape, cin)))
+    w = _bf16_exact(rng_arr(rng, (3, 3, 3, cin, cout), 0.2))
+    b = rng_arr(rng, (cout,), 0.1)
+    sc, sh = rng_arr(rng, (cout,)), rng_arr(rng, (cout,))
+    spec = ops.ConvSpec(3, cin, cout, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=mode)
+    ref = ops.conv_fwd(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec, post_scale=dev(sc, cuda),
+                       post_shift=dev(sh, cuda))
+    assert ops.small_bf16_ok(spec)
+    y = ops.conv_fwd_small_bf16(dev(x, cuda), dev(w, cuda), dev(b, cuda), spec,
+                                post_scale=dev(sc, cuda), post_shift=dev(sh, cuda))
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+def test_umma_d2s_16bit_destination_feeds_small_conv(cuda):
+    """64 -> 200 head with fused 5x depth_to_space writing an unpadded bf16 tensor, consumed by the
+    narrow tensor-core conv (bf16 input path): both against the fp32 kernels."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(5)
+    n, dims = 1, (4, 5, 24)
+    x = _bf16_exact(rng_arr(rng, (n, *dims, 64)))
+    w = _bf16_exact(rng_arr(rng, (3, 3, 3, 64, 200), 0.05))
+    b = rng_arr(rng, (200,), 0.1)
+    xd, wd, bd = dev(x, cuda), dev(w, cuda), dev(b, cuda)
+    spec = ops.ConvSpec(3, 64, 200, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
+                        d2s=5)
+    ref = ops.conv_fwd(xd, wd, bd, spec)                      # (1, 20, 25, 24, 8) f32
+    x_hi, _ = ops.pack_act_pad16(xd)
+    w_hi, _ = ops.pack_weights_umma(wd, ndim=3)
+    _, y16, _ = ops.conv_fwd_umma(x_hi, None, w_hi, None, bd, spec, n, dims, want_f32=False,
+                                  want_map16=True)
+    assert y16.dtype == torch.bfloat16 and tuple(y16.shape) == tuple(ref.shape)
+    d = (y16.float() - ref.to(torch.bfloat16).float()).abs().max().item()
+    assert d <= float(ref.abs().max()) * 2.0 ** -7
+    assert (y16 == ref.to(torch.bfloat16)).float().mean().item() > 0.995
+    # consumer: 8 -> 4 conv reading the bf16 tensor directly
+    w2 = _bf16_exact(rng_arr(rng, (3, 3, 3, 8, 4), 0.2))
+    b2 = rng_arr(rng, (4,), 0.1)
+    spec2 = ops.ConvSpec(3, 8, 4, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1)
+    ref2 = ops.conv_fwd(y16.float(), dev(w2, cuda), dev(b2, cuda), spec2)
+    got2 = ops.conv_fwd_small_bf16(y16, dev(w2, cuda), dev(b2, cuda), spec2)
+    assert rel_err(got2.cpu().numpy(), ref2.cpu().numpy()) < 2e-5

@@ -43,4 +43,4 @@ for name, kw in [("pad16", dict(want_f32=False, out_hi=y_hi)),
     tr = trace.cpu().tolist()
     items = max(tr[5], 1)
     print(f"flags {flags} {name:16s}: {us:7.1f} us/launch ({2*n*16*16*288*27*64*64/us/1e6:6.1f} TF/s) items/CTA {tr[5]} "
-          f"MMA warp {tr[0]/items:.0f} cyc/item | epilogue warp: wait acc_full {tr[8]/items:.0f}, work {tr[9]/items:.0f} (res-load waits {tr[10]/items:.0f}, store-read waits {tr[11]/items:.0f}) per item")
+          f"MMA warp {tr[0]/items:.0f} cyc/item | epilogue warp: wait acc_full {tr[8]/items:.0f}, work {tr[9]/items:.0f} (res-load waits {tr[10]/items:.0f}, store-read waits {tr[11]/items:.0f}; phases: tmem-ld {tr[12]/items:.0f}, +bias/act {tr[13]/items:.0f}, residual {tr[14]/items:.0f}, output {tr[15]/items:.0f}) per item")
