@@ -57,6 +57,7 @@ __device__ __forceinline__ ItemCoord decode_item(const UmmaParams& p, int item) 
 }
 
 constexpr int kThreads = 192;
+constexpr int kTileThreads = 320;   // tile kernel: TMA + MMA + 8 epilogue warps
 constexpr int kMaxWS = 8;
 constexpr int kMaxPlanes = 10;
 
@@ -106,7 +107,7 @@ __device__ __forceinline__ uint32_t setup_cta(const UmmaParams& p, const SmemMap
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(m.bar_base + 8u * (B_ACCFULL + i), 1);
-      mbar_init(m.bar_base + 8u * (B_ACCEMPTY + i), 4);
+      mbar_init(m.bar_base + 8u * (B_ACCEMPTY + i), (blockDim.x >> 5) - 2);   // epilogue warps
     }
     fence_barrier_init();
   }
@@ -154,6 +155,63 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const SmemMap
   epilogue_row<EPI>(g, p.ep, sm.sbias, t_addr + ((uint32_t)(q * 32) << 16), rp);
 }
 
+
+// depth_to_space head writing an unpadded 16-bit tensor (3-D, spatial factor r, 8 mapped channels
+// per voxel, no residual / affine): one thread = one LR voxel, its cout = r*r*8 channels go to
+// r*r HR voxels as 16-byte runs; 8 consecutive x voxels of a warp form full 128-byte lines.
+// Two 16-column TMEM loads in flight per step, no divisions (run counters advance (i, j)).
+__device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const SmemMap& sm,
+                                                    const ItemCoord& c, int fr0, uint32_t t_addr,
+                                                    int warp, int lane) {
+  const ConvGeom& g = p.g;
+  const Epilogue& ep = p.ep;
+  const int q = warp & 3;
+  const int mrow = q * 32 + lane;
+  const int grp = mrow >> 3, xl = mrow & 7;
+  const int fr = fr0 + grp;
+  const int zq = fr / p.YB, yq = fr - zq * p.YB;
+  const int plane = c.pl0 + zq;
+  const int y = c.y0 + yq, x = c.xb * 8 + xl;
+  const bool valid = yq <= p.YB - 3 && y < g.in[1] && x < g.in[2] && plane < p.planes;
+  const uint32_t ta = t_addr + ((uint32_t)(q * 32) << 16);
+  const int r = g.r;
+  // destination element offset of run (i = 0, j = 0): HR voxel (z r, y r, x), 8 channels
+  const long long sy = (long long)g.fd[2] * g.cstride, sz = (long long)g.fd[1] * sy;
+  uint16_t* base = reinterpret_cast<uint16_t*>(ep.y_hi) +
+                   ((((long long)c.b * g.fd[0] + (long long)plane * r) * g.fd[1] + (long long)y * r) *
+                        g.fd[2] + x) * g.cstride + g.coff;
+  int ri = 0, rj = 0;   // run counters: channel run number = ri * r + rj
+  const int cout = g.cout;
+#pragma unroll 1
+  for (int c0 = 0; c0 < cout; c0 += 32) {
+    uint32_t raw[32];
+    tmem_ld16(ta + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+    if (c0 + 16 < cout) tmem_ld16(ta + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+    tmem_ld_wait();
+    if (!valid) continue;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (c0 + 8 * s < cout) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a = __uint_as_float(raw[8 * s + k]) + sm.sbias[c0 + 8 * s + k];
+          if (g.act == S3_ACT_LEAKY) a = a >= 0.f ? a : g.alpha * a;
+          else if (g.act == S3_ACT_RELU) a = fmaxf(a, 0.f);
+          else if (g.act != S3_ACT_NONE) a = apply_act(a, g.act, g.alpha);
+          v[k] = a;
+        }
+        uint4 u;
+        u.x = pack2(v[0], v[1], ep.fmt);
+        u.y = pack2(v[2], v[3], ep.fmt);
+        u.z = pack2(v[4], v[5], ep.fmt);
+        u.w = pack2(v[6], v[7], ep.fmt);
+        *reinterpret_cast<uint4*>(base + ri * sz + rj * sy) = u;
+        if (++rj == r) { rj = 0; ++ri; }
+      }
+    }
+  }
+}
 
 // launchers implemented in conv_umma_zcat.cu / conv_umma_tile.cu
 int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,

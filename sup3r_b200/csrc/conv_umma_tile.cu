@@ -9,7 +9,7 @@ namespace s3 {
 // Every output tile accumulates all taps itself (N = npad).  Used for 2-D convolutions and
 // for wide outputs (npad > 80) where one MMA already has N >= 128.
 template <int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTileThreads, 1)
 conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                       const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_w_hi,
@@ -106,9 +106,14 @@ conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       const ItemCoord c = decode_item(p, item);
       mbar_wait(bar(B_ACCFULL + ab), abph, p.dbg, 6, ab, it);
       tc_fence_after();
-      for (int r = 0; r < p.R; ++r)
-        epilogue_tile<EPI>(p, sm, c, c.row0 + r * p.TS, tmem_base + (uint32_t)((ab * p.R + r) * p.npad),
-                      warp, lane);
+      // two epilogue warps per TMEM lane quarter: they alternate over the R tiles of the item
+      for (int r = (warp - 2) >> 2; r < p.R; r += 2) {
+        const uint32_t ta = tmem_base + (uint32_t)((ab * p.R + r) * p.npad);
+        if (EPI == EPI_D2S16)
+          epilogue_tile_d2s16(p, sm, c, c.row0 + r * p.TS, ta, warp, lane);
+        else
+          epilogue_tile<EPI == EPI_D2S16 ? EPI_D2S : EPI>(p, sm, c, c.row0 + r * p.TS, ta, warp, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + ab));
@@ -131,7 +136,7 @@ static int launch_tile_t(const UmmaParams& p, const CUtensorMap& a_hi, const CUt
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr = true;
   }
-  conv_umma_tile_kernel<EPI><<<ctas, kThreads, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  conv_umma_tile_kernel<EPI><<<ctas, kTileThreads, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   S3_CUDA(cudaGetLastError());
   return S3_OK;
 }
@@ -140,6 +145,8 @@ int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtenso
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st) {
   if (epi == EPI_PLAIN) return launch_tile_t<EPI_PLAIN>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
+  if (epi == EPI_D2S && p.g.ndim == 3 && p.g.m == 1 && p.g.cmap == 8 && p.ep.y_hi && !p.ep.y)
+    return launch_tile_t<EPI_D2S16>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
   if (epi == EPI_D2S) return launch_tile_t<EPI_D2S>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
   return launch_tile_t<EPI_GENERIC>(p, a_hi, a_lo, w_hi, w_lo, ctas, smem, st);
 }
