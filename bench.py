@@ -60,42 +60,60 @@ def algorithmic_flops_per_chunk(hl, lr_shape):
     return flops
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """Streams nvidia-smi SM clocks / throttle reasons (one line every 50 ms) while the timed
+    region runs; only samples taken between start() and finish() are kept."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self._stop_evt = threading.Event()
+        self.lines = []
+        self.proc = None
+        self.reader = None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}",
-                                      f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for ln in self.proc.stdout:
+                self.lines.append((time.perf_counter(), ln.strip()))
+        self.reader = threading.Thread(target=pump, daemon=True)
+        self.reader.start()
+        # wait for the first sample so that the stream is live when the timed region starts
+        t_end = time.perf_counter() + 3.0
+        while not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
+        self.t0 = time.perf_counter()
 
     def finish(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        t1 = time.perf_counter()
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+        rows = [ln.split(",") for t, ln in self.lines if self.t0 <= t <= t1 + 0.06 and ln]
+        rows = [[v.strip() for v in r] for r in rows if len(r) >= 6]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[6]) for r in rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6])
-                          if v.lower() == "active"})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 def load_peaks():
@@ -157,7 +175,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=8, help="LR chunks per step (batch)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
@@ -276,6 +294,9 @@ def main():
     flops_chunk = algorithmic_flops_per_chunk(hl, LR_CHUNK)
     roof = None
     try:
+        # the body convolution as the model runs it: 64 -> 64 channels, 3x3x3, 16-bit padded in /
+        # out; 17 launches per step write LeakyReLU output only ("plain"), 16 add the
+        # SkipConnection pair and write hi + lo ("residual")
         n, dims = B, (16, 16, 288)
         xb = torch.randn((n, *dims, 64), device=dev)
         wb = torch.randn((3, 3, 3, 64, 64), device=dev) * 0.03
@@ -283,41 +304,56 @@ def main():
         split = args.precision == "bf16x3"
         x_hi, x_lo = ops.pack_act_pad16(xb, split=split)
         w_hi, w_lo = ops.pack_weights_umma(wb, split=split, ndim=3)
-        spec = ops.ConvSpec(3, 64, 64, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
-                            act=2, alpha=0.2)
+        r_hi, r_lo = ops.pack_act_pad16(torch.randn_like(xb), split=True)
         y_hi = torch.empty_like(x_hi)
-        y_lo = torch.empty_like(x_hi) if split else None
+        y_lo = torch.empty_like(x_hi)
 
-        def body():
-            ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
-                              out_hi=y_hi, out_lo=y_lo)
-        for _ in range(3):
-            body()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            body()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            g.replay()
-            e1.record()
+        def time_variant(residual):
+            spec = ops.ConvSpec(3, 64, 64, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1),
+                                pad_mode=1, act=0 if residual else 2, alpha=0.2)
+
+            def body():
+                if residual and not split:
+                    ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
+                                      out_hi=y_hi, out_lo=y_lo, res_hi=r_hi, res_lo=r_lo)
+                else:
+                    ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
+                                      out_hi=y_hi, out_lo=y_lo if split else None)
+            for _ in range(3):
+                body()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        k_ms = float(np.mean(ts))
+            ts = []
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = (torch.cuda.Event(enable_timing=True),
+                          torch.cuda.Event(enable_timing=True))
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts))
+        ms_plain, ms_res = time_variant(False), time_variant(True)
         k_flops = 2.0 * n * np.prod(dims) * 27 * 64 * 64
+        n_plain, n_res = 17, 16
+        k_ms = (n_plain * ms_plain + n_res * ms_res) / (n_plain + n_res)
         achieved = k_flops / (k_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_body_conv_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "conv_umma_zcat_kernel (64->64 3x3x3, "
-                f"{n}x16x16x288 voxels, bf16 -> padded bf16)", "achieved": achieved,
+        roof = {"bound": "tensor", "kernel": "conv_umma_zring_kernel<4, EPI_V3> (64->64 3x3x3 reflect "
+                f"conv, {n}x16x16x288 voxels, bf16 padded in/out; launch mix of the model step: "
+                f"{n_plain} plain + {n_res} residual launches)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": f"{peaks_src} bf16_tflops_sustained", "kernel_ms": k_ms,
+                "kernel_ms_plain": ms_plain, "kernel_ms_residual": ms_res,
+                "achieved_plain": k_flops / (ms_plain / 1e3) / 1e12,
+                "achieved_residual": k_flops / (ms_res / 1e3) / 1e12,
                 "algorithmic_flops_per_launch": k_flops}
     except Exception as e:  # pragma: no cover
         roof = {"error": repr(e)[:300]}

@@ -66,8 +66,9 @@ def full(tag):
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
-        out = [f"# {name}: `ncu --set full --clock-control none --import-source on` (1 launch)", ""]
+        out = [f"# {name}: `ncu --set full --clock-control none --import-source on` ({len(rows) - 2} launch(es); SASS hot spots: first launch)", ""]
         summary = {}
+        traffic_rows = []
         for r in rows[2:]:
             out += [f"kernel `{r[4][:100]}` grid {r[8]} block {r[7]}", "",
                     "| metric | unit | value |", "|---|---|---|"]
@@ -81,8 +82,10 @@ def full(tag):
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(
                 units[ui] if ui is not None else "byte", 1.0)
             out += ["", f"dram traffic per launch: {(rd + wr) * scale / 1e6:.2f} MB"]
-            json.dump({"dram_bytes_per_launch": (rd + wr) * scale, "kernel": r[4][:80]},
-                      open(os.path.join(ROOT, "profiles", f"{name}_traffic.json"), "w"))
+            traffic_rows.append({"dram_bytes_per_launch": (rd + wr) * scale, "kernel": r[4][:80],
+                                 "gpu_time_us": summary.get("gpu__time_duration.sum")})
+        json.dump(traffic_rows if len(traffic_rows) > 1 else traffic_rows[0],
+                  open(os.path.join(ROOT, "profiles", f"{name}_traffic.json"), "w"), indent=1)
         # hottest SASS lines by stall samples
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source",
                               "sass"], capture_output=True, text=True).stdout
@@ -91,7 +94,12 @@ def full(tag):
             shdr = srows[1]
             isamp, isrc, iex = (shdr.index(k) for k in ("# Samples", "Source",
                                                          "Instructions Executed"))
-            data = srows[2:]
+            data = [r for r in srows[2:] if len(r) > max(isamp, isrc, iex)]
+            # (multi-launch reports repeat the header block per launch: keep the first launch)
+            for k, r in enumerate(data):
+                if r[isamp] == '# Samples' or not (r[isamp] or '0').isdigit():
+                    data = data[:k]
+                    break
             tot = sum(int(r[isamp] or 0) for r in data)
             out += ["", f"## hottest SASS instructions ({tot} samples over {len(data)} instrs)", "",
                     "| idx | samples | executed | instruction | top stalls |", "|---|---|---|---|---|"]
