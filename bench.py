@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--impl", default="sup3r_b200", choices=["sup3r_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -287,6 +288,8 @@ def main():
     del y_sync
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     # ---------------- roofline of the dominant kernel (tcgen05 body conv) ----------------------
@@ -346,7 +349,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r01_body_conv_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "conv_umma_zring_kernel<4, EPI_V3> (64->64 3x3x3 reflect "
+        kname = ("conv_umma_tile_kernel (split operands, 3 MMA passes)" if split
+                 else "conv_umma_zring_kernel<4, EPI_V3>")
+        roof = {"bound": "tensor", "kernel": kname + " (64->64 3x3x3 reflect "
                 f"conv, {n}x16x16x288 voxels, bf16 padded in/out; launch mix of the model step: "
                 f"{n_plain} plain + {n_res} residual launches)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
@@ -357,6 +362,38 @@ def main():
                 "algorithmic_flops_per_launch": k_flops}
     except Exception as e:  # pragma: no cover
         roof = {"error": repr(e)[:300]}
+
+    # ---------------- the precision mode that meets the 1e-3 parity bound ---------------------
+    # (north star: outputs within 1e-3 relative of the fp32 reference; single-pass bf16 operands
+    # through 38 stacked convolutions cannot, the split-operand mode does)
+    parity = None
+    if args.precision == "bf16" and not args.no_parity_mode:
+        try:
+            plan3 = model.plan_for(model.generator, "bf16x3")
+            for _ in range(2):
+                plan3.run_graphed(x_dev)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = (torch.cuda.Event(enable_timing=True),
+                          torch.cuda.Event(enable_timing=True))
+                e0.record()
+                y3 = plan3.run_graphed(x_dev)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            y32 = model.plan_for(model.generator, "fp32").run(x_dev[:1])
+            y16 = plan.run(x_dev[:1])
+            y3b = plan3.run(x_dev[:1])
+            sc = float(y32.abs().max())
+            parity = {"precision": "bf16x3", "value": vox_step / (float(np.mean(ts)) / 1e3),
+                      "unit": "LR voxels/s", "ms_per_step": float(np.mean(ts)),
+                      "max_rel_err_vs_fp32_kernels": float((y3b - y32).abs().max()) / sc,
+                      "headline_mode_max_rel_err_vs_fp32_kernels":
+                          float((y16 - y32).abs().max()) / sc}
+        except Exception as e:  # pragma: no cover
+            parity = {"error": repr(e)[:300]}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -381,9 +418,12 @@ def main():
                 "d2h_bytes_per_step": d2h, "api": "GeneratePipeline (pinned, 2 slots, 3 streams)",
                 "sync_generate_value": sync_value},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "parity_mode": parity,
         "host_cores": os.cpu_count(),
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -28,6 +28,7 @@ struct UmmaParams {
   int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
   int epi_v2;         // zring 16-bit epilogue: 0 thread-per-row, 1 LSU-coalescing, 2 TMA tile I/O
   int epi_bufs;       // TMA epilogue: staging boxes per warp (1 or 2)
+  int tile_fast;      // tile kernel: straight-line MMA role (3-D plane mode, R = 2, XB = 10, WS = 4)
   int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
 };
 

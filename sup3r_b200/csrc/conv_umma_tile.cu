@@ -5,6 +5,69 @@
 
 namespace s3 {
 
+// bounded spin without clock reads
+__device__ __forceinline__ void tile_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t n = 0; !mbar_try_wait(bar, parity); ++n)
+    if (n > (1u << 26)) __trap();
+}
+
+// MMA role for the hot wide-N shape (3-D, plane mode, R = 2 tiles per item, 18 x 10 voxel planes,
+// 4 weight stages, single-pass operands): one elected thread issues a whole item (27 taps x 2
+// tiles x 4 k-steps) as straight-line code with immediate descriptor offsets, and waits for the
+// next tap's weights before the last MMA group of the current tap -- the tcgen05 queue only
+// holds ~2 MMAs, so every longer stretch of issue-side code is a tensor-pipe bubble (see
+// conv_umma_zring.cu).
+__device__ __forceinline__ void tile_mma_fast(const UmmaParams& p, const SmemMap& sm,
+                                              uint32_t tmem_base) {
+  constexpr int kR = 2, kWS = 4;
+  auto bar = [&](int i) { return sm.bar_base + 8u * i; };
+  const uint32_t hi_a = sdesc_hi_sw128(1280u), hi_b = sdesc_hi_sw128(1024u);
+  const uint32_t idesc = p.idesc;
+  int as = 0, aph = 0, ab = 0, abph = 0;
+  int g = 0;   // weight slabs consumed: stage g & 3, parity (g >> 2) & 1
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const uint32_t a_lo = sdesc_lo(sm.a_base + as * sm.a_stage_bytes);
+    const uint32_t d0 = tmem_base + (uint32_t)(ab * kR * p.npad);
+    const uint32_t d1 = d0 + (uint32_t)p.npad;
+    if (elect_one()) {
+      tile_wait(bar(B_ACCEMPTY + ab), (uint32_t)(abph ^ 1));
+      tile_wait(bar(B_AFULL + as), (uint32_t)aph);
+      tile_wait(bar(B_WFULL + (g & 3)), (uint32_t)((g >> 2) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int tap = 0; tap < 27; ++tap) {
+        const int dx = tap % 3, dy = (tap / 3) % 3, dz = tap / 9;
+        const int gs = g + tap;
+        const uint32_t wl = sdesc_lo(sm.w_base + (uint32_t)(gs & (kWS - 1)) * sm.w_stage_bytes);
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const uint32_t al = a_lo + (uint32_t)(((r + dz) * 180 + dy * 10 + dx) * 8);
+          const uint32_t dd = r == 0 ? d0 : d1;
+          if (r == kR - 1 && tap < 26)
+            tile_wait(bar(B_WFULL + ((gs + 1) & (kWS - 1))), (uint32_t)(((gs + 1) >> 2) & 1));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (tap == 0 && kk == 0)
+              umma_f16_new(dd, mk_desc(al, hi_a), mk_desc(wl, hi_b), idesc);
+            else
+              umma_f16_acc(dd, mk_desc(al + 2u * kk, hi_a), mk_desc(wl + 2u * kk, hi_b), idesc);
+          }
+        }
+        umma_commit(bar(B_WEMPTY + (gs & (kWS - 1))));
+        if (tap == 26) {
+          umma_commit(bar(B_AEMPTY + as));
+          umma_commit(bar(B_ACCFULL + ab));
+        }
+      }
+    }
+    __syncwarp();
+    g += 27;
+    if (++as == p.AS) { as = 0; aph ^= 1; }
+    if (++ab == p.acc_bufs) { ab = 0; abph ^= 1; }
+  }
+}
+
 // ============================================================================ kernel "tile"
 // Every output tile accumulates all taps itself (N = npad).  Used for 2-D convolutions and
 // for wide outputs (npad > 80) where one MMA already has N >= 128.
@@ -52,6 +115,8 @@ conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
         if (++ws == p.WS) { ws = 0; wph ^= 1; }
       }
     }
+  } else if (warp == 1 && p.tile_fast) {
+    tile_mma_fast(p, sm, tmem_base);
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (warp-uniform, elected issue)
     int as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0, it = 0;
