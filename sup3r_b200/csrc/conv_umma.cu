@@ -186,12 +186,13 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
                           g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.fd[0] >= 4 && g.fd[1] >= 4 &&
                           g.fd[2] >= 4 && !post_scale;
     p.epi_v2 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
-                p.planes >= 4) ? ((t.box_y & 128) ? 1 : 2) : 0;
+                p.planes >= 4) ? ((t.box_y & 128) ? 1 : ((t.box_y & 512) ? 2 : 3)) : 0;
     S3_REQUIRE(!res_hi || p.epi_v2, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
                "64-channel 16-bit-output configuration");
     // residual layers keep two transfers per warp in flight (costs one plane slot: P = 6)
     p.epi_bufs = (p.epi_v2 == 2 && res_hi && !(t.box_y & 256)) ? 2 : 1;
-    const uint32_t stage_bytes = p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u;
+    // V4 (epi_v2 == 3): sixteen epilogue warps with one box each
+    const uint32_t stage_bytes = p.epi_v2 == 3 ? 32768u : (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u);
     int P = (int)((kSmemLimit - fixed - 1024u - stage_bytes - (uint32_t)ws * w_slab) / plane);
     if (P > 8) P = 8;
     if (t.ring_slots > 0 && t.ring_slots < P) P = t.ring_slots;
@@ -285,7 +286,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
   if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed +
-                    (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u);
+                    (p.epi_v2 == 3 ? 32768u : (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u));
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
   // epilogue specialisation: fast paths only when their preconditions hold for EVERY row
@@ -304,7 +305,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   if (zring) {
     CUtensorMap em[4];
     memset(em, 0, sizeof(em));
-    if (p.epi_v2 == 2) {
+    if (p.epi_v2 >= 2) {
       // interior views (x + 1, y + 1) of the padded tensors: tile coordinates are plain voxel
       // indices, ragged tiles are clipped by the map extents
       const uint64_t edims[4] = {64, (uint64_t)g.fd[2], (uint64_t)g.fd[1], total_planes};

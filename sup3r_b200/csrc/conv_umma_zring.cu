@@ -20,6 +20,8 @@
 namespace s3 {
 
 constexpr int kRingThreads = 384;    // WG0: TMA + MMA (+2 idle warps); WG1, WG2: epilogue
+constexpr int kRingThreadsV4 = 640;  // ... WG1..WG4: sixteen epilogue warps (EPI_V4)
+__host__ __device__ constexpr int ring_threads(int epi) { return epi == 6 ? kRingThreadsV4 : kRingThreads; }
 constexpr int kRingMaxP = 8;
 constexpr int kRingMaxWS = 4;
 constexpr int RB_PFULL = 0;
@@ -545,6 +547,139 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
   if (et.trace) et.t_ph[3] += clock64() - tp2;
 }
 
+// ---------------------------------------------------------- TMA epilogue, 16 warps (V4)
+// The V3 epilogue is bound by the serial load -> add -> store chain of each warp (two 32-row
+// tiles per warp and item, ~12 k cycles each against 16 k cycles of MMA per item).  V4 runs
+// SIXTEEN epilogue warps (one per output plane and TMEM lane quarter, so every warp has exactly
+// one tile per item) on 104 registers each: the row is processed in two 32-channel passes
+// (v[32] instead of v[64]) and every pass moves through ONE 2 KiB SWIZZLE_64B staging box per
+// warp: residual hi, residual lo (TMA loads), output hi, output lo (TMA stores).
+template <bool kRes>
+__device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const Epilogue& ep,
+                                                      const float* sbias, uint32_t t_addr,
+                                                      const TileGeom& tg, int plane_coord,
+                                                      int mz_planes, EpiTma& et, int lane) {
+  const int fmt = ep.fmt;
+  const int FY = g.fd[1], FX = g.fd[2];
+  const int yl = lane >> 3, xl = lane & 7;
+  const int y = tg.y0 + yl, x = tg.x0 + xl;
+  const bool row_valid = y < FY && x < FX;
+  const bool has_lo = ep.y_lo != nullptr;
+  const bool res_has_lo = kRes && ep.res_lo != nullptr;
+  uint8_t* const sb = et.stage0;
+  const uint32_t sbs = et.stage_s0;
+
+  auto box_free = [&]() {   // the last store issued by this warp has read the box
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  };
+  auto issue_res = [&](int op, int c2) {
+    if (lane == 0) {
+      mbar_expect_tx(et.bar0, 2048u);
+      tma_load_4d(sbs, op ? et.res[1] : et.res[0], et.bar0, 32 * c2, tg.x0, tg.y0, plane_coord);
+    }
+  };
+  box_free();
+  if (kRes) issue_res(0, 0);
+
+  const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * 128;
+  const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
+  const long long mx = x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL);
+  const long long mzb = (long long)mz_planes * tg.sz;
+
+#pragma unroll
+  for (int c2 = 0; c2 < 2; ++c2) {
+    if (kRes && c2 == 1) {
+      box_free();
+      issue_res(0, 1);
+    }
+    float v[32];
+    {
+      uint32_t raw[32];
+      tmem_ld16(t_addr + 32 * c2, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+      tmem_ld16(t_addr + 32 * c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bv = *reinterpret_cast<const float4*>(sbias + 32 * c2 + 4 * q);
+        v[4 * q] = __uint_as_float(raw[4 * q]) + bv.x;
+        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bv.y;
+        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bv.z;
+        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bv.w;
+      }
+    }
+    if (g.act == S3_ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
+    } else if (g.act == S3_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (g.act != S3_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+    }
+    if (kRes) {
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        if (op == 0 || res_has_lo) {
+          mbar_wait_lean(et.bar0, et.phase0);
+          et.phase0 ^= 1u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sb + stage64_off(lane, k));
+            unpack_add8(&v[8 * k], u, fmt);
+          }
+          __syncwarp();
+          if (op == 0 && res_has_lo) issue_res(1, c2);
+        }
+      }
+    }
+#pragma unroll
+    for (int op = 0; op < 2; ++op) {
+      if (op == 0 || has_lo) {
+        uint4 hrow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xv = v[8 * k + j];
+            a[j] = op == 0 ? xv : xv - from16(to16(xv, fmt), fmt);
+          }
+          hrow[k].x = pack2(a[0], a[1], fmt);
+          hrow[k].y = pack2(a[2], a[3], fmt);
+          hrow[k].z = pack2(a[4], a[5], fmt);
+          hrow[k].w = pack2(a[6], a[7], fmt);
+        }
+        if (op == 1 || (c2 == 1 && !kRes)) box_free();   // (after a residual round the box is free)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(sb + stage64_off(lane, k)) = hrow[k];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord);
+          if (mz_planes != 0)
+            tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes);
+          tma_store_commit();
+        }
+        if (row_valid && (my | mx) != 0) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(op == 0 ? ep.y_hi : ep.y_lo) + row_off + 64 * c2;
+#pragma unroll 1
+          for (int combo = 1; combo < 8; ++combo) {
+            const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
+            if (!(bq || cq)) continue;
+            if ((a && mzb == 0) || (bq && my == 0) || (cq && mx == 0)) continue;
+            uint4* d = reinterpret_cast<uint4*>(dst + (a ? mzb : 0) + (bq ? my : 0) + (cq ? mx : 0));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[k] = hrow[k];
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void ring_epilogue_tile(const UmmaParams& p, const float* sbias,
                                                    const RingItem& c, int r, uint32_t t_addr,
@@ -734,7 +869,7 @@ __device__ __forceinline__ void ring_mma_fast(const UmmaParams& p, uint32_t bar_
 // ------------------------------------------------------------------------------------ kernel
 // kR > 0: compile-time planes per item (fully unrolled issue loop); kR == 0: runtime p.R
 template <int kR, int EPI>
-__global__ void __launch_bounds__(kRingThreads, 1)
+__global__ void __launch_bounds__(ring_threads(EPI), 1)
 conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
                        const __grid_constant__ CUtensorMap tm_w,
                        const __grid_constant__ EpiMaps em, const UmmaParams p) {
@@ -762,7 +897,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(RB_ACCFULL + i), 1);
-      mbar_init(bar(RB_ACCEMPTY + i), 8);
+      mbar_init(bar(RB_ACCEMPTY + i), EPI == EPI_V4 ? 16 : 8);
     }
     for (int i = 0; i < 16; ++i) mbar_init(bar(RB_EPILD + i), 1);
     fence_barrier_init();
@@ -942,18 +1077,19 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
   } else {
     // ------------------------------------------------------------------------------ epilogue
-    reg_inc<216>();
+    if (EPI == EPI_V4) reg_inc<104>(); else reg_inc<216>();
+    constexpr int kWgs = EPI == EPI_V4 ? 4 : 2;   // epilogue warpgroups
     const int wg = (warp - 4) >> 2, q = warp & 3;
     int ab = 0, abph = 0;
     EpiTma et;
     et.res[0] = &em.res_hi; et.res[1] = &em.res_lo;
     et.out[0] = &em.y_hi; et.out[1] = &em.y_lo;
-    et.nb = p.epi_bufs;
+    et.nb = EPI == EPI_V4 ? 1 : p.epi_bufs;
     et.stage_s0 = bar_base + 2048u + (uint32_t)((warp - 4) * et.nb) * 2048u;
     et.stage_s1 = et.stage_s0 + 2048u;
     et.stage0 = smem_raw + (et.stage_s0 - smem_u32(smem_raw));
     et.stage1 = et.stage0 + 2048;
-    et.bar0 = bar(RB_EPILD + 2 * (warp - 4));
+    et.bar0 = bar(RB_EPILD + (EPI == EPI_V4 ? 1 : 2) * (warp - 4));
     et.bar1 = et.bar0 + 8u;
     et.phase0 = et.phase1 = 0;
     et.trace = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
@@ -969,7 +1105,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       long long c1 = tr ? clock64() : 0;
       if (tr) t_wait += c1 - c0;
       tc_fence_after();
-      if (EPI == EPI_V3) {
+      if (EPI == EPI_V3 || EPI == EPI_V4) {
         if (!(p.dbg_flags & 8)) {
           const ConvGeom& g = p.g;
           TileGeom tg;
@@ -978,7 +1114,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
           tg.y0 = c.yb * 16 + q * 4;
           tg.x0 = c.xb * 8;
           tg.mz = 0;
-          for (int r = wg; r < c.ri; r += 2) {
+          for (int r = wg; r < c.ri; r += kWgs) {
             const int z = c.pl0 + r;
             const int plane_coord = c.b * (g.fd[0] + 2) + z + 1;
             tg.base = (((long long)plane_coord * (g.fd[1] + 2) + tg.y0 + 1) * (g.fd[2] + 2) +
@@ -986,7 +1122,12 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
             const int mzp = z == 1 ? -2 : (z == g.fd[0] - 2 ? 2 : 0);
             const uint32_t ta = tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)) +
                                 ((uint32_t)(q * 32) << 16);
-            if (p.ep.res_hi)
+            if (EPI == EPI_V4) {
+              if (p.ep.res_hi)
+                ring_epilogue_warp_v4<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+              else
+                ring_epilogue_warp_v4<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+            } else if (p.ep.res_hi)
               ring_epilogue_warp_v3<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
             else
               ring_epilogue_warp_v3<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
@@ -1016,7 +1157,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
         }
       } else if (!(p.dbg_flags & 8)) {
         for (int r = wg; r < c.ri; r += 2)
-          ring_epilogue_tile<(EPI == EPI_V2 || EPI == EPI_V3) ? EPI_PLAIN : EPI>(
+          ring_epilogue_tile<(EPI == EPI_V2 || EPI == EPI_V3 || EPI == EPI_V4) ? EPI_PLAIN : EPI>(
               p, sbias, c, r, tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)), q, lane);
       }
       tc_fence_before();
@@ -1042,7 +1183,7 @@ static int launch_zring_t(const UmmaParams& p, const CUtensorMap& a, const CUten
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr = true;
   }
-  conv_umma_zring_kernel<kR, EPI><<<ctas, kRingThreads, smem, st>>>(a, w, em, p);
+  conv_umma_zring_kernel<kR, EPI><<<ctas, ring_threads(EPI), smem, st>>>(a, w, em, p);
   S3_CUDA(cudaGetLastError());
   return S3_OK;
 }
@@ -1055,6 +1196,7 @@ int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorM
   if (epi_maps) {
     em.res_hi = epi_maps[0]; em.res_lo = epi_maps[1]; em.y_hi = epi_maps[2]; em.y_lo = epi_maps[3];
   }
+  if (p.epi_v2 == 3 && p.R == 4) return launch_zring_t<4, EPI_V4>(p, a, w, em, ctas, smem, st);
   if (p.epi_v2 == 2 && p.R == 4) return launch_zring_t<4, EPI_V3>(p, a, w, em, ctas, smem, st);
   if (p.epi_v2 == 1 && p.R == 4) return launch_zring_t<4, EPI_V2>(p, a, w, em, ctas, smem, st);
   if (epi == EPI_PLAIN && p.R == 4) return launch_zring_t<4, EPI_PLAIN>(p, a, w, em, ctas, smem, st);

@@ -11,7 +11,7 @@ namespace s3 {
 
 // epilogue specialisations (one per kernel instantiation keeps the SASS small: the generic
 // scatter is ~10x the code of the fast paths and would thrash the instruction cache)
-enum { EPI_PLAIN = 0, EPI_D2S = 1, EPI_GENERIC = 2, EPI_V2 = 3, EPI_V3 = 4, EPI_D2S16 = 5 };  // zring: V2 LSU-coalescing, V3 TMA tile I/O
+enum { EPI_PLAIN = 0, EPI_D2S = 1, EPI_GENERIC = 2, EPI_V2 = 3, EPI_V3 = 4, EPI_D2S16 = 5, EPI_V4 = 6 };  // zring: V2 LSU-coalescing, V3 TMA tile I/O
 
 struct RowPlan {
   bool valid, slow;

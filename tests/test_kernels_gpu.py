@@ -1,6 +1,8 @@
 """Parity of every C-ABI kernel against the CPU oracle (numpy restatement of the reference's
 layer semantics, oracle/layers_ref.py) on seeded inputs.  fp32 kernels: rtol 1e-4 of the tensor
 scale (the north-star bound is 1e-3 relative)."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -394,7 +396,7 @@ def test_umma_conv_matches_direct(cuda, n, dims, variant):
     direct kernel on bf16-exact operands: products are exact, only the fp32 summation order
     differs.  16-bit outputs are compared INCLUDING the REFLECT halo the epilogue writes."""
     from sup3r_b200 import ops
-    rng = np.random.default_rng(hash((n, dims, variant)) % (2 ** 31))
+    rng = np.random.default_rng(zlib.crc32(repr((n, dims, variant)).encode()))
     x = _bf16_exact(rng_arr(rng, (n, *dims, 64)))
     w = _bf16_exact(rng_arr(rng, (3, 3, 3, 64, 64), 0.05))
     b = rng_arr(rng, (64,), 0.1)
