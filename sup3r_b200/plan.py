@@ -207,7 +207,11 @@ def _umma_ok(fc: FusedConv, in_shape, precision):
         return False
     conv = fc.conv
     nd = conv.nd
-    if in_shape[-1] != 64 or conv.filters > 256 or nd not in (2, 3):
+    # (narrow inputs, e.g. the 4-feature first layer, run on the tensor cores with the channel
+    # axis zero-padded to 64: cheaper than the latency-bound generic kernel)
+    if in_shape[-1] > 64 or conv.filters > 256 or nd not in (2, 3):
+        return False
+    if in_shape[-1] < 64 and (nd != 3 or precision != "bf16" or conv.filters < 32):
         return False
     if any(k != 3 for k in conv.kernel_size) or any(s != 1 for s in conv.strides):
         return False
@@ -238,6 +242,8 @@ class Plan:
         if hit is None or hit[0] != ver:
             with torch.no_grad():
                 w = conv.conv_kernel().detach()
+                if w.shape[-2] < 64:     # zero rows for the padded input channels
+                    w = torch.nn.functional.pad(w, (0, 0, 0, 64 - w.shape[-2]))
                 hi, lo = ops.pack_weights_umma(w, split=split, ndim=conv.nd)
             hit = (ver, hi, lo)
             self._wcache[key] = hit
@@ -349,7 +355,12 @@ class Plan:
                  and st.m == 1 and oc == 8 and res_act is None and not st.skip_store and not last
                  and post_scale is None and self._next_is_small_bf16(steps, si, out_shape))
         if _umma_ok(st, shp, self.precision):
-            x_hi, x_lo = cur.need_pad16(split)
+            if cin < 64:
+                x_hi, x_lo = ops.pack_act_pad16(
+                    torch.nn.functional.pad(cur.need_f32(), (0, 64 - cin)), split=split)
+                spec = dataclasses.replace(spec, cin=64)
+            else:
+                x_hi, x_lo = cur.need_pad16(split)
             w_hi, w_lo = self._packed(conv, split)
             res16 = (res_act is not None and not split and not want32 and want16
                      and self._ring16_ok(st, out_shape) and post_scale is None
