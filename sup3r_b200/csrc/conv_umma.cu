@@ -303,8 +303,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     epi = EPI_D2S;
   }
   if (zring) {
-    CUtensorMap em[4];
+    CUtensorMap em[6];
     memset(em, 0, sizeof(em));
+    p.epi_row_tma = (p.epi_v2 == 3 && g.fd[2] % 8 == 0 && !(t.box_y & 1024)) ? 1 : 0;
     if (p.epi_v2 >= 2) {
       // interior views (x + 1, y + 1) of the padded tensors: tile coordinates are plain voxel
       // indices, ragged tiles are clipped by the map extents
@@ -319,6 +320,18 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
         if ((rc = encode_map_strided(&em[i], static_cast<const uint8_t*>(ptrs[i]) + shift, t.fmt, 4,
                                      edims, estr, ebox, CU_TENSOR_MAP_SWIZZLE_64B)))
           return rc;
+      }
+      if (p.epi_row_tma) {
+        // padded view (halo included) with one-row boxes for the y mirrors
+        const uint64_t rdims[4] = {64, (uint64_t)g.fd[2] + 2, (uint64_t)g.fd[1] + 2, total_planes};
+        const uint32_t rbox[4] = {32, 8, 1, 1};
+        const void* rptrs[2] = {y_hi, y_lo};
+        for (int i = 0; i < 2; ++i) {
+          if (!rptrs[i]) continue;
+          if ((rc = encode_map_strided(&em[4 + i], rptrs[i], t.fmt, 4, rdims, estr, rbox,
+                                       CU_TENSOR_MAP_SWIZZLE_64B)))
+            return rc;
+        }
       }
     }
     rc = launch_umma_zring(p, tm_a_hi, tm_w_hi, em, epi, ctas, smem, as_stream(stream));

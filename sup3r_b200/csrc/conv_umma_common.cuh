@@ -27,6 +27,7 @@ struct UmmaParams {
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
   int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
   int epi_v2;         // zring 16-bit epilogue: 0 thread-per-row, 1 LSU-coalescing, 2 TMA tile I/O
+  int epi_row_tma;    // V4: y-halo rows stored by TMA (needs X % 8 == 0)
   int epi_bufs;       // TMA epilogue: staging boxes per warp (1 or 2)
   int tile_fast;      // tile kernel: straight-line MMA role (3-D plane mode, R = 2, XB = 10, WS = 4)
   int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
@@ -219,7 +220,7 @@ int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtenso
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
                      uint32_t smem, cudaStream_t st);
 int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w,
-                      const CUtensorMap* epi_maps /* res_hi, res_lo, y_hi, y_lo or NULL */,
+                      const CUtensorMap* epi_maps /* res_hi, res_lo, y_hi, y_lo, row_hi, row_lo or NULL */,
                       int epi, int ctas, uint32_t smem, cudaStream_t st);
 int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                      const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,

@@ -34,7 +34,8 @@ constexpr int RB_TMEMPTR = RB_ACCEMPTY + 2;
 constexpr int RB_EPILD = RB_TMEMPTR + 2;     // 2 x 8 per-warp residual load barriers (TMA epilogue)
 
 struct EpiMaps {
-  CUtensorMap res_hi, res_lo, y_hi, y_lo;   // interior views, box 64 x 8 x 2 x 1 (TMA epilogue)
+  CUtensorMap res_hi, res_lo, y_hi, y_lo;   // interior views, box 32 ch x 8 x 4 x 1 (TMA epilogue)
+  CUtensorMap row_hi, row_lo;               // padded views, box 32 ch x 8 x 1 x 1 (y halo rows)
 };
 
 template <int N>
@@ -369,6 +370,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v2(const ConvGeom& g, const E
 struct EpiTma {
   const CUtensorMap* res[2];   // hi, lo (interior view of the padded 16-bit tensor)
   const CUtensorMap* out[2];
+  const CUtensorMap* row[2];   // y-halo rows by TMA (nullptr: from registers)
   uint32_t stage_s0, stage_s1; // shared addresses of this warp's staging boxes (1 KiB aligned)
   uint8_t *stage0, *stage1;    // generic pointers to the same
   uint32_t bar0, bar1;         // load barrier of each box
@@ -558,7 +560,8 @@ template <bool kRes>
 __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const Epilogue& ep,
                                                       const float* sbias, uint32_t t_addr,
                                                       const TileGeom& tg, int plane_coord,
-                                                      int mz_planes, EpiTma& et, int lane) {
+                                                      int mz_planes, EpiTma& et, int lane,
+                                                      bool prefetched) {
   const int fmt = ep.fmt;
   const int FY = g.fd[1], FX = g.fd[2];
   const int yl = lane >> 3, xl = lane & 7;
@@ -568,6 +571,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
   const bool res_has_lo = kRes && ep.res_lo != nullptr;
   uint8_t* const sb = et.stage0;
   const uint32_t sbs = et.stage_s0;
+  const bool row_tma = et.row[0] != nullptr;
 
   auto box_free = [&]() {   // the last store issued by this warp has read the box
     if (lane == 0) tma_store_wait_read();
@@ -579,8 +583,10 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
       tma_load_4d(sbs, op ? et.res[1] : et.res[0], et.bar0, 32 * c2, tg.x0, tg.y0, plane_coord);
     }
   };
-  box_free();
-  if (kRes) issue_res(0, 0);
+  if (!prefetched) {   // (the caller may have done this before waiting for the accumulator)
+    box_free();
+    if (kRes) issue_res(0, 0);
+  }
 
   const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * 128;
   const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
@@ -661,14 +667,29 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
           tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord);
           if (mz_planes != 0)
             tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes);
+          if (row_tma) {
+            // REFLECT halo rows y = -1 (copy of y = 1) and y = FY (copy of FY - 2): one 8-voxel
+            // row of the box each, stored at the padded row index (and its z mirror)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int yy = e == 0 ? 1 : FY - 2;
+              if (yy >= tg.y0 && yy < tg.y0 + 4) {
+                const uint32_t src = sbs + (uint32_t)(yy - tg.y0) * 512u;
+                const int ypad = e == 0 ? 0 : FY + 1;
+                tma_store_4d(et.row[op], src, 32 * c2, tg.x0 + 1, ypad, plane_coord);
+                if (mz_planes != 0)
+                  tma_store_4d(et.row[op], src, 32 * c2, tg.x0 + 1, ypad, plane_coord + mz_planes);
+              }
+            }
+          }
           tma_store_commit();
         }
-        if (row_valid && (my | mx) != 0) {
+        if (row_valid && (row_tma ? mx : (my | mx)) != 0) {
           uint8_t* dst = reinterpret_cast<uint8_t*>(op == 0 ? ep.y_hi : ep.y_lo) + row_off + 64 * c2;
 #pragma unroll 1
           for (int combo = 1; combo < 8; ++combo) {
             const bool a = combo & 4, bq = combo & 2, cq = combo & 1;
-            if (!(bq || cq)) continue;
+            if (!(bq || cq) || (row_tma && !cq)) continue;
             if ((a && mzb == 0) || (bq && my == 0) || (cq && mx == 0)) continue;
             uint4* d = reinterpret_cast<uint4*>(dst + (a ? mzb : 0) + (bq ? my : 0) + (cq ? mx : 0));
 #pragma unroll
@@ -1084,6 +1105,8 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     EpiTma et;
     et.res[0] = &em.res_hi; et.res[1] = &em.res_lo;
     et.out[0] = &em.y_hi; et.out[1] = &em.y_lo;
+    et.row[0] = p.epi_row_tma ? &em.row_hi : nullptr;
+    et.row[1] = p.epi_row_tma ? &em.row_lo : nullptr;
     et.nb = EPI == EPI_V4 ? 1 : p.epi_bufs;
     et.stage_s0 = bar_base + 2048u + (uint32_t)((warp - 4) * et.nb) * 2048u;
     et.stage_s1 = et.stage_s0 + 2048u;
@@ -1101,6 +1124,20 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     for (int i = i0; i < i1; ++i) {
       const RingItem c = ring_decode(p, i, i0, i1);
       long long c0 = tr ? clock64() : 0;
+      bool prefetched = false;
+      if (EPI == EPI_V4 && wg < c.ri && !(p.dbg_flags & 8)) {
+        // the residual tile does not depend on the accumulator: start its first TMA load (and
+        // retire the previous tile's stores) before waiting for the MMAs of this item
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (p.ep.res_hi && lane == 0) {
+          const ConvGeom& g = p.g;
+          const int plane_coord = c.b * (g.fd[0] + 2) + c.pl0 + wg + 1;
+          mbar_expect_tx(et.bar0, 2048u);
+          tma_load_4d(et.stage_s0, et.res[0], et.bar0, 0, c.xb * 8, c.yb * 16 + q * 4, plane_coord);
+        }
+        prefetched = true;
+      }
       mbar_wait_inl(bar(RB_ACCFULL + ab), abph, p.dbg, 6, ab, i - i0);
       long long c1 = tr ? clock64() : 0;
       if (tr) t_wait += c1 - c0;
@@ -1124,9 +1161,11 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
                                 ((uint32_t)(q * 32) << 16);
             if (EPI == EPI_V4) {
               if (p.ep.res_hi)
-                ring_epilogue_warp_v4<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+                ring_epilogue_warp_v4<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
+                                            prefetched);
               else
-                ring_epilogue_warp_v4<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
+                ring_epilogue_warp_v4<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
+                                             prefetched);
             } else if (p.ep.res_hi)
               ring_epilogue_warp_v3<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane);
             else
@@ -1195,6 +1234,7 @@ int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorM
   memset(&em, 0, sizeof(em));
   if (epi_maps) {
     em.res_hi = epi_maps[0]; em.res_lo = epi_maps[1]; em.y_hi = epi_maps[2]; em.y_lo = epi_maps[3];
+    em.row_hi = epi_maps[4]; em.row_lo = epi_maps[5];
   }
   if (p.epi_v2 == 3 && p.R == 4) return launch_zring_t<4, EPI_V4>(p, a, w, em, ctas, smem, st);
   if (p.epi_v2 == 2 && p.R == 4) return launch_zring_t<4, EPI_V3>(p, a, w, em, ctas, smem, st);
