@@ -76,6 +76,13 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   }
 }
 
+// out-of-line copy for hot epilogues: keeps tanh / sigmoid code out of their unrolled loops
+// (the inlined switch per element bloated the epilogues past the instruction cache: ncu showed
+// `no_inst` stalls on the LeakyReLU compares of the depth_to_space head)
+static __device__ __noinline__ float apply_act_slow(float v, int act, float alpha) {
+  return apply_act(v, act, alpha);
+}
+
 __device__ __forceinline__ uint16_t to16(float v, int fmt) {
   if (fmt == 0) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
   return __half_as_ushort(__float2half_rn(v));

@@ -255,6 +255,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   S3_REQUIRE(found, "s3_conv_fwd_umma: no tile shape fits shared memory (Y=%d, npad=%d)", Y, p.npad);
   p.acc_bufs = (2 * p.R * p.npad <= 512) ? 2 : 1;
+  if (!zring) p.dbg_flags = t.ring_slots;   // tile / zcat kernels: ring_slots carries experiment flags
   p.tile_fast = (!zcat && kz == 3 && !p.split && !p.flat && p.R == 2 && p.XB == 10 && p.YB == 18 &&
                  p.WS == 4 && p.ntaps == 27 && !(t.box_y & 16)) ? 1 : 0;
   if (!p.flat) {

@@ -183,7 +183,8 @@ __device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const S
                    ((((long long)c.b * g.fd[0] + (long long)plane * r) * g.fd[1] + (long long)y * r) *
                         g.fd[2] + x) * g.cstride + g.coff;
   int ri = 0, rj = 0;   // run counters: channel run number = ri * r + rj
-  const int cout = g.cout;
+  const int cout = g.cout, act = g.act;
+  const float alpha = g.alpha;
 #pragma unroll 1
   for (int c0 = 0; c0 < cout; c0 += 32) {
     uint32_t raw[32];
@@ -195,13 +196,21 @@ __device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const S
     for (int s = 0; s < 4; ++s) {
       if (c0 + 8 * s < cout) {
         float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(sm.sbias + c0 + 8 * s);
+        const float4 b1 = *reinterpret_cast<const float4*>(sm.sbias + c0 + 8 * s + 4);
+        v[0] = __uint_as_float(raw[8 * s]) + b0.x;     v[1] = __uint_as_float(raw[8 * s + 1]) + b0.y;
+        v[2] = __uint_as_float(raw[8 * s + 2]) + b0.z; v[3] = __uint_as_float(raw[8 * s + 3]) + b0.w;
+        v[4] = __uint_as_float(raw[8 * s + 4]) + b1.x; v[5] = __uint_as_float(raw[8 * s + 5]) + b1.y;
+        v[6] = __uint_as_float(raw[8 * s + 6]) + b1.z; v[7] = __uint_as_float(raw[8 * s + 7]) + b1.w;
+        if (act == S3_ACT_LEAKY) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float a = __uint_as_float(raw[8 * s + k]) + sm.sbias[c0 + 8 * s + k];
-          if (g.act == S3_ACT_LEAKY) a = a >= 0.f ? a : g.alpha * a;
-          else if (g.act == S3_ACT_RELU) a = fmaxf(a, 0.f);
-          else if (g.act != S3_ACT_NONE) a = apply_act(a, g.act, g.alpha);
-          v[k] = a;
+          for (int k = 0; k < 8; ++k) v[k] = v[k] >= 0.f ? v[k] : alpha * v[k];
+        } else if (act == S3_ACT_RELU) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        } else if (act != S3_ACT_NONE) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = apply_act_slow(v[k], act, alpha);
         }
         uint4 u;
         u.x = pack2(v[0], v[1], ep.fmt);

@@ -172,7 +172,7 @@ conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
       mbar_wait(bar(B_ACCFULL + ab), abph, p.dbg, 6, ab, it);
       tc_fence_after();
       // two epilogue warps per TMEM lane quarter: they alternate over the R tiles of the item
-      for (int r = (warp - 2) >> 2; r < p.R; r += 2) {
+      for (int r = (warp - 2) >> 2; r < p.R && !(p.dbg_flags & 8); r += 2) {
         const uint32_t ta = tmem_base + (uint32_t)((ab * p.R + r) * p.npad);
         if (EPI == EPI_D2S16)
           epilogue_tile_d2s16(p, sm, c, c.row0 + r * p.TS, ta, warp, lane);

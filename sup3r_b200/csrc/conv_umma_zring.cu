@@ -121,7 +121,7 @@ __device__ __forceinline__ void ring_epilogue_row64(const ConvGeom& g, const Epi
     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+    for (int j = 0; j < 64; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
   }
   if (has_res) {
 #pragma unroll
@@ -282,7 +282,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v2(const ConvGeom& g, const E
     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+    for (int j = 0; j < 64; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
   }
 
   // ---- residual: coalesced registers -> staging -> own row (rounds: hi h0, hi h1, lo h0, lo h1)
@@ -453,7 +453,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v3(const ConvGeom& g, const E
     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+    for (int j = 0; j < 64; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
   }
 
   const long long tp1 = et.trace ? clock64() : 0;
@@ -622,7 +622,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+      for (int j = 0; j < 32; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
     }
     if (kRes) {
 #pragma unroll
