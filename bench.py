@@ -350,7 +350,7 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         kname = ("conv_umma_tile_kernel (split operands, 3 MMA passes)" if split
-                 else "conv_umma_zring_kernel<4, EPI_V3>")
+                 else "conv_umma_zring_kernel<4, EPI_V4>")
         roof = {"bound": "tensor", "kernel": kname + " (64->64 3x3x3 reflect "
                 f"conv, {n}x16x16x288 voxels, bf16 padded in/out; launch mix of the model step: "
                 f"{n_plain} plain + {n_res} residual launches)", "achieved": achieved,
