@@ -61,6 +61,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 __device__ __noinline__ float act_slow(float v, int act, float alpha) { return apply_act(v, act, alpha); }
 
+// kTwo (cout <= 4): one accumulator row holds TWO neighbouring output voxels (n = voxel * 4 +
+// channel) computed from a 4-wide x window (K = 9 x 4 taps x 8 ch = 18 k-steps per voxel pair
+// instead of 2 x 14): the kernel is bound by the legacy HMMA issue rate (~32 cycles per
+// m16n8k16 and SM sub-partition on B200), so fewer MMAs per voxel is the lever.
+template <bool kTwo>
 __global__ void __launch_bounds__(M_THREADS, 3)
 conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
                       const uint4* __restrict__ x16, const float* __restrict__ w,
@@ -178,17 +183,27 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
   // ---- B fragments: k = tap * 8 + ci (tap 27 = zero), n = output channel (>= cout -> 0)
   // thread (grp = lane / 4, t4 = lane % 4) holds b0 = {B[2 t4][grp], B[2 t4 + 1][grp]},
   // b1 = {B[2 t4 + 8][grp], B[2 t4 + 9][grp]} of every k-step
-  uint32_t bf[M_KSTEPS][2];
+  constexpr int kSteps = kTwo ? 18 : M_KSTEPS;
+  uint32_t bf[kSteps][2];
   {
     const int grp = lane >> 2, t4 = lane & 3;
 #pragma unroll
-    for (int j = 0; j < M_KSTEPS; ++j) {
+    for (int j = 0; j < kSteps; ++j) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int tap = 2 * j + hh;
         float v0 = 0.f, v1 = 0.f;
-        if (tap < 27 && grp < cout) {
-          const int c0 = 2 * t4, c1 = 2 * t4 + 1;
+        const int c0 = 2 * t4, c1 = 2 * t4 + 1;
+        if (kTwo) {
+          // tap = (dz, dy, dxw) over a 4-wide x window; n = grp = voxel * 4 + channel
+          const int dz = tap / 12, dy = (tap / 4) % 3, dxw = tap % 4;
+          const int vsel = grp >> 2, co = grp & 3, dx = dxw - vsel;
+          if (dx >= 0 && dx < 3 && co < cout) {
+            const int t3 = (dz * 3 + dy) * 3 + dx;
+            if (c0 < cin) v0 = __ldg(w + ((size_t)t3 * cin + c0) * cout + co);
+            if (c1 < cin) v1 = __ldg(w + ((size_t)t3 * cin + c1) * cout + co);
+          }
+        } else if (tap < 27 && grp < cout) {
           if (c0 < cin) v0 = __ldg(w + ((size_t)tap * cin + c0) * cout + grp);
           if (c1 < cin) v1 = __ldg(w + ((size_t)tap * cin + c1) * cout + grp);
         }
@@ -197,32 +212,42 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
     }
   }
 
-  // ---- main loop: warp = (z, x half); two y rows per iteration
-  const int wz = warp >> 1, wx = (warp & 1) * 16;
+  // ---- main loop.  !kTwo: warp = (z, 16-voxel x half), all 16 y rows; kTwo: warp = (z, y half),
+  // the 32 x voxels of a row are 16 accumulator rows of two voxels each.  Two y rows per step.
+  const int wz = warp >> 1;
+  const int wx = kTwo ? 0 : (warp & 1) * 16;
+  const int y_begin = kTwo ? (warp & 1) * (MT_Y / 2) : 0;
+  const int y_end = kTwo ? y_begin + MT_Y / 2 : MT_Y;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sin);
   const uint32_t zero_addr = (uint32_t)__cvta_generic_to_shared(szero) + (uint32_t)(lane & 7) * 16u;
-  // ldmatrix row address of this lane: matrix (lane / 8): voxels (lane % 8) + 8 * (mat & 1) of
+  // ldmatrix row address of this lane: matrix (lane / 8): rows (lane % 8) + 8 * (mat & 1) of
   // tap 2 j + (mat >> 1)
   const int mat = lane >> 3;
-  const int lvox = (lane & 7) + 8 * (mat & 1);
+  const int lrow = (lane & 7) + 8 * (mat & 1);
   const int ltap = mat >> 1;
   const int grp = lane >> 2, t4 = lane & 3;
   const int oz = z0 + wz;
 
-  // per-lane shared-memory offset of every k-step's row address at y row 0 (tap 27 = zero row)
-  uint32_t toff[M_KSTEPS];
+  // per-lane shared-memory offset of every k-step's row address at y row 0
+  uint32_t toff[kSteps];
 #pragma unroll
-  for (int j = 0; j < M_KSTEPS; ++j) {
+  for (int j = 0; j < kSteps; ++j) {
     const int tap = 2 * j + ltap;
-    const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
-    toff[j] = sbase + (uint32_t)((((wz + dz) * MH_Y + dy) * MH_X + wx + lvox + dx) * 16);
+    if (kTwo) {
+      const int dz = tap / 12, dy = (tap / 4) % 3, dxw = tap % 4;
+      toff[j] = sbase + (uint32_t)((((wz + dz) * MH_Y + dy) * MH_X + 2 * lrow + dxw) * 16);
+    } else {
+      const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
+      toff[j] = sbase + (uint32_t)((((wz + dz) * MH_Y + dy) * MH_X + wx + lrow + dx) * 16);
+    }
   }
-  const bool zero_last = ltap == 1;   // tap 27 only occurs in the last k-step, second half
-  // per-thread epilogue constants (channels 2 t4, 2 t4 + 1)
+  const bool zero_last = !kTwo && ltap == 1;   // tap 27 (zero) = last k-step, second half
+  // per-thread epilogue constants
   const int act = g.act, cstride = g.cstride, coff = g.coff;
   const float alpha = g.alpha;
   const bool pair_ok = ((cstride | coff) & 1) == 0;
-  const int ec0 = 2 * t4, ec1 = 2 * t4 + 1;
+  const int ec0 = kTwo ? (2 * t4) & 3 : 2 * t4, ec1 = ec0 + 1;
+  const int vsel = kTwo ? t4 >> 1 : 0;
   const float bias0 = (ep.bias && ec0 < cout) ? ep.bias[ec0] : 0.f;
   const float bias1 = (ep.bias && ec1 < cout) ? ep.bias[ec1] : 0.f;
   const float sc0 = (ep.post_scale && ec0 < cout) ? ep.post_scale[ec0] : 1.f;
@@ -231,18 +256,18 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
   const float sh1 = (ep.post_scale && ep.post_shift && ec1 < cout) ? ep.post_shift[ec1] : 0.f;
 
 #pragma unroll 1
-  for (int yy = 0; yy < MT_Y; yy += 2) {
+  for (int yy = y_begin; yy < y_end; yy += 2) {
     float acc[2][4];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
 #pragma unroll
-    for (int j = 0; j < M_KSTEPS; ++j) {
+    for (int j = 0; j < kSteps; ++j) {
       uint32_t a[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const uint32_t addr = (j == M_KSTEPS - 1 && zero_last)
+        const uint32_t addr = (j == kSteps - 1 && zero_last)
                                   ? zero_addr
                                   : toff[j] + (uint32_t)((yy + u) * MH_X * 16);
         ldmatrix_x4(addr, a[u]);
@@ -250,17 +275,18 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
 #pragma unroll
       for (int u = 0; u < 2; ++u) mma_bf16_16816(acc[u], a[u], bf[j][0], bf[j][1]);
     }
-    // ---- epilogue: thread holds (voxel grp, channels 2 t4, 2 t4 + 1) and (voxel grp + 8, same)
+    // ---- epilogue: thread holds rows grp and grp + 8, accumulator columns 2 t4, 2 t4 + 1
     if (oz < Z && ec0 < cout) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int oy = y0 + yy + u;
         if (oy >= Y) continue;
-        const size_t vox0 = (((size_t)b * Z + oz) * Y + oy) * X + x0 + wx + grp;
+        const size_t row0 = (((size_t)b * Z + oz) * Y + oy) * X;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          if (x0 + wx + grp + 8 * hh >= X) continue;
-          const size_t vox = vox0 + 8 * hh;
+          const int ox = kTwo ? x0 + 2 * (grp + 8 * hh) + vsel : x0 + wx + grp + 8 * hh;
+          if (ox >= X) continue;
+          const size_t vox = row0 + ox;
           float v0 = acc[u][2 * hh] + bias0, v1 = acc[u][2 * hh + 1] + bias1;
           if (act == S3_ACT_LEAKY) {
             v0 = v0 >= 0.f ? v0 : alpha * v0;
@@ -307,8 +333,10 @@ int try_conv_small_mma(const ConvGeom& g, const float* x, const void* x16, const
   const size_t smem = sizeof(uint4) * (M_HALO_VOX + 8);
   static bool set = false;
   if (!set) {
-    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = true;
   }
   const int tx = (g.in[2] + MT_X - 1) / MT_X, ty = (g.in[1] + MT_Y - 1) / MT_Y;
@@ -318,8 +346,12 @@ int try_conv_small_mma(const ConvGeom& g, const float* x, const void* x16, const
     set_error("conv_small_mma: grid too large");
     return S3_ERR_INVALID;
   }
-  conv_small_mma_kernel<<<(unsigned)blocks, M_THREADS, smem, st>>>(
-      g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
+  if (g.cout <= 4)
+    conv_small_mma_kernel<true><<<(unsigned)blocks, M_THREADS, smem, st>>>(
+        g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
+  else
+    conv_small_mma_kernel<false><<<(unsigned)blocks, M_THREADS, smem, st>>>(
+        g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
   S3_CUDA(cudaGetLastError());
   return 1;
 }
