@@ -17,7 +17,13 @@ class GeneratePipeline:
     a pinned buffer that stays valid until two more batches have been pushed)."""
 
     def __init__(self, model, lr_shape, precision=None, norm_in=True, un_norm_out=True,
-                 slots=2):
+                 slots=2, fresh_host=False, check=False):
+        """``fresh_host``: every result gets its own pinned buffer (from torch's caching
+        host allocator) that the caller may keep; ``check``: per-chunk device-side
+        (min, max, n_nan) of every output channel (``ForwardPass._output_check``,
+        forward_pass.py:384-425) travels with the result: ``pop()`` -> (array, checks)."""
+        self.fresh_host = fresh_host
+        self.check = check
         if not torch.cuda.is_available():
             raise RuntimeError("GeneratePipeline needs a CUDA device (no CPU fallback)")
         self.model = model
@@ -52,6 +58,8 @@ class GeneratePipeline:
                 x_dev=torch.empty(self.lr_shape, dtype=torch.float32, device=self.dev),
                 y_host=torch.empty(self.hr_shape, dtype=torch.float32).pin_memory(),
                 h2d=torch.cuda.Event(), run=torch.cuda.Event(), d2h=torch.cuda.Event(),
+                chk_host=torch.empty((self.hr_shape[0], self.hr_shape[-1], 3),
+                                     dtype=torch.float32).pin_memory(),
                 busy=False))
         self._next = 0
         self._queue = []
@@ -67,7 +75,9 @@ class GeneratePipeline:
                 sl["plan"].run_graphed(x, None, *self.post)
         torch.cuda.synchronize(self.dev)
 
-    def push(self, lr_batch):
+    def push(self, lr_batch, crops=None):
+        """``crops``: optional per-chunk high-res slices the device-side check is restricted to
+        (the reference checks the cropped chunk)."""
         sl = self.slots[self._next]
         if sl["busy"]:
             raise RuntimeError("pipeline slot still holds an un-popped result: call pop() first")
@@ -84,10 +94,23 @@ class GeneratePipeline:
                 from .. import ops
                 x = ops.channel_affine(x, *self.norm)
             out = sl["plan"].run_graphed(x, None, *self.post)
+            chk = None
+            if self.check:
+                from .. import ops
+                parts = []
+                for k in range(out.shape[0]):
+                    o = out[k] if crops is None or crops[k] is None else out[k][crops[k]]
+                    parts.append(ops.channel_check(o.contiguous()))
+                chk = torch.stack(parts)
             sl["run"].record(self.s_run)
+        if self.fresh_host:
+            sl["y_host"] = torch.empty(self.hr_shape, dtype=torch.float32, pin_memory=True)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(sl["run"])
             sl["y_host"].copy_(out, non_blocking=True)
+            if chk is not None:
+                chk.record_stream(self.s_out)
+                sl["chk_host"].copy_(chk, non_blocking=True)
             sl["d2h"].record(self.s_out)
         sl["busy"] = True
         self._queue.append(self._next)
@@ -98,6 +121,8 @@ class GeneratePipeline:
         sl = self.slots[i]
         sl["d2h"].synchronize()
         sl["busy"] = False
+        if self.check:
+            return sl["y_host"].numpy(), sl["chk_host"].numpy().copy()
         return sl["y_host"].numpy()
 
     def run(self, batches):

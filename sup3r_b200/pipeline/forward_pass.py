@@ -218,27 +218,73 @@ class ForwardPass:
             cls._check_nan_input(chunk, model)
             groups.setdefault(chunk.input_data.shape, []).append(chunk)
         outputs = {}
+        from .engine import GeneratePipeline
+        cache = model.__dict__.setdefault("_fwp_pipelines", {})
         for shape, chunks in groups.items():
-            for i in range(0, len(chunks), batch_size):
-                part = chunks[i:i + batch_size]
-                batch = np.stack([c.input_data for c in part], axis=0)
-                try:
-                    hi_res = model.generate(batch)
-                except Exception as e:
-                    msg = f"Forward pass failed on chunk batch with shape {batch.shape}."
-                    logger.exception(msg)
-                    raise RuntimeError(msg) from e
-                cls._check_enhancement(hi_res, batch, model.s_enhance, model.t_enhance, 1, 3)
-                for c, hr in zip(part, hi_res):
-                    data = hr[c.hr_crop_slice]
-                    if cls._output_check(data, strategy.allowed_const):
+            lr_shape = (batch_size, *shape)
+            key = (lr_shape, model.precision)
+            pipe = cache.get(key)
+            if pipe is None:
+                # pinned buffers, H2D / generator / D2H on three streams, device-side output
+                # check: the host only slices views of the returned arrays
+                pipe = cache[key] = GeneratePipeline(model, lr_shape, check=True)
+            parts = [chunks[i:i + batch_size] for i in range(0, len(chunks), batch_size)]
+
+            def batches():
+                for part in parts:
+                    batch = np.stack([c.input_data for c in part]
+                                     + [part[-1].input_data] * (batch_size - len(part)), axis=0)
+                    yield batch, [c.hr_crop_slice for c in part] + [None] * (batch_size - len(part))
+
+            def finish(part, hi_res, checks):
+                cls._check_enhancement(hi_res, np.empty(lr_shape), model.s_enhance,
+                                       model.t_enhance, 1, 3)
+                if any(c.out_file is None for c in part):
+                    # results kept in memory leave the (reused) pinned slot through one
+                    # multi-threaded copy; chunk files are written straight from the slot
+                    import torch
+                    hi_res = torch.empty(hi_res.shape, dtype=torch.float32).copy_(
+                        torch.from_numpy(hi_res)).numpy()
+                for k, c in enumerate(part):
+                    if cls._device_check_failed(checks[k], strategy.allowed_const):
                         raise MemoryError(f"Forward pass for chunk_index {c.index} failed with "
                                           "constant output or NaNs.")
+                    data = hi_res[k][c.hr_crop_slice]
                     if c.out_file is not None:
                         cls._write_output(data, c, fwp.meta)
                     else:
                         outputs[c.index] = data
+
+            pending = []          # chunk lists of the batches in flight, oldest first
+            for part, (batch, crops) in zip(parts, batches()):
+                if len(pipe._queue) == len(pipe.slots):
+                    hi_res, checks = pipe.pop()
+                    finish(pending.pop(0), hi_res, checks)
+                pipe.push(batch, crops)
+                pending.append(part)
+            while pending:
+                hi_res, checks = pipe.pop()
+                finish(pending.pop(0), hi_res, checks)
         return outputs
+
+    @staticmethod
+    def _device_check_failed(chk, allowed_const):
+        """``_output_check`` (forward_pass.py:384-425) from the device-side per-channel
+        (min, max, n_nan) table of one chunk."""
+        if allowed_const is True:
+            return False
+        if allowed_const is False or allowed_const is None:
+            allowed_const = []
+        elif not isinstance(allowed_const, (list, tuple)):
+            allowed_const = [allowed_const]
+        if (chk[:, 2] > 0).any() or np.isnan(chk[:, :2]).any():
+            logger.error("Forward pass output contains NaN values!")
+            return True
+        for i in range(chk.shape[0]):
+            if chk[i, 0] == chk[i, 1] and chk[i, 0] not in allowed_const:
+                logger.error("All values are the same for feature channel %d!", i)
+                return True
+        return False
 
     @staticmethod
     def _check_nan_input(chunk, model):

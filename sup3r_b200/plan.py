@@ -475,6 +475,13 @@ class Plan:
     def run_graphed(self, x, exo=None, post_scale=None, post_shift=None):
         """Replay a captured CUDA graph of ``run`` for this input shape (launch-bound nets)."""
         exo = exo or {}
+        # packed tensor-core weights are baked into the captured graph: re-capture after any
+        # weight update (optimizer step, set_weights, load)
+        wver = tuple((st.conv.kernel.version, st.conv.kernel.value.data_ptr())
+                     for st in self.steps if isinstance(st, FusedConv))
+        if wver != getattr(self, "_graph_wver", None):
+            self._graphs.clear()
+            self._graph_wver = wver
         key = (tuple(x.shape), tuple(sorted((k, tuple(v.shape)) for k, v in exo.items())),
                post_scale is not None)
         g = self._graphs.get(key)
