@@ -407,3 +407,29 @@ def test_multi_step_gan_chain(cuda):
     step1 = m1.generate(x)
     step2 = m2.generate(np.transpose(step1, (1, 2, 0, 3))[None])
     assert out.shape == (1, 12, 12, 8, 2) and np.array_equal(out, step2)
+
+
+def test_graph_recaptured_after_weight_update(cuda):
+    """The packed tensor-core weights are baked into the captured CUDA graph: a weight update
+    (optimizer step / set_weights) must re-capture it."""
+    m = _fwp_model()
+    x = np.random.default_rng(3).standard_normal((1, 8, 8, 6, 2)).astype(np.float32)
+    y0 = m.generate(x, precision="bf16")
+    w = m.generator.get_weights()
+    m.generator.set_weights([a * 1.5 for a in w])
+    y1 = m.generate(x, precision="bf16")                     # graph path
+    y1_eager = m.generate(x, precision="bf16", use_graph=False)
+    assert not np.allclose(y0, y1)
+    assert np.array_equal(y1, y1_eager)
+
+
+def test_forward_pass_output_check_on_device(cuda):
+    """_output_check semantics (forward_pass.py:384-425) of the batched path: NaN / constant
+    channels are found from the device-side (min, max, n_nan) table."""
+    from sup3r_b200.pipeline import ForwardPass
+    chk = np.array([[0.0, 1.0, 0.0], [2.0, 2.0, 0.0]], dtype=np.float32)
+    assert ForwardPass._device_check_failed(chk, allowed_const=None)
+    assert not ForwardPass._device_check_failed(chk, allowed_const=[2.0])
+    assert not ForwardPass._device_check_failed(chk, allowed_const=True)
+    chk[0, 2] = 3.0
+    assert ForwardPass._device_check_failed(chk, allowed_const=[2.0])
