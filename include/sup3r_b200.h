@@ -68,6 +68,17 @@ typedef struct s3_conv_desc {
   int32_t out_repeat[3]; /* nearest-neighbour repeat of the mapped output per dim (>= 1) */
   int32_t out_cstride; /* channels per voxel of the destination buffer (0 = mapped channels) */
   int32_t out_coffset; /* first destination channel (concat-by-stride) */
+  /* channel slice of a wider convolution (both 0 = the whole convolution): this call computes
+   * output channels [cout_base, cout_base + cout) of a convolution with cout_total channels --
+   * w / bias are the slice, the scatter map (d2s / d2t) is that of the full convolution.  Lets a
+   * head with more than 256 channels (e.g. 64 -> 1600 with 5x depth_to_space) run as several
+   * tcgen05 launches into one destination. */
+  int32_t cout_total;
+  int32_t cout_base;
+  /* 1: the f32 `residual` is added BEFORE the activation (partial sums of a convolution split
+   * over input-channel groups, e.g. 64 tensor-core channels + the Sup3rConcat exo channel);
+   * 0: after it (SkipConnection). */
+  int32_t res_pre_act;
 } s3_conv_desc;
 
 /* conv_dims: conv output extents before the scatter; out_dims/out_channels: after it. */

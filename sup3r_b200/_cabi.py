@@ -28,6 +28,7 @@ class ConvDesc(C.Structure):
         ("pad_mode", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
         ("d2s", C.c_int32), ("d2t", C.c_int32), ("t_roll", C.c_int32),
         ("out_repeat", c_i32x3), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32),
+        ("cout_total", C.c_int32), ("cout_base", C.c_int32), ("res_pre_act", C.c_int32),
     ]
 
 

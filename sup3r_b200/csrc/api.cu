@@ -72,9 +72,14 @@ int make_geom(const s3_conv_desc* d, ConvGeom* g) {
   g->m = d->d2t < 1 ? 1 : d->d2t;
   g->roll = d->t_roll;
   S3_REQUIRE(g->m == 1 || d->ndim == 3, "depth_to_time needs a 3-D conv");
-  S3_REQUIRE(g->cout % (g->r * g->r * g->m) == 0,
-             "cout %d not divisible by d2s^2 * d2t = %d", g->cout, g->r * g->r * g->m);
-  g->cmap = g->cout / (g->r * g->r * g->m);
+  g->res_pre = d->res_pre_act ? 1 : 0;
+  g->ctotal = d->cout_total > 0 ? d->cout_total : g->cout;
+  g->cbase = d->cout_base;
+  S3_REQUIRE(g->cbase >= 0 && g->cbase + g->cout <= g->ctotal,
+             "channel slice [%d, %d) exceeds cout_total %d", g->cbase, g->cbase + g->cout, g->ctotal);
+  S3_REQUIRE(g->ctotal % (g->r * g->r * g->m) == 0,
+             "cout %d not divisible by d2s^2 * d2t = %d", g->ctotal, g->r * g->r * g->m);
+  g->cmap = g->ctotal / (g->r * g->r * g->m);
   if (d->ndim == 3) {
     g->fd[0] = g->od[0] * g->r * g->rep[0];
     g->fd[1] = g->od[1] * g->r * g->rep[1];

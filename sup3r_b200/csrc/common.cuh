@@ -48,6 +48,8 @@ struct ConvGeom {
   int fd[3];       // final (mapped) extents
   int cmap;        // mapped channels per voxel (cout / (r*r*m))
   int cstride, coff;
+  int ctotal, cbase;   // channel slice of a wider convolution (scatter map of the full one)
+  int res_pre;         // f32 residual is added before the activation
 };
 
 int make_geom(const s3_conv_desc* d, ConvGeom* g);  // validates; returns S3_OK or error
@@ -99,9 +101,9 @@ struct Dest {
 
 __device__ __forceinline__ Dest map_dest(const ConvGeom& g, int z, int y, int x, int c) {
   Dest d;
-  int c0 = c, tt = 0, i = 0, j = 0;
+  int c0 = c + g.cbase, tt = 0, i = 0, j = 0;
   if (g.m > 1) {
-    int cq = g.cout / g.m;
+    int cq = g.ctotal / g.m;
     tt = c0 / cq;
     c0 -= tt * cq;
   }
@@ -225,8 +227,9 @@ __device__ __forceinline__ float finish(const ConvGeom& g, const Epilogue& ep, f
                                         size_t conv_vox) {
   float v = acc;
   if (ep.bias) v += ep.bias[c];
+  if (ep.residual && g.res_pre) v += ep.residual[conv_vox * g.cout + c];
   v = apply_act(v, g.act, g.alpha);
-  if (ep.residual) v += ep.residual[conv_vox * g.cout + c];
+  if (ep.residual && !g.res_pre) v += ep.residual[conv_vox * g.cout + c];
   if (ep.post_scale) v = v * ep.post_scale[c] + (ep.post_shift ? ep.post_shift[c] : 0.f);
   return v;
 }

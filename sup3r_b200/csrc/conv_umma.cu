@@ -299,10 +299,15 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     epi = EPI_PLAIN;
   } else if ((g.r > 1 || g.m > 1) && g.rep[0] * g.rep[1] * g.rep[2] == 1 && (y || mapped16) &&
              (!y_hi || mapped16) &&
-             (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) && g.cout % g.cmap == 0 &&
+             (g.cmap == 4 || g.cmap == 8 || g.cmap % 16 == 0) &&
+             g.cout % (g.cmap < 16 ? g.cmap : 16) == 0 && g.cbase % 16 == 0 &&
              g.cstride % 4 == 0 && g.coff % 4 == 0) {
     epi = EPI_D2S;
   }
+  S3_REQUIRE(!g.res_pre || (!zring && !zcat && epi == EPI_PLAIN && g.cout == 64 && g.cstride == 64 &&
+                            g.coff == 0 && !post_scale && residual),
+             "s3_conv_fwd_umma: res_pre_act needs the plain 64-channel tile-kernel configuration "
+             "(2-D or split precision) with an f32 residual");
   if (zring) {
     CUtensorMap em[6];
     memset(em, 0, sizeof(em));

@@ -101,6 +101,13 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
       v[4 * q + 2] = __uint_as_float(raw[cc * 16 + 4 * q + 2]) + bv.z;
       v[4 * q + 3] = __uint_as_float(raw[cc * 16 + 4 * q + 3]) + bv.w;
     }
+    if (has_res && g.res_pre) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 r4 = rpre[cc * 4 + q];
+        v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+      }
+    }
     if (g.act == S3_ACT_LEAKY) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : g.alpha * v[j];
@@ -109,9 +116,9 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
     } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+      for (int j = 0; j < 16; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
     }
-    if (has_res) {
+    if (has_res && !g.res_pre) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 r4 = rpre[cc * 4 + q];
@@ -303,12 +310,15 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
       }
     } else if (EPI == EPI_D2S ||
                (EPI == EPI_GENERIC && mapped && g.rep[0] * g.rep[1] * g.rep[2] == 1 &&
-                (ep.y || ep.y_hi) && (g.cmap == 4 || g.cmap == 8 || g.cmap == 16) &&
-                len % g.cmap == 0)) {
+                (ep.y || ep.y_hi) && (g.cmap == 4 || g.cmap == 8 || g.cmap % 16 == 0) &&
+                len % (g.cmap < 16 ? g.cmap : 16) == 0 && g.cbase % 16 == 0)) {
       // ---- depth_to_space / depth_to_time fast path: runs of cmap channels; f32 (ep.y) or an
       // unpadded 16-bit mapped tensor (ep.y_hi; 8-channel runs of 8 consecutive x voxels form
       // full 128-byte lines per warp instruction)
-      const int nrun = len / g.cmap;
+      // runs of min(cmap, 16) channels: wider mapped voxels (cmap 32, 64, ...) take one
+      // 16-channel piece per step at channel offset d.c
+      const int rs = g.cmap < 16 ? g.cmap : 16;
+      const int nrun = len / rs;
       if (g.cmap == 8 && ep.y_hi && !ep.y) {
         // hot case (5x spatial head -> bf16 high-resolution tensor): static register indices
 #pragma unroll
@@ -328,12 +338,12 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
         continue;
       }
       for (int s = 0; s < nrun; ++s) {
-        const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + s * g.cmap);
+        const Dest d = map_dest(g, rp.z, rp.y, rp.x, c0 + s * rs);
         const size_t doff = ((((size_t)rp.b * g.fd[0] + d.z) * g.fd[1] + d.y) * g.fd[2] + d.x) *
-                                g.cstride + g.coff;
+                                g.cstride + g.coff + d.c;
         if (ep.y_hi) {
           uint16_t* d16 = reinterpret_cast<uint16_t*>(ep.y_hi) + doff;
-          const float* vs = v + s * g.cmap;   // (s * cmap is a multiple of 4: register select below)
+          const float* vs = v + s * rs;   // (s * rs is a multiple of 4: register select below)
           if (g.cmap == 8) {
             const int o = s * 8;
             uint4 u;
@@ -343,7 +353,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
             u.w = pack2(o == 0 ? v[6] : v[14], o == 0 ? v[7] : v[15], ep.fmt);
             *reinterpret_cast<uint4*>(d16) = u;
           } else {
-            for (int k = 0; k < g.cmap; ++k) d16[k] = to16(v[(s * g.cmap + k) & 15], ep.fmt);
+            for (int k = 0; k < rs; ++k) d16[k] = to16(v[(s * rs + k) & 15], ep.fmt);
           }
           (void)vs;
           if (!ep.y) continue;

@@ -85,6 +85,9 @@ class ConvSpec:
     out_repeat: tuple = (1, 1, 1)
     out_cstride: int = 0
     out_coffset: int = 0
+    cout_total: int = 0     # channel slice of a wider convolution (0 = whole convolution)
+    cout_base: int = 0
+    res_pre_act: int = 0    # f32 residual added before the activation (split-K partial sums)
 
     def desc(self, n, in_dims):
         d = ConvDesc()
@@ -99,6 +102,8 @@ class ConvSpec:
         d.d2s, d.d2t, d.t_roll = self.d2s, self.d2t, self.t_roll
         d.out_repeat = c_i32x3(*self.out_repeat)
         d.out_cstride, d.out_coffset = self.out_cstride, self.out_coffset
+        d.cout_total, d.cout_base = self.cout_total, self.cout_base
+        d.res_pre_act = self.res_pre_act
         return d
 
     def out_dims(self, n, in_dims):

@@ -209,9 +209,24 @@ def _umma_ok(fc: FusedConv, in_shape, precision):
     nd = conv.nd
     # (narrow inputs, e.g. the 4-feature first layer, run on the tensor cores with the channel
     # axis zero-padded to 64: cheaper than the latency-bound generic kernel)
-    if in_shape[-1] > 64 or conv.filters > 256 or nd not in (2, 3):
+    if nd not in (2, 3):
         return False
-    if in_shape[-1] < 64 and (nd != 3 or precision != "bf16" or conv.filters < 32):
+    if in_shape[-1] > 64:
+        # 64 feature channels + a few Sup3rConcat exo channels (2-D): tensor cores for the 64,
+        # the fp32 kernel for the rest, summed before the activation
+        if not (nd == 2 and in_shape[-1] <= 72 and conv.filters == 64 and precision == "bf16"
+                and fc.r == 1 and fc.m == 1 and fc.skip_add is None):
+            return False
+    if conv.filters > 256:
+        # wide scatter heads (e.g. 64 -> 1600 with 5x depth_to_space, 64 -> 768 with 24x
+        # depth_to_time) run as channel slices of <= 256 when the mapped voxel is 16-aligned
+        d2t = fc.m if (fc.m > 1 and fc.method == 1) else 1
+        groups = fc.r * fc.r * d2t
+        if groups == 1 or conv.filters % groups or (conv.filters // groups) % 16:
+            return False
+        if fc.m > 1 and fc.method == 0:
+            return False
+    if in_shape[-1] < 64 and (precision != "bf16" or conv.filters < 32):
         return False
     if any(k != 3 for k in conv.kernel_size) or any(s != 1 for s in conv.strides):
         return False
@@ -346,14 +361,40 @@ class Plan:
         # producer writes 16-bit output anyway: hi is the next convolution's operand, hi + lo
         # (~16 mantissa bits) is the addend of the consuming convolution's epilogue
         # (phygnn SkipConnection semantics, call site sup3r/models/abstract.py:1081-1092)
-        pair_skip = want16 and bool(st.skip_store) and not split
+        pair_skip = (want16 and bool(st.skip_store) and not split
+                     and self._ring16_ok(st, out_shape))
         want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
+        if os.environ.get("SUP3R_B200_TRACE_PLAN"):
+            route = ("umma" if _umma_ok(st, shp, self.precision) else
+                     ("small_bf16" if (self.precision == "bf16" and not want16
+                                       and ops.small_bf16_ok(spec)) else "direct"))
+            print(f"[plan] conv {tuple(shp)} -> cout {conv.filters} r={st.r} m={st.m} "
+                  f"skip_add={st.skip_add} store={st.skip_store} want16={want16} route={route}")
         # depth_to_space head feeding the narrow output convolution: hand the high-resolution
         # tensor over as unpadded bf16 (8-channel voxels = 16 B) instead of f32
         map16 = (self.precision == "bf16" and _umma_ok(st, shp, self.precision) and st.r > 1
                  and st.m == 1 and oc == 8 and res_act is None and not st.skip_store and not last
                  and post_scale is None and self._next_is_small_bf16(steps, si, out_shape))
+        if _umma_ok(st, shp, self.precision) and cin > 64:
+            # split over input-channel groups: direct kernel on the exo channels first (no bias,
+            # no activation), then the tensor-core conv on the 64 features adds it pre-activation
+            xf = cur.need_f32()
+            w = conv.conv_kernel().detach()
+            sp_rem = dataclasses.replace(spec, cin=cin - 64, act=S3_ACT_NONE, alpha=0.0)
+            part = ops.conv_fwd(xf[..., 64:].contiguous(), w[..., 64:, :].contiguous(), None, sp_rem)
+            x_hi, x_lo = ops.pack_act_pad16(xf[..., :64].contiguous(), split=split)
+            key = (id(conv), split, "main64")
+            ver = (conv.kernel.version, conv.kernel.value.data_ptr())
+            hit = self._wcache.get(key)
+            if hit is None or hit[0] != ver:
+                hit = (ver, *ops.pack_weights_umma(w[..., :64, :].contiguous(), split=split,
+                                                   ndim=conv.nd))
+                self._wcache[key] = hit
+            sp_main = dataclasses.replace(spec, cin=64, res_pre_act=1)
+            y, y_hi, y_lo = ops.conv_fwd_umma(x_hi, x_lo, hit[1], hit[2], bias, sp_main, n, dims,
+                                              residual=part, want_f32=want32, want_pad16=want16)
+            return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
         if _umma_ok(st, shp, self.precision):
             if cin < 64:
                 x_hi, x_lo = ops.pack_act_pad16(
@@ -361,6 +402,9 @@ class Plan:
                 spec = dataclasses.replace(spec, cin=64)
             else:
                 x_hi, x_lo = cur.need_pad16(split)
+            if conv.filters > 256:
+                y = self._run_wide_head(conv, spec, x_hi, x_lo, bias, n, dims, split, out_shape)
+                return self._finish_conv(st, Act(out_shape, f32=y), skips)
             w_hi, w_lo = self._packed(conv, split)
             res16 = (res_act is not None and not split and not want32 and want16
                      and self._ring16_ok(st, out_shape) and post_scale is None
@@ -390,10 +434,37 @@ class Plan:
                                post_scale=post_scale, post_shift=post_shift,
                                want_pad16=want16, split=split or pair_skip, want_f32=want32)
             y, y_hi, y_lo = res if want16 else (res, None, None)
-        out = Act(out_shape, f32=y, hi=y_hi, lo=y_lo)
+        return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
+
+    @staticmethod
+    def _finish_conv(st, out, skips):
         for name in st.skip_store:
             skips[name] = out
         return out
+
+    def _run_wide_head(self, conv, spec, x_hi, x_lo, bias, n, dims, split, out_shape):
+        """cout > 256 with a depth_to_space / depth_to_time map: channel slices of <= 256 into
+        one f32 destination (``cout_total`` / ``cout_base`` of ``s3_conv_desc``)."""
+        key = (id(conv), split, "wide")
+        ver = (conv.kernel.version, conv.kernel.value.data_ptr())
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                w = conv.conv_kernel().detach()
+                packs = []
+                for cb in range(0, conv.filters, 256):
+                    nc = min(256, conv.filters - cb)
+                    packs.append((cb, nc, *ops.pack_weights_umma(
+                        w[..., cb:cb + nc].contiguous(), split=split, ndim=conv.nd)))
+            hit = (ver, packs)
+            self._wcache[key] = hit
+        y = torch.empty(out_shape, device=x_hi.device, dtype=torch.float32)
+        for cb, nc, w_hi, w_lo in hit[1]:
+            sp = dataclasses.replace(spec, cout=nc, cout_total=conv.filters, cout_base=cb)
+            ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo,
+                              None if bias is None else bias[cb:cb + nc].contiguous(), sp, n, dims,
+                              out=y)
+        return y
 
     def _next_is_small_bf16(self, steps, si, out_shape):
         """Is the consumer of step si's output the narrow tensor-core convolution?"""

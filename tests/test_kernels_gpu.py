@@ -486,3 +486,59 @@ def test_umma_d2s_16bit_destination_feeds_small_conv(cuda):
     ref2 = ops.conv_fwd(y16.float(), dev(w2, cuda), dev(b2, cuda), spec2)
     got2 = ops.conv_fwd_small_bf16(y16, dev(w2, cuda), dev(b2, cuda), spec2)
     assert rel_err(got2.cpu().numpy(), ref2.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("ndim,dims,cout,d2s,d2t,roll", [(2, (1, 12, 16), 1600, 5, 1, 0),
+                                                          (3, (4, 5, 8), 768, 1, 24, 12),
+                                                          (3, (4, 5, 8), 288, 3, 1, 0)])
+def test_umma_wide_scatter_head_in_channel_slices(cuda, ndim, dims, cout, d2s, d2t, roll):
+    """cout > 256 with a depth_to_space / depth_to_time map: <= 256-channel slices of the
+    convolution (cout_total / cout_base) into one destination == the fp32 direct kernel."""
+    from sup3r_b200 import ops
+    import dataclasses
+    rng = np.random.default_rng(cout)
+    n = 2
+    shape = (n, *dims[1:], 64) if ndim == 2 else (n, *dims, 64)
+    k = (3,) * ndim
+    x = _bf16_exact(rng_arr(rng, shape))
+    w = _bf16_exact(rng_arr(rng, (*k, 64, cout), 0.05))
+    b = rng_arr(rng, (cout,), 0.1)
+    xd, wd, bd = dev(x, cuda), dev(w, cuda), dev(b, cuda)
+    pz = 1 if ndim == 3 else 0
+    spec = ops.ConvSpec(ndim, 64, cout, (3 if ndim == 3 else 1, 3, 3), pad_lo=(pz, 1, 1),
+                        pad_hi=(pz, 1, 1), pad_mode=1, act=2, alpha=0.2, d2s=d2s, d2t=d2t,
+                        t_roll=roll)
+    ref = ops.conv_fwd(xd, wd, bd, spec)
+    x_hi, _ = ops.pack_act_pad16(xd)
+    y = torch.empty_like(ref)
+    kd = (1, *dims[1:]) if ndim == 2 else dims
+    for cb in range(0, cout, 256):
+        nc = min(256, cout - cb)
+        w_hi, _ = ops.pack_weights_umma(wd[..., cb:cb + nc].contiguous(), ndim=ndim)
+        sp = dataclasses.replace(spec, cout=nc, cout_total=cout, cout_base=cb)
+        ops.conv_fwd_umma(x_hi, None, w_hi, None, bd[cb:cb + nc].contiguous(), sp, n, kd, out=y)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+def test_umma_split_input_channels_pre_activation_residual(cuda):
+    """65-channel 2-D conv (64 features + 1 Sup3rConcat exo channel) = tensor-core conv on the 64
+    + fp32 conv on the rest, summed BEFORE the LeakyReLU (res_pre_act)."""
+    from sup3r_b200 import ops
+    import dataclasses
+    rng = np.random.default_rng(65)
+    n, dims = 3, (1, 12, 20)
+    x = _bf16_exact(rng_arr(rng, (n, 12, 20, 65)))
+    w = _bf16_exact(rng_arr(rng, (3, 3, 65, 64), 0.05))
+    b = rng_arr(rng, (64,), 0.1)
+    xd, wd, bd = dev(x, cuda), dev(w, cuda), dev(b, cuda)
+    spec = ops.ConvSpec(2, 65, 64, (1, 3, 3), pad_lo=(0, 1, 1), pad_hi=(0, 1, 1), pad_mode=1,
+                        act=2, alpha=0.2)
+    ref = ops.conv_fwd(xd, wd, bd, spec)
+    part = ops.conv_fwd(xd[..., 64:].contiguous(), wd[..., 64:, :].contiguous(), None,
+                        dataclasses.replace(spec, cin=1, act=0))
+    x_hi, _ = ops.pack_act_pad16(xd[..., :64].contiguous())
+    w_hi, _ = ops.pack_weights_umma(wd[..., :64, :].contiguous(), ndim=2)
+    y, _, _ = ops.conv_fwd_umma(x_hi, None, w_hi, None, bd,
+                                dataclasses.replace(spec, cin=64, res_pre_act=1), n, dims,
+                                residual=part)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
