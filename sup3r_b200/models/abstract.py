@@ -494,12 +494,18 @@ class AbstractSingleModel(TensorboardMixIn):
         as a fused plan on the GPU; ``precision`` overrides the model's precision mode."""
         if exogenous_data is not None and not isinstance(exogenous_data, ExoData):
             exogenous_data = ExoData(exogenous_data)
-        low_res = self._combine_fwp_input(np.asarray(low_res), exogenous_data)
+        if isinstance(low_res, torch.Tensor):
+            # device-resident input (MultiStepGan keeps intermediates on the GPU); exo channels
+            # that must be appended to the input are combined on the host like the reference
+            if exogenous_data is not None and len(self.lr_features) > low_res.shape[-1]:
+                low_res = self._combine_fwp_input(low_res.detach().cpu().numpy(), exogenous_data)
+        else:
+            low_res = self._combine_fwp_input(np.asarray(low_res), exogenous_data)
         gen = self.generator
         rank = getattr(gen.layers[0], "rank", None)
         if rank is not None and low_res.ndim != rank:
             raise RuntimeError(f"generator expects {rank}-D input but received shape "
-                               f"{low_res.shape}")
+                               f"{tuple(low_res.shape)}")
         dev = self.torch_device()
         if dev.type != "cuda":
             raise RuntimeError("sup3r_b200 needs a CUDA device to run the generator "

@@ -8,6 +8,7 @@ import logging
 import os
 
 import numpy as np
+import torch
 
 from ..exo import ExoData
 from .base import Sup3rGan
@@ -71,15 +72,19 @@ class MultiStepGan(AbstractInterface):
     def _transpose_model_input(self, model, hi_res):
         """(t, s1, s2, c) <-> (1, s1, s2, t, c) between 4-D and 5-D steps
         (multi_step.py:128-170)."""
+        on_dev = isinstance(hi_res, torch.Tensor)
         if model.is_5d and hi_res.ndim == 4:
-            hi_res = np.transpose(hi_res, axes=(1, 2, 0, 3))[np.newaxis]
+            hi_res = (hi_res.permute(1, 2, 0, 3)[None] if on_dev
+                      else np.transpose(hi_res, axes=(1, 2, 0, 3))[np.newaxis])
         elif model.is_4d and hi_res.ndim == 5:
             assert hi_res.shape[0] == 1, (
-                f"Recieved 5D input data with shape ({hi_res.shape}) to a 4D model.")
-            hi_res = np.transpose(hi_res[0], axes=(2, 0, 1, 3))
+                f"Recieved 5D input data with shape ({tuple(hi_res.shape)}) to a 4D model.")
+            hi_res = (hi_res[0].permute(2, 0, 1, 3) if on_dev
+                      else np.transpose(hi_res[0], axes=(2, 0, 1, 3)))
         else:
             assert model.input_dims == hi_res.ndim, (
-                f"Recieved input data with shape {hi_res.shape} to a {model.input_dims}D model.")
+                f"Recieved input data with shape {tuple(hi_res.shape)} to a {model.input_dims}D "
+                "model.")
         return hi_res
 
     def _match_model_input(self, model_step, hi_res, exo_data):
@@ -104,13 +109,24 @@ class MultiStepGan(AbstractInterface):
         hi_res = np.array(low_res, copy=True)
         for i, model in enumerate(self.models):
             i_norm_in = not (i == 0 and not norm_in)
-            i_un_norm_out = not (i + 1 == len(self.models) and not un_norm_out)
+            last = i + 1 == len(self.models)
+            i_un_norm_out = not (last and not un_norm_out)
             i_exo = None if exogenous_data is None else exogenous_data.get_model_step_exo(i)
+            # intermediates stay on the GPU between steps (the reference round-trips numpy
+            # arrays and transposes on the host)
+            keep_dev = not last and "to_numpy" not in kwargs
             try:
                 hi_res = self._transpose_model_input(model, hi_res)
                 hi_res = self._match_model_input(i, hi_res, i_exo)
-                hi_res = model.generate(np.ascontiguousarray(hi_res), norm_in=i_norm_in,
-                                        un_norm_out=i_un_norm_out, exogenous_data=i_exo, **kwargs)
+                if not isinstance(hi_res, torch.Tensor):
+                    hi_res = np.ascontiguousarray(hi_res)
+                hi_res = model.generate(hi_res, norm_in=i_norm_in, un_norm_out=i_un_norm_out,
+                                        exogenous_data=i_exo,
+                                        **({"to_numpy": False} if keep_dev else {}), **kwargs)
+                if keep_dev and i_exo is not None and \
+                        len(model.hr_out_features) > hi_res.shape[-1]:
+                    # exo channels appended to this step's output: host-side like the reference
+                    hi_res = model._combine_fwp_output(hi_res.cpu().numpy(), i_exo)
             except Exception as e:
                 msg = (f'Could not run model #{i + 1} of {len(self.models)} "{model}" on tensor '
                        f"of shape {hi_res.shape}")

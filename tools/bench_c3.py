@@ -37,8 +37,15 @@ def chain():
     for i in range(0, x2.shape[0], 432):
         outs.append(m2.generate(x2[i:i + 432], exogenous_data=exo))
     return np.concatenate(outs, 0)
+from sup3r_b200.models import MultiStepGan
+ms = MultiStepGan([m1, m2])
+exo_ms = {"topography": {"steps": [{"model": 1, "combine_type": "layer", "data": topo}]}}
 y = chain()
 print("out", y.shape)
+y_ms = ms.generate(x, exogenous_data=exo_ms)
+print("MultiStepGan out", y_ms.shape, "max |diff| vs manual chain", float(np.abs(y_ms - y).max()))
+torch.cuda.synchronize(); t0 = time.perf_counter(); y_ms = ms.generate(x, exogenous_data=exo_ms); torch.cuda.synchronize()
+print(f"MultiStepGan.generate (device-resident intermediates): {(time.perf_counter()-t0)*1e3:.1f} ms wall")
 torch.cuda.synchronize(); t0 = time.perf_counter(); y = chain(); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print(f"{prec}: 2-step chain on one 20x20x72 chunk: {dt*1e3:.1f} ms wall -> {20*20*72/dt/1e3:.1f} k LR voxels/s")
