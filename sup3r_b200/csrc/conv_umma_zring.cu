@@ -1205,6 +1205,9 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       if (++ab == 2) { ab = 0; abph ^= 1; }
       if (tr) t_work += clock64() - c1;
     }
+    // the staging boxes must outlive the TMA stores that read them: retire this thread's bulk
+    // groups before the CTA (and its shared memory) goes away
+    if ((EPI == EPI_V3 || EPI == EPI_V4) && lane == 0) tma_store_wait_read();
     if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; p.trace[10] = et.t_load; p.trace[11] = et.t_store;
               for (int k = 0; k < 4; ++k) p.trace[12 + k] = et.t_ph[k]; }
   }
