@@ -546,6 +546,8 @@ class Plan:
     def run_graphed(self, x, exo=None, post_scale=None, post_shift=None):
         """Replay a captured CUDA graph of ``run`` for this input shape (launch-bound nets)."""
         exo = exo or {}
+        if not self.net.built:
+            self.net.build(tuple(x.shape), {k: v.shape[-1] for k, v in exo.items()})
         # packed tensor-core weights are baked into the captured graph: re-capture after any
         # weight update (optimizer step, set_weights, load)
         wver = tuple((st.conv.kernel.version, st.conv.kernel.value.data_ptr())
