@@ -90,13 +90,19 @@ typedef struct s3_umma_tuning {
   int32_t tiles;            /* M tiles (128 voxels) per CTA work item, 1..8 */
   int32_t w_stages;         /* weight ring depth */
   int32_t box_x;            /* smem x extent of the activation box (>= 10) */
-  int32_t box_y;            /* smem y extent of one activation plane (zcat kernel; >= 18) */
+  int32_t box_y;            /* zcat kernel: smem y extent of one activation plane (>= 18).
+                               Ring kernel (scheme 0): bit flags for A/B experiments, 0 = product
+                               path -- 2 / 4 no plane / weight TMA after the first item, 8 no
+                               epilogue work, 16 generic MMA role + thread-per-row epilogue,
+                               128 LSU-coalescing epilogue (V2), 512 eight-warp TMA epilogue (V3),
+                               256 one staging box (V3), 1024 y-halo rows from registers (V4) */
   int32_t max_ctas;         /* 0 = SM count */
   int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
   void* trace;              /* optional device buffer of 16 int64: role timings of CTA 0 */
   int32_t scheme;           /* 3-D narrow convs: 0 = plane-ring pipeline ("zring"), 1 = per-item
                                halo boxes ("zcat", the round-1 baseline kept for A/B runs) */
-  int32_t ring_slots;       /* zring: activation plane slots in shared memory (0 = as many as fit) */
+  int32_t ring_slots;       /* ring kernel: activation plane slots in shared memory (0 = as many
+                               as fit); tile / zcat kernels: experiment flags (8 = no epilogue work) */
 } s3_umma_tuning;
 
 int s3_init(int device);

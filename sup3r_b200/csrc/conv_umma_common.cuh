@@ -25,7 +25,7 @@ struct UmmaParams {
   uint32_t idesc;
   DebugRec* dbg;
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
-  int dbg_flags;      // zring experiments: 2 no plane TMA, 4 no weight TMA, 8 no epilogue work
+  int dbg_flags;      // experiment flags (s3_umma_tuning.box_y / ring_slots, see include/sup3r_b200.h)
   int epi_v2;         // zring 16-bit epilogue: 0 thread-per-row, 1 LSU-coalescing, 2 TMA tile I/O
   int epi_row_tma;    // V4: y-halo rows stored by TMA (needs X % 8 == 0)
   int epi_bufs;       // TMA epilogue: staging boxes per warp (1 or 2)
