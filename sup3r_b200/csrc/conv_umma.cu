@@ -230,6 +230,21 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     S3_REQUIRE(r_max >= 1, "s3_conv_fwd_umma: npad %d too wide for TMEM", p.npad);
     const double eff_plane = (double)Y / (((Y + 15) / 16) * 16.0);
     const double eff_flat = (double)Y / (Y + 2.0);
+    if (p.split && kz == 3 && t.tiles <= 0 && t.w_stages <= 0) {
+      // split operands: the weight taps are re-streamed per work item, so more tiles per item
+      // beats a deeper weight ring (measured 64 -> 64 body conv: R = 2 / 2 stages 450 us,
+      // R = 1 / 4 stages 547 us)
+      for (int R = r_max; R >= 2 && !found; --R)
+        for (int ws = 3; ws >= 2 && !found; --ws) {
+          const uint32_t box = (uint32_t)(R + 2) * 18u * p.XB * 128u;
+          const uint32_t boxs = (box + 1023u) & ~1023u;
+          if (boxs * halves + (uint32_t)ws * w_slab * halves + fixed > kSmemLimit) continue;
+          p.flat = 0; p.R = R; p.YB = 18; p.ZB = R + 2; p.TS = 18; p.WS = ws;
+          p.box_bytes = box; p.box_stride = boxs;
+          p.AS = 1;
+          found = true;
+        }
+    }
     for (int ws = p.WS; ws >= 1 && !found; --ws)
       for (int use_flat = (eff_flat > eff_plane + 0.02 ? 1 : 0); use_flat >= 0 && !found;
            --use_flat)

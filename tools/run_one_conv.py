@@ -30,7 +30,13 @@ kw = dict(out=y) if variant == "f32out" else dict(want_f32=False, out_hi=y_hi, o
 scheme = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 flags = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 t = UmmaTuning(tiles=tiles, w_stages=ws, scheme=scheme, box_y=flags)
-for _ in range(iters):
+for _ in range(2):
     ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims, tune=t, **kw)
 torch.cuda.synchronize()
-print("done")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims, tune=t, **kw)
+e1.record()
+torch.cuda.synchronize()
+print(f"{variant} tiles={tiles} ws={ws}: {e0.elapsed_time(e1) * 1e3 / iters:.1f} us/launch")
