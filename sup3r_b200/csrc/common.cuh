@@ -85,6 +85,14 @@ static __device__ __noinline__ float apply_act_slow(float v, int act, float alph
   return apply_act(v, act, alpha);
 }
 
+// inline fast cases + out-of-line rest (for unrolled epilogue loops)
+__device__ __forceinline__ float apply_act_lean(float v, int act, float alpha) {
+  if (act == S3_ACT_NONE) return v;
+  if (act == S3_ACT_LEAKY) return v >= 0.f ? v : alpha * v;
+  if (act == S3_ACT_RELU) return fmaxf(v, 0.f);
+  return apply_act_slow(v, act, alpha);
+}
+
 __device__ __forceinline__ uint16_t to16(float v, int fmt) {
   if (fmt == 0) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
   return __half_as_ushort(__float2half_rn(v));
@@ -228,7 +236,7 @@ __device__ __forceinline__ float finish(const ConvGeom& g, const Epilogue& ep, f
   float v = acc;
   if (ep.bias) v += ep.bias[c];
   if (ep.residual && g.res_pre) v += ep.residual[conv_vox * g.cout + c];
-  v = apply_act(v, g.act, g.alpha);
+  v = apply_act_lean(v, g.act, g.alpha);
   if (ep.residual && !g.res_pre) v += ep.residual[conv_vox * g.cout + c];
   if (ep.post_scale) v = v * ep.post_scale[c] + (ep.post_shift ? ep.post_shift[c] : 0.f);
   return v;

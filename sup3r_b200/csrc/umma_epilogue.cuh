@@ -225,7 +225,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       } else if (g.act != S3_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act, g.alpha);
+        for (int j = 0; j < 16; ++j) v[j] = apply_act_slow(v[j], g.act, g.alpha);
       }
       if (ep.residual) {
         if (kPrefetchResidual && g.cout <= 64) {
