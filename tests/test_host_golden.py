@@ -116,3 +116,20 @@ def test_timer_records_calls():
         return 3
     t(f, call_id=7)()
     assert "f" in t.log[7]
+
+
+def test_forward_pass_device_check_table():
+    """_output_check (sup3r/pipeline/forward_pass.py:384-425) evaluated from the per-channel
+    (min, max, n_nan) table the device-side check returns (host logic, no GPU needed)."""
+    import numpy as np
+    from sup3r_b200.pipeline import ForwardPass
+    ok = np.array([[0.0, 1.0, 0.0], [-2.0, 3.0, 0.0]], dtype=np.float32)
+    assert not ForwardPass._device_check_failed(ok, allowed_const=None)
+    const = np.array([[0.0, 1.0, 0.0], [2.0, 2.0, 0.0]], dtype=np.float32)
+    assert ForwardPass._device_check_failed(const, allowed_const=None)
+    assert ForwardPass._device_check_failed(const, allowed_const=False)
+    assert not ForwardPass._device_check_failed(const, allowed_const=[2.0])
+    assert not ForwardPass._device_check_failed(const, allowed_const=2.0)
+    assert not ForwardPass._device_check_failed(const, allowed_const=True)
+    nan = ok.copy(); nan[1, 2] = 5.0
+    assert ForwardPass._device_check_failed(nan, allowed_const=[2.0])
