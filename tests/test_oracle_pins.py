@@ -129,3 +129,32 @@ def test_loss_identities():
     assert disc_loss(t, g) > 0
     c = torch.full((5, 1), 0.7)
     assert torch.isclose(disc_loss(c, c), torch.log(torch.tensor(2.0)))
+
+
+@pytest.mark.parametrize("nd,strides,padding", [(3, 1, "valid"), (2, 1, "valid"), (3, 2, "valid"),
+                                                 (2, 2, "same"), (3, 1, "same")])
+def test_conv_oracle_agrees_with_scipy_correlate(nd, strides, padding):
+    """Third independent statement of the Keras ConvND arithmetic (cross-correlation, kernel
+    (k..., cin, cout), 'same' = TF end-biased zero padding): scipy.signal.correlate per channel
+    pair, strided by subsampling the stride-1 result."""
+    from scipy.signal import correlate
+    rng = np.random.default_rng(nd * 10 + strides)
+    sp = (6, 7, 5)[:nd]
+    cin, cout = 3, 2
+    x = rng.standard_normal((2, *sp, cin))
+    w = rng.standard_normal((3,) * nd + (cin, cout))
+    b = rng.standard_normal(cout)
+    got = L.conv_nd(x, w, b, strides, padding)
+    xp = x
+    if padding == "same":
+        pads = [(0, 0)] + [L.same_pads(sp[d], 3, strides) for d in range(nd)] + [(0, 0)]
+        xp = np.pad(x, pads)
+    ref = np.zeros_like(got)
+    sl = (slice(None, None, strides),) * nd
+    for n in range(x.shape[0]):
+        for co in range(cout):
+            acc = 0.0
+            for ci in range(cin):
+                acc = acc + correlate(xp[n, ..., ci], w[..., ci, co], mode="valid")[sl]
+            ref[n, ..., co] = acc + b[co]
+    assert np.allclose(got, ref, atol=1e-12)
