@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=8, help="LR chunks per step (batch)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--precision", default="fp16c", choices=["fp16c", "bf16", "bf16x3", "fp32"])
     ap.add_argument("--impl", default="sup3r_b200", choices=["sup3r_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true")
@@ -307,10 +307,14 @@ def main():
         xb = torch.randn((n, *dims, 64), device=dev)
         wb = torch.randn((3, 3, 3, 64, 64), device=dev) * 0.03
         bb = torch.randn(64, device=dev) * 0.1
-        split = args.precision == "bf16x3"
-        x_hi, x_lo = ops.pack_act_pad16(xb, split=split)
-        w_hi, w_lo = ops.pack_weights_umma(wb, split=split, ndim=3)
-        r_hi, r_lo = ops.pack_act_pad16(torch.randn_like(xb), split=True)
+        split = args.precision in ("bf16x3", "fp16c")
+        c_mode = args.precision == "fp16c"
+        fmt = 2 if c_mode else 0
+        x_hi, x_lo = ops.pack_act_pad16(xb, split=split, fmt=fmt)
+        packed = ops.pack_weights_umma(wb, split=split, ndim=3, fmt=fmt)
+        w_hi, w_lo = packed[:2]
+        acc_scale = packed[2] if len(packed) == 3 else 0.0
+        r_hi, r_lo = ops.pack_act_pad16(torch.randn_like(xb), split=True, fmt=fmt)
         y_hi = torch.empty_like(x_hi)
         y_lo = torch.empty_like(x_hi)
 
@@ -319,12 +323,14 @@ def main():
                                 pad_mode=1, act=0 if residual else 2, alpha=0.2)
 
             def body():
-                if residual and not split:
+                if residual and (c_mode or not split):
                     ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
-                                      out_hi=y_hi, out_lo=y_lo, res_hi=r_hi, res_lo=r_lo)
+                                      out_hi=y_hi, out_lo=y_lo, res_hi=r_hi, res_lo=r_lo,
+                                      fmt=fmt, acc_scale=acc_scale)
                 else:
                     ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bb, spec, n, dims, want_f32=False,
-                                      out_hi=y_hi, out_lo=y_lo if split else None)
+                                      out_hi=y_hi, out_lo=y_lo if split else None, fmt=fmt,
+                                      acc_scale=acc_scale)
             for _ in range(3):
                 body()
             g = torch.cuda.CUDAGraph()
@@ -352,8 +358,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r01_body_conv_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        kname = ("conv_umma_tile_kernel (split operands, 3 MMA passes)" if split
-                 else "conv_umma_zring_kernel<4, EPI_V4>")
+        kname = ("conv_umma_zring_kernel<4, EPI_V4> (fp16 pass + e4m3 correction pass)" if c_mode
+                 else ("conv_umma_tile_kernel (split operands, 3 MMA passes)" if split
+                       else "conv_umma_zring_kernel<4, EPI_V4>"))
         roof = {"bound": "tensor", "kernel": kname + " (64->64 3x3x3 reflect "
                 f"conv, {n}x16x16x288 voxels, bf16 padded in/out; launch mix of the model step: "
                 f"{n_plain} plain + {n_res} residual launches)", "achieved": achieved,
@@ -437,7 +444,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "LR voxels/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32",
+                                       "fp16c": "f16+e4m3 (fp32 accumulate)"}[
             args.precision], "data": "synthetic",
         "config": {"workload": WORKLOAD, "chunks_per_step": B, "precision": args.precision,
                    "l2": "flushed between timed steps (256 MiB write outside the event pairs)",

@@ -85,24 +85,28 @@ typedef struct s3_conv_desc {
 int s3_conv_out_dims(const s3_conv_desc* d, int32_t conv_dims[3], int32_t out_dims[3],
                      int32_t* out_channels);
 
-/* Tuning / probing knobs of the tcgen05 kernel (all 0 = library default). */
+/* Operand format and tuning knobs of the tcgen05 kernels (all 0 = library default). */
+#define S3_FMT_BF16 0  /* bf16 operands (x_lo / w_lo given: three-pass bf16x3 split) */
+#define S3_FMT_FP16 1  /* fp16 operands */
+#define S3_FMT_FP16C 2 /* fp16 operands + e4m3 correction rows: x_lo / w_lo are the "corr" tensors
+                          written by s3_pack_act_pad16 / s3_pack_weights_umma_c / the kernels'
+                          own epilogues; one fp16 MMA pass + one e4m3 MMA pass (same time as an
+                          fp16 pass) give ~2^-15 relative operand precision */
 typedef struct s3_umma_tuning {
   int32_t tiles;            /* M tiles (128 voxels) per CTA work item, 1..8 */
   int32_t w_stages;         /* weight ring depth */
   int32_t box_x;            /* smem x extent of the activation box (>= 10) */
-  int32_t box_y;            /* zcat kernel: smem y extent of one activation plane (>= 18).
-                               Ring kernel (scheme 0): bit flags for A/B experiments, 0 = product
-                               path -- 2 / 4 no plane / weight TMA after the first item, 8 no
-                               epilogue work, 16 generic MMA role + thread-per-row epilogue,
-                               128 LSU-coalescing epilogue (V2), 512 eight-warp TMA epilogue (V3),
-                               256 one staging box (V3), 1024 y-halo rows from registers (V4) */
+  int32_t box_y;            /* ring kernel: bit flags for A/B measurements, 0 = product path --
+                               8 no epilogue work, 16 generic MMA role + thread-per-row epilogue,
+                               1024 y-halo rows from registers */
   int32_t max_ctas;         /* 0 = SM count */
-  int32_t fmt;              /* 0 bf16 operands, 1 fp16 operands */
+  int32_t fmt;              /* S3_FMT_* */
   void* trace;              /* optional device buffer of 16 int64: role timings of CTA 0 */
-  int32_t scheme;           /* 3-D narrow convs: 0 = plane-ring pipeline ("zring"), 1 = per-item
-                               halo boxes ("zcat", the round-1 baseline kept for A/B runs) */
+  int32_t scheme;           /* reserved (0) */
   int32_t ring_slots;       /* ring kernel: activation plane slots in shared memory (0 = as many
-                               as fit); tile / zcat kernels: experiment flags (8 = no epilogue work) */
+                               as fit); tile kernel: experiment flags (8 = no epilogue work) */
+  float acc_scale;          /* accumulator -> value factor applied before the bias (0 = 1): the
+                               inverse of the power-of-two weight scale of S3_FMT_FP16C */
 } s3_umma_tuning;
 
 int s3_init(int device);
@@ -143,8 +147,9 @@ int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, fl
                       float* dbias, void* scratch, s3_stream stream);
 
 /* ---- tcgen05 implicit-GEMM convolution (cin == 64, 3x3[x3], stride 1, reflect-1) ---------
- * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single-pass bf16, else the
- * 3-pass split-precision product hi*hi + lo*hi + hi*lo).  w_hi/w_lo: from s3_pack_weights_umma.
+ * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single pass; bf16 lo = the 3-pass
+ * split-precision product hi*hi + lo*hi + hi*lo; S3_FMT_FP16C lo = e4m3 correction rows, one
+ * extra e4m3 pass).  w_hi/w_lo: from s3_pack_weights_umma[_c].
  * The SkipConnection addend is either `residual` (f32, output layout) or the pair res_hi/res_lo
  * (16-bit padded layout of y_hi; value = hi + lo; res_lo may be NULL).
  * y_hi: padded+mirrored 16-bit destination for plain output maps; for depth_to_space /
@@ -163,7 +168,13 @@ int s3_umma_weight_layout(int ndim, int cout, int split);
  * cout rows zero padded to npad.  w_lo NULL = no split. */
 int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
                          int fmt, int layout, s3_stream stream);
-/* f32 (n, z, y, x, c) -> 16-bit (n, z+2*pz, y+2, x+2, c), pz = (ndim == 3), reflect halo. */
+/* S3_FMT_FP16C weights: w_hi = fp16(w * scale), w_corr = e4m3 correction rows; `scale` is a
+ * power of two chosen by the caller so that max|w| * scale lies in [2^13, 2^14) (the kernel is
+ * then called with s3_umma_tuning.acc_scale = 1 / scale). */
+int s3_pack_weights_umma_c(const float* w, int taps, int cin, int cout, void* w_hi, void* w_corr,
+                           float scale, int layout, s3_stream stream);
+/* f32 (n, z, y, x, c) -> 16-bit (n, z+2*pz, y+2, x+2, c), pz = (ndim == 3), reflect halo.
+ * fmt S3_FMT_FP16C (c == 64): lo receives the e4m3 correction rows (same byte geometry). */
 int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
                       void* lo, int fmt, s3_stream stream);
 /* inverse (interior only); lo may be NULL.  For tests. */

@@ -14,6 +14,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 
 S3_PAD_ZERO, S3_PAD_REFLECT, S3_PAD_SYMMETRIC = 0, 1, 2
 S3_ACT_NONE, S3_ACT_RELU, S3_ACT_LEAKY, S3_ACT_SIGMOID, S3_ACT_TANH = 0, 1, 2, 3, 4
+S3_FMT_BF16, S3_FMT_FP16, S3_FMT_FP16C = 0, 1, 2
 
 c_i32x3 = C.c_int32 * 3
 c_i32x5 = C.c_int32 * 5
@@ -36,7 +37,7 @@ class UmmaTuning(C.Structure):
     """``s3_umma_tuning``"""
     _fields_ = [("tiles", C.c_int32), ("w_stages", C.c_int32), ("box_x", C.c_int32),
                 ("box_y", C.c_int32), ("max_ctas", C.c_int32), ("fmt", C.c_int32), ("trace", C.c_void_p),
-                ("scheme", C.c_int32), ("ring_slots", C.c_int32)]
+                ("scheme", C.c_int32), ("ring_slots", C.c_int32), ("acc_scale", C.c_float)]
 
 
 _P = C.c_void_p
@@ -60,6 +61,7 @@ SIGNATURES = {
     "s3_umma_npad": (_I, [_I]),
     "s3_umma_weight_layout": (_I, [_I, _I, _I]),
     "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P]),
+    "s3_pack_weights_umma_c": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P]),
     "s3_pack_act_pad16": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _P]),
     "s3_unpack_act_pad16": (_I, [_P, _P, _I, _I, c_i32x3, _I, _P, _I, _P]),
     "s3_pad_fwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),

@@ -5,7 +5,7 @@
 // (sup3r/configs/spatiotemporal/gen_*.json, executed by sup3r/models/abstract.py:1081-1092).
 //
 // This file: host side (work-item shape selection, TMA descriptors, kernel choice).  Kernels:
-// conv_umma_zcat.cu (narrow 3-D outputs) and conv_umma_tile.cu (wide / 2-D / split precision);
+// conv_umma_zring.cu (narrow 3-D outputs) and conv_umma_tile.cu (wide / 2-D / bf16x3);
 // data layouts are described in conv_umma_common.cuh and DESIGN.md section 3.
 #include <cstring>
 
@@ -104,9 +104,9 @@ constexpr uint32_t kSmemLimit = 232448;  // 227 KB
 using namespace s3;
 
 extern "C" int s3_umma_weight_layout(int ndim, int cout, int split) {
-  // 1: zcat layout [9 (dy,dx)][3 (dz)][npad][64];  0: tap-major [taps][npad][64]
-  // (the split-precision path keeps the tap-major kernel: its doubled operands do not fit
-  // the zcat kernel's shared-memory plan)
+  // 1: z-concatenated layout [9 (dy,dx)][3 (dz)][npad][64] (ring kernel);  0: tap-major
+  // [taps][npad][64] (tile kernel).  `split` = the three-pass bf16x3 operands, which keep the
+  // tile kernel (the fp16c pair runs on the ring kernel: pass split = 0 for it).
   return (ndim == 3 && !split && 3 * s3_umma_npad(cout) <= 256) ? 1 : 0;
 }
 
@@ -149,7 +149,10 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   if (tune) t = *tune;
   S3_REQUIRE(!(residual && res_hi), "s3_conv_fwd_umma: give the residual as f32 OR as a 16-bit pair");
   S3_REQUIRE(!(res_lo && !res_hi), "s3_conv_fwd_umma: res_lo without res_hi");
-  p.ep = Epilogue{bias, residual, post_scale, post_shift, y, y_hi, y_lo, t.fmt, res_hi, res_lo};
+  S3_REQUIRE(t.fmt >= 0 && t.fmt <= 2, "s3_conv_fwd_umma: fmt must be 0 (bf16), 1 (fp16) or 2 (fp16c)");
+  const bool fp16c = t.fmt == kFmtFp16c;
+  p.ep = Epilogue{bias, residual, post_scale, post_shift, y, y_hi, y_lo, t.fmt, res_hi, res_lo,
+                  t.acc_scale > 0.f ? t.acc_scale : 1.f};
   p.kz = kz;
   p.ntaps = kz * 9;
   p.npad = s3_umma_npad(g.cout);
@@ -163,7 +166,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   p.nb = kz == 3 ? g.n : 1;
   p.plane_pitch = kz == 3 ? g.in[0] + 2 : 0;
   p.nxb = (X + 7) / 8;
-  const bool zcat = s3_umma_weight_layout(g.ndim, g.cout, p.split) == 1;
+  const bool zcat = s3_umma_weight_layout(g.ndim, g.cout, p.split && !fp16c) == 1;
+  p.npass = (zcat && p.split) ? 2 : 1;
   p.w_bytes = (uint32_t)p.npad * 128u * (zcat ? 3u : 1u);
   const uint32_t w_slab = (p.w_bytes + 1023u) & ~1023u;
   p.WS = t.w_stages > 0 ? t.w_stages : (zcat ? 3 : 4);
@@ -171,7 +175,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   const uint32_t fixed = 3072u;  // alignment slack + barrier block + staged bias
 
   bool found = false;
-  const bool zring = zcat && t.scheme == 0;
+  const bool zring = zcat;
   if (zring) {
     // plane-ring pipeline: P plane slots (18 x XB voxels each) + a WS-deep slab ring
     int R = t.tiles > 0 ? t.tiles : 4;
@@ -185,14 +189,12 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     const bool v2_shape = g.cout == 64 && g.cstride == 64 && g.coff == 0 && g.r == 1 && g.m == 1 &&
                           g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.fd[0] >= 4 && g.fd[1] >= 4 &&
                           g.fd[2] >= 4 && !post_scale;
-    p.epi_v2 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
-                p.planes >= 4) ? ((t.box_y & 128) ? 1 : ((t.box_y & 512) ? 2 : 3)) : 0;
-    S3_REQUIRE(!res_hi || p.epi_v2, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
+    p.epi_v4 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
+                p.planes >= 4) ? 1 : 0;
+    S3_REQUIRE(!res_hi || p.epi_v4, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
                "64-channel 16-bit-output configuration");
-    // residual layers keep two transfers per warp in flight (costs one plane slot: P = 6)
-    p.epi_bufs = (p.epi_v2 == 2 && res_hi && !(t.box_y & 256)) ? 2 : 1;
-    // V4 (epi_v2 == 3): sixteen epilogue warps with one box each
-    const uint32_t stage_bytes = p.epi_v2 == 3 ? 32768u : (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u);
+    // sixteen epilogue warps with one 2 KiB staging box each
+    const uint32_t stage_bytes = p.epi_v4 ? 32768u : 0u;
     int P = (int)((kSmemLimit - fixed - 1024u - stage_bytes - (uint32_t)ws * w_slab) / plane);
     if (P > 8) P = 8;
     if (t.ring_slots > 0 && t.ring_slots < P) P = t.ring_slots;
@@ -204,24 +206,6 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
                    !(p.dbg_flags & 16)) ? 1 : 0;
     p.box_bytes = plane; p.box_stride = plane;
     found = true;
-  } else if (zcat) {
-    int r_max = t.tiles > 0 ? t.tiles : 4;
-    if (2 * r_max * p.npad > 512) r_max = 512 / (2 * p.npad);
-    if (r_max > p.planes) r_max = p.planes;
-    if (r_max < 1) r_max = 1;
-    const int YB = t.box_y > 0 ? t.box_y : 18;
-    S3_REQUIRE(YB >= 18 && YB <= 64, "s3_conv_fwd_umma: box_y must be in [18, 64]");
-    for (int ws = p.WS; ws >= 2 && !found; --ws)
-      for (int R = r_max; R >= 1 && !found; --R) {
-        const int ZB = R + 2;
-        const uint32_t box = (uint32_t)ZB * YB * p.XB * 128u;
-        const uint32_t boxs = (box + 1023u) & ~1023u;
-        if (boxs * halves + (uint32_t)ws * w_slab * halves + fixed > kSmemLimit) continue;
-        p.flat = 0; p.R = R; p.YB = YB; p.ZB = ZB; p.TS = YB; p.WS = ws;
-        p.box_bytes = box; p.box_stride = boxs;
-        p.AS = (2 * boxs * halves + (uint32_t)ws * w_slab * halves + fixed <= kSmemLimit) ? 2 : 1;
-        found = true;
-      }
   } else {
     const int max_r_tmem = 512 / p.npad;
     int r_max = t.tiles > 0 ? t.tiles : (p.npad >= 128 ? 2 : 4);
@@ -270,7 +254,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   S3_REQUIRE(found, "s3_conv_fwd_umma: no tile shape fits shared memory (Y=%d, npad=%d)", Y, p.npad);
   p.acc_bufs = (2 * p.R * p.npad <= 512) ? 2 : 1;
-  if (!zring) p.dbg_flags = t.ring_slots;   // tile / zcat kernels: ring_slots carries experiment flags
+  if (!zring) p.dbg_flags = t.ring_slots;   // tile kernel: ring_slots carries experiment flags
   p.tile_fast = (!zcat && kz == 3 && !p.split && !p.flat && p.R == 2 && p.XB == 10 && p.YB == 18 &&
                  p.WS == 4 && p.ntaps == 27 && !(t.box_y & 16)) ? 1 : 0;
   if (!p.flat) {
@@ -302,7 +286,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   }
   uint32_t smem = p.box_stride * halves * p.AS + (uint32_t)p.WS * w_slab * halves + fixed;
   if (zring) smem = ((p.box_stride * (uint32_t)p.AS + 1023u) & ~1023u) + (uint32_t)p.WS * w_slab + fixed +
-                    (p.epi_v2 == 3 ? 32768u : (p.epi_v2 ? 16384u * (uint32_t)p.epi_bufs : 0u));
+                    (p.epi_v4 ? 32768u : 0u);
   int ctas = t.max_ctas > 0 ? t.max_ctas : sm_count();
   if (ctas > p.n_items) ctas = p.n_items;
   // epilogue specialisation: fast paths only when their preconditions hold for EVERY row
@@ -319,6 +303,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
              g.cstride % 4 == 0 && g.coff % 4 == 0) {
     epi = EPI_D2S;
   }
+  S3_REQUIRE(!(fp16c && (y_lo || res_lo)) ||
+                 (epi == EPI_PLAIN && g.cout == 64 && g.cstride == 64 && g.coff == 0 && !post_scale),
+             "s3_conv_fwd_umma: fp16c corr rows (y_lo / res_lo) need the plain 64-channel configuration");
   S3_REQUIRE(!g.res_pre || (!zring && !zcat && epi == EPI_PLAIN && g.cout == 64 && g.cstride == 64 &&
                             g.coff == 0 && !post_scale && residual),
              "s3_conv_fwd_umma: res_pre_act needs the plain 64-channel tile-kernel configuration "
@@ -326,8 +313,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   if (zring) {
     CUtensorMap em[6];
     memset(em, 0, sizeof(em));
-    p.epi_row_tma = (p.epi_v2 == 3 && g.fd[2] % 8 == 0 && !(t.box_y & 1024)) ? 1 : 0;
-    if (p.epi_v2 >= 2) {
+    p.epi_row_tma = (p.epi_v4 && g.fd[2] % 8 == 0 && !(t.box_y & 1024)) ? 1 : 0;
+    if (p.epi_v4) {
       // interior views (x + 1, y + 1) of the padded tensors: tile coordinates are plain voxel
       // indices, ragged tiles are clipped by the map extents
       const uint64_t edims[4] = {64, (uint64_t)g.fd[2], (uint64_t)g.fd[1], total_planes};
@@ -355,11 +342,9 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
         }
       }
     }
-    rc = launch_umma_zring(p, tm_a_hi, tm_w_hi, em, epi, ctas, smem, as_stream(stream));
+    const CUtensorMap maps[4] = {tm_a_hi, tm_w_hi, tm_a_lo, tm_w_lo};
+    rc = launch_umma_zring(p, maps, em, epi, ctas, smem, as_stream(stream));
   }
-  else if (zcat)
-    rc = launch_umma_zcat(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
-                          as_stream(stream));
   else
     rc = launch_umma_tile(p, tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, epi, ctas, smem,
                           as_stream(stream));

@@ -13,6 +13,7 @@ struct UmmaParams {
   ConvGeom g;
   Epilogue ep;
   int kz, ntaps, npad, split, fmt;
+  int npass;          // zring: operand passes per item (2 = fp16 pass + e4m3 corr pass, fp16c)
   int R, TS, XB, YB, ZB, WS, AS, acc_bufs;
   int flat;           // 0: plane mode (16-row y blocks), 1: flat mode (full padded height)
   int nxb, nyb;       // x blocks of 8, y blocks of 16 (plane mode)
@@ -26,9 +27,8 @@ struct UmmaParams {
   DebugRec* dbg;
   long long* trace;   // optional device buffer: per-role clock64 accumulators of CTA 0
   int dbg_flags;      // experiment flags (s3_umma_tuning.box_y / ring_slots, see include/sup3r_b200.h)
-  int epi_v2;         // zring 16-bit epilogue: 0 thread-per-row, 1 LSU-coalescing, 2 TMA tile I/O
+  int epi_v4;         // zring 16-bit epilogue: 0 thread-per-row (8 warps), 1 TMA tile I/O (16 warps)
   int epi_row_tma;    // V4: y-halo rows stored by TMA (needs X % 8 == 0)
-  int epi_bufs;       // TMA epilogue: staging boxes per warp (1 or 2)
   int tile_fast;      // tile kernel: straight-line MMA role (3-D plane mode, R = 2, XB = 10, WS = 4)
   int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
 };
@@ -184,7 +184,7 @@ __device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const S
                         g.fd[2] + x) * g.cstride + g.coff;
   int ri = 0, rj = 0;   // run counters: channel run number = ri * r + rj
   const int cout = g.cout, act = g.act;
-  const float alpha = g.alpha;
+  const float alpha = g.alpha, sc = ep.acc_scale;
 #pragma unroll 1
   for (int c0 = 0; c0 < cout; c0 += 32) {
     uint32_t raw[32];
@@ -198,10 +198,10 @@ __device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const S
         float v[8];
         const float4 b0 = *reinterpret_cast<const float4*>(sm.sbias + c0 + 8 * s);
         const float4 b1 = *reinterpret_cast<const float4*>(sm.sbias + c0 + 8 * s + 4);
-        v[0] = __uint_as_float(raw[8 * s]) + b0.x;     v[1] = __uint_as_float(raw[8 * s + 1]) + b0.y;
-        v[2] = __uint_as_float(raw[8 * s + 2]) + b0.z; v[3] = __uint_as_float(raw[8 * s + 3]) + b0.w;
-        v[4] = __uint_as_float(raw[8 * s + 4]) + b1.x; v[5] = __uint_as_float(raw[8 * s + 5]) + b1.y;
-        v[6] = __uint_as_float(raw[8 * s + 6]) + b1.z; v[7] = __uint_as_float(raw[8 * s + 7]) + b1.w;
+        v[0] = fmaf(__uint_as_float(raw[8 * s]), sc, b0.x);     v[1] = fmaf(__uint_as_float(raw[8 * s + 1]), sc, b0.y);
+        v[2] = fmaf(__uint_as_float(raw[8 * s + 2]), sc, b0.z); v[3] = fmaf(__uint_as_float(raw[8 * s + 3]), sc, b0.w);
+        v[4] = fmaf(__uint_as_float(raw[8 * s + 4]), sc, b1.x); v[5] = fmaf(__uint_as_float(raw[8 * s + 5]), sc, b1.y);
+        v[6] = fmaf(__uint_as_float(raw[8 * s + 6]), sc, b1.z); v[7] = fmaf(__uint_as_float(raw[8 * s + 7]), sc, b1.w);
         if (act == S3_ACT_LEAKY) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = v[k] >= 0.f ? v[k] : alpha * v[k];
@@ -224,11 +224,8 @@ __device__ __forceinline__ void epilogue_tile_d2s16(const UmmaParams& p, const S
   }
 }
 
-// launchers implemented in conv_umma_zcat.cu / conv_umma_tile.cu
-int launch_umma_zcat(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
-                     const CUtensorMap& w_hi, const CUtensorMap& w_lo, int epi, int ctas,
-                     uint32_t smem, cudaStream_t st);
-int launch_umma_zring(const UmmaParams& p, const CUtensorMap& a, const CUtensorMap& w,
+// launchers implemented in conv_umma_zring.cu / conv_umma_tile.cu
+int launch_umma_zring(const UmmaParams& p, const CUtensorMap* maps /* a, w, a2, w2 */,
                       const CUtensorMap* epi_maps /* res_hi, res_lo, y_hi, y_lo, row_hi, row_lo or NULL */,
                       int epi, int ctas, uint32_t smem, cudaStream_t st);
 int launch_umma_tile(const UmmaParams& p, const CUtensorMap& a_hi, const CUtensorMap& a_lo,

@@ -1,6 +1,7 @@
 // tcgen05 convolution, "tile" scheme: every 128-voxel output tile accumulates all taps itself
 // (N = npad).  Used for wide outputs (npad > 80, e.g. the 64 -> 200 head with the fused
-// depth_to_space scatter), 2-D convolutions and the split-precision (bf16x3) mode.
+// depth_to_space scatter), 2-D convolutions and the split-operand modes (bf16x3: three kind::f16
+// MMAs per k-step; fp16c: one kind::f16 + one kind::f8f6f4 MMA per k-step, common.cuh).
 #include "conv_umma_common.cuh"
 
 namespace s3 {
@@ -148,8 +149,13 @@ conv_umma_tile_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
               if (tap == 0 && kk == 0) umma_f16_new(d_addr, da, db, p.idesc);
               else umma_f16_acc(d_addr, da, db, p.idesc);
               if (p.split) {
-                umma_f16_acc(d_addr, mk_desc(al_lo + 2u * kk, hi_a), db, p.idesc);
-                umma_f16_acc(d_addr, da, mk_desc(wl_lo + 2u * kk, hi_b), p.idesc);
+                if (p.fmt == kFmtFp16c) {   // e4m3 corr rows: lo_x w + x lo_w in one K = 32 MMA
+                  umma_f8_acc(d_addr, mk_desc(al_lo + 2u * kk, hi_a),
+                              mk_desc(wl_lo + 2u * kk, hi_b), p.idesc);
+                } else {
+                  umma_f16_acc(d_addr, mk_desc(al_lo + 2u * kk, hi_a), db, p.idesc);
+                  umma_f16_acc(d_addr, da, mk_desc(wl_lo + 2u * kk, hi_b), p.idesc);
+                }
               }
             }
           }

@@ -294,7 +294,15 @@ __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restric
     float v = ok ? x[((((size_t)b * Z + z) * Y + y) * X + xx) * c + ch] : 0.f;
     uint16_t h = to16(v, fmt);
     hi[idx] = h;
-    if (lo) lo[idx] = to16(v - from16(h, fmt), fmt);
+    if (lo) {
+      if (fmt == kFmtFp16c) {   // corr row (c == 64): e4m3 residue and e4m3 copy
+        uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (idx - ch) * 2;
+        row[corr_byte(0, ch)] = (uint8_t)e4m3x2((v - from16(h, fmt)) * kCorrScale, 0.f);
+        row[corr_byte(1, ch)] = (uint8_t)e4m3x2(v, 0.f);
+      } else {
+        lo[idx] = to16(v - from16(h, fmt), fmt);
+      }
+    }
   }
 }
 
@@ -312,14 +320,20 @@ __global__ void unpack_act_kernel(const uint16_t* __restrict__ hi, const uint16_
     int b = (int)(t / Z);
     size_t p = ((((size_t)b * PZ + z + pz) * PY + y + 1) * PX + xx + 1) * c + ch;
     float v = from16(hi[p], fmt);
-    if (lo) v += from16(lo[p], fmt);
+    if (lo) {
+      if (fmt == kFmtFp16c)
+        v += e4m3_to_f32(reinterpret_cast<const uint8_t*>(lo)[(p - ch) * 2 + corr_byte(0, ch)]) *
+             kCorrInv;
+      else
+        v += from16(lo[p], fmt);
+    }
     x[idx] = v;
   }
 }
 
 __global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi,
                               uint16_t* __restrict__ lo, int taps, int cin, int cout, int npad,
-                              int fmt, int layout, size_t total) {
+                              int fmt, int layout, size_t total, float scale) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     size_t t = idx;
@@ -330,10 +344,18 @@ __global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict_
       const int dz = tap % 3, dydx = tap / 3;
       tap = dz * 9 + dydx;
     }
-    float v = co < cout ? w[((size_t)tap * cin + ci) * cout + co] : 0.f;
+    float v = (co < cout ? w[((size_t)tap * cin + ci) * cout + co] : 0.f) * scale;
     uint16_t h = to16(v, fmt);
     hi[idx] = h;
-    if (lo) lo[idx] = to16(v - from16(h, fmt), fmt);
+    if (lo) {
+      if (fmt == kFmtFp16c) {   // corr row (cin == 64): [e4m3(w S 2^-11) | e4m3(w S - hi)] per half
+        uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (idx - ci) * 2;
+        row[corr_byte(0, ci)] = (uint8_t)e4m3x2(v * kCorrInv, 0.f);
+        row[corr_byte(1, ci)] = (uint8_t)e4m3x2(v - from16(h, fmt), 0.f);
+      } else {
+        lo[idx] = to16(v - from16(h, fmt), fmt);
+      }
+    }
   }
 }
 
@@ -700,6 +722,7 @@ extern "C" int s3_channel_affine(const float* x, float* y, size_t nvox, int c, c
 extern "C" int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c,
                                  void* hi, void* lo, int fmt, s3_stream stream) {
   S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_pack_act_pad16: bad arguments");
+  S3_REQUIRE(fmt != kFmtFp16c || !lo || c == 64, "s3_pack_act_pad16: fp16c rows need c == 64");
   const int pz = ndim == 3 ? 1 : 0;
   S3_REQUIRE(dims[1] >= 2 && dims[2] >= 2 && (!pz || dims[0] >= 2),
              "s3_pack_act_pad16: reflect halo needs extents >= 2");
@@ -714,6 +737,7 @@ extern "C" int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int
                                    const int32_t dims[3], int c, float* x, int fmt,
                                    s3_stream stream) {
   S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_unpack_act_pad16: bad arguments");
+  S3_REQUIRE(fmt != kFmtFp16c || !lo || c == 64, "s3_unpack_act_pad16: fp16c rows need c == 64");
   const int pz = ndim == 3 ? 1 : 0;
   size_t total = (size_t)n * dims[0] * dims[1] * dims[2] * c;
   unpack_act_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
@@ -725,8 +749,24 @@ extern "C" int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int
 
 extern "C" int s3_umma_npad(int cout) { return (cout + 15) / 16 * 16; }
 
+static int pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
+                             int fmt, int layout, float scale, s3_stream stream);
+
 extern "C" int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi,
                                     void* w_lo, int fmt, int layout, s3_stream stream) {
+  S3_REQUIRE(fmt != kFmtFp16c, "s3_pack_weights_umma: fp16c weights carry a scale, use "
+             "s3_pack_weights_umma_c");
+  return pack_weights_umma(w, taps, cin, cout, w_hi, w_lo, fmt, layout, 1.f, stream);
+}
+
+extern "C" int s3_pack_weights_umma_c(const float* w, int taps, int cin, int cout, void* w_hi,
+                                      void* w_corr, float scale, int layout, s3_stream stream) {
+  S3_REQUIRE(w_corr && scale > 0.f, "s3_pack_weights_umma_c: needs w_corr and a positive scale");
+  return pack_weights_umma(w, taps, cin, cout, w_hi, w_corr, kFmtFp16c, layout, scale, stream);
+}
+
+static int pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
+                             int fmt, int layout, float scale, s3_stream stream) {
   S3_REQUIRE(layout == 0 || (layout == 1 && taps == 27),
              "s3_pack_weights_umma: layout 1 (zcat) needs 27 taps");
   S3_REQUIRE(w && w_hi && taps > 0 && cin == 64 && cout > 0 && cout <= 256,
@@ -734,7 +774,7 @@ extern "C" int s3_pack_weights_umma(const float* w, int taps, int cin, int cout,
   const int npad = s3_umma_npad(cout);
   size_t total = (size_t)taps * npad * cin;
   pack_w_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
-      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, layout, total);
+      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, layout, total, scale);
   S3_LAUNCH_CHECK("pack_w");
   return S3_OK;
 }

@@ -266,8 +266,21 @@ __device__ __forceinline__ void umma_f16_new(uint32_t tmem_d, uint64_t adesc, ui
       : "memory");
 }
 
+// kind::f8f6f4 (e4m3 x e4m3 -> fp32, K = 32 per instruction): same accumulator layout and same
+// cycles per instruction as kind::f16 (tools/microbench/f8_probe.cu)
+__device__ __forceinline__ void umma_f8_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, K-major A and B, M = 128.
-// fmt: 0 = fp16 operands, 1 = bf16 operands.
+// fmt: 0 = fp16 operands, 1 = bf16 operands.  (fmt 0 is also the kind::f8f6f4 descriptor of
+// e4m3 x e4m3: format code 0 = E4M3 there.)
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }

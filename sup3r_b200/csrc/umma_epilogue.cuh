@@ -54,8 +54,32 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  if (fmt == kFmtFp16c) return f16x2_sat(a, b);
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// fp16c: the "lo" half of 16 consecutive channels c0 .. c0 + 15 (c0 % 16 == 0) of one voxel:
+// l8 = e4m3((v - fp16(v)) 2^11), a8 = e4m3(v); destination = byte offsets corr_byte(0 / 1, c0)
+// inside the voxel's 128-byte corr row
+__device__ __forceinline__ void corr16(const float* v, uint4& l8, uint4& a8) {
+  float e[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) e[j] = (v[j] - from16(to16(v[j], kFmtFp16c), kFmtFp16c)) * kCorrScale;
+  l8.x = e4m3x4(e[0], e[1], e[2], e[3]);     l8.y = e4m3x4(e[4], e[5], e[6], e[7]);
+  l8.z = e4m3x4(e[8], e[9], e[10], e[11]);   l8.w = e4m3x4(e[12], e[13], e[14], e[15]);
+  a8.x = e4m3x4(v[0], v[1], v[2], v[3]);     a8.y = e4m3x4(v[4], v[5], v[6], v[7]);
+  a8.z = e4m3x4(v[8], v[9], v[10], v[11]);   a8.w = e4m3x4(v[12], v[13], v[14], v[15]);
+}
+// v[0..15] += lo8 2^-11 of 16 channels (one uint4 of a corr row)
+__device__ __forceinline__ void corr_add16(float* v, const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = e4m3x2_to_f32(w[j]), b = e4m3x2_to_f32(w[j] >> 16);
+    v[4 * j] += a.x * kCorrInv;     v[4 * j + 1] += a.y * kCorrInv;
+    v[4 * j + 2] += b.x * kCorrInv; v[4 * j + 3] += b.y * kCorrInv;
+  }
 }
 
 __device__ __forceinline__ void store16x2(uint16_t* base, long long off, const uint4& a,
@@ -90,16 +114,18 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
   const int fmt = ep.fmt;
   uint16_t* yh = reinterpret_cast<uint16_t*>(ep.y_hi);
   uint16_t* yl = reinterpret_cast<uint16_t*>(ep.y_lo);
+  const float sc = ep.acc_scale;
+  const bool corr = fmt == kFmtFp16c;
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     float v[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 bv = *reinterpret_cast<const float4*>(sbias + cc * 16 + 4 * q);
-      v[4 * q] = __uint_as_float(raw[cc * 16 + 4 * q]) + bv.x;
-      v[4 * q + 1] = __uint_as_float(raw[cc * 16 + 4 * q + 1]) + bv.y;
-      v[4 * q + 2] = __uint_as_float(raw[cc * 16 + 4 * q + 2]) + bv.z;
-      v[4 * q + 3] = __uint_as_float(raw[cc * 16 + 4 * q + 3]) + bv.w;
+      v[4 * q] = fmaf(__uint_as_float(raw[cc * 16 + 4 * q]), sc, bv.x);
+      v[4 * q + 1] = fmaf(__uint_as_float(raw[cc * 16 + 4 * q + 1]), sc, bv.y);
+      v[4 * q + 2] = fmaf(__uint_as_float(raw[cc * 16 + 4 * q + 2]), sc, bv.z);
+      v[4 * q + 3] = fmaf(__uint_as_float(raw[cc * 16 + 4 * q + 3]), sc, bv.w);
     }
     if (has_res && g.res_pre) {
 #pragma unroll
@@ -131,7 +157,9 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
       h0.z = pack2(v[4], v[5], fmt);   h0.w = pack2(v[6], v[7], fmt);
       h1.x = pack2(v[8], v[9], fmt);   h1.y = pack2(v[10], v[11], fmt);
       h1.z = pack2(v[12], v[13], fmt); h1.w = pack2(v[14], v[15], fmt);
-      if (yl) {
+      if (yl && corr) {
+        corr16(v, l0, l1);   // l0 = lo8 x 16, l1 = a8 x 16
+      } else if (yl) {
         float e[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) e[j] = v[j] - from16(to16(v[j], fmt), fmt);
@@ -141,6 +169,17 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
         l1.z = pack2(e[12], e[13], fmt); l1.w = pack2(e[14], e[15], fmt);
       }
     }
+    // lo destination of this 16-channel chunk: 16-bit lo = same offsets as hi; corr rows =
+    // 16 B of lo8 at byte corr_byte(0, 16 cc) and 16 B of a8 at corr_byte(1, 16 cc) of the voxel
+    auto store_lo = [&](long long o) {   // o = element offset of this chunk in the hi tensor
+      if (corr) {
+        uint8_t* row = reinterpret_cast<uint8_t*>(yl) + (o - cc * 16) * 2;
+        *reinterpret_cast<uint4*>(row + corr_byte(0, cc * 16)) = l0;
+        *reinterpret_cast<uint4*>(row + corr_byte(1, cc * 16)) = l1;
+      } else {
+        store16x2(yl, o, l0, l1);
+      }
+    };
 #pragma unroll 1
     for (int rx = 0; rx < rep; ++rx) {
       if (ep.y) {
@@ -154,7 +193,7 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
         const long long mx = ox == 1 ? -128LL : (ox == g.fd[2] - 2 ? 128LL : 0LL);
         const long long o0 = (long long)rp.base16 + (long long)rx * 64 + cc * 16;
         store16x2(yh, o0, h0, h1);
-        if (yl) store16x2(yl, o0, l0, l1);
+        if (yl) store_lo(o0);
         if ((rp.mz | rp.my | mx) != 0) {
 #pragma unroll 1
           for (int combo = 1; combo < 8; ++combo) {
@@ -162,7 +201,7 @@ __device__ __forceinline__ void epilogue_row_plain64(const ConvGeom& g, const Ep
             if ((a && rp.mz == 0) || (bq && rp.my == 0) || (cq && mx == 0)) continue;
             const long long o = o0 + (a ? rp.mz : 0) + (bq ? rp.my : 0) + (cq ? mx : 0);
             store16x2(yh, o, h0, h1);
-            if (yl) store16x2(yl, o, l0, l1);
+            if (yl) store_lo(o);
           }
         }
       }
@@ -210,7 +249,7 @@ __device__ __forceinline__ void epilogue_row(const ConvGeom& g, const Epilogue& 
     const int len = min(16, g.cout - c0);
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * ep.acc_scale;
     if (EPI == EPI_PLAIN || len == 16) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

@@ -12,7 +12,7 @@ import torch
 from . import _cabi
 from ._cabi import (ConvDesc, UmmaTuning, c_i32x3, c_i32x5, S3_PAD_ZERO, S3_PAD_REFLECT,
                     S3_PAD_SYMMETRIC, S3_ACT_NONE, S3_ACT_RELU, S3_ACT_LEAKY, S3_ACT_SIGMOID,
-                    S3_ACT_TANH)
+                    S3_ACT_TANH, S3_FMT_BF16, S3_FMT_FP16, S3_FMT_FP16C)
 
 ACT_CODES = {None: S3_ACT_NONE, "linear": S3_ACT_NONE, "relu": S3_ACT_RELU,
              "leaky_relu": S3_ACT_LEAKY, "sigmoid": S3_ACT_SIGMOID, "tanh": S3_ACT_TANH}
@@ -209,9 +209,15 @@ def umma_npad(cout):
     return _cabi.load().s3_umma_npad(cout)
 
 
+def _dt16(fmt):
+    return torch.bfloat16 if fmt == S3_FMT_BF16 else torch.float16
+
+
 def pack_weights_umma(w, split=False, fmt=0, ndim=None):
     """keras kernel ``(*k, 64, cout)`` f32 -> packed 16-bit (hi, lo|None) in the layout the
-    tcgen05 kernel wants for this rank / cout (``s3_umma_weight_layout``)."""
+    tcgen05 kernel wants for this rank / cout (``s3_umma_weight_layout``).  ``fmt`` 2 (fp16c):
+    -> (hi, corr, acc_scale): fp16 weights scaled by a power of two S with max|w| S in
+    [2^13, 2^14), their e4m3 correction rows, and 1 / S for the kernel's epilogue."""
     w = _f32(w)
     ensure_device(w)
     cin, cout = w.shape[-2], w.shape[-1]
@@ -219,9 +225,20 @@ def pack_weights_umma(w, split=False, fmt=0, ndim=None):
     npad = umma_npad(cout)
     if ndim is None:
         ndim = 3 if taps == 27 else 2
+    if fmt == S3_FMT_FP16C:
+        import math
+        layout = _cabi.load().s3_umma_weight_layout(ndim, cout, 0)
+        wmax = float(w.abs().max())
+        scale = 2.0 ** math.floor(math.log2(16383.0 / wmax)) if wmax > 0 else 1.0
+        scale = min(max(scale, 2.0 ** -24), 2.0 ** 24)
+        hi = torch.empty((taps, npad, cin), device=w.device, dtype=torch.float16)
+        corr = torch.empty_like(hi)
+        _cabi.call("s3_pack_weights_umma_c", _p(w), taps, cin, cout, _p(hi), _p(corr),
+                   float(scale), layout, _s())
+        _count()
+        return hi, corr, 1.0 / scale
     layout = _cabi.load().s3_umma_weight_layout(ndim, cout, 1 if split else 0)
-    dt = torch.bfloat16 if fmt == 0 else torch.float16
-    hi = torch.empty((taps, npad, cin), device=w.device, dtype=dt)
+    hi = torch.empty((taps, npad, cin), device=w.device, dtype=_dt16(fmt))
     lo = torch.empty_like(hi) if split else None
     _cabi.call("s3_pack_weights_umma", _p(w), taps, cin, cout, _p(hi), _p(lo), fmt, layout, _s())
     _count()
@@ -232,8 +249,7 @@ def pack_act_pad16(x, split=False, fmt=0):
     x = _f32(x)
     ensure_device(x)
     n, dims, c, ndim = dims3(x.shape)
-    dt = torch.bfloat16 if fmt == 0 else torch.float16
-    hi = torch.empty(pad16_shape(n, dims, c, ndim), device=x.device, dtype=dt)
+    hi = torch.empty(pad16_shape(n, dims, c, ndim), device=x.device, dtype=_dt16(fmt))
     lo = torch.empty_like(hi) if split else None
     _cabi.call("s3_pack_act_pad16", _p(x), ndim, n, c_i32x3(*dims), c, _p(hi), _p(lo), fmt, _s())
     _count()
@@ -254,8 +270,9 @@ def unpack_act_pad16(hi, lo, ndim, fmt=0):
 def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residual=None,
                   post_scale=None, post_shift=None, out=None, want_f32=True, want_pad16=False,
                   tune=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, want_lo=False,
-                  want_map16=False):
-    """tcgen05 convolution on padded 16-bit activations.  ``dims`` = unpadded (z, y, x)."""
+                  want_map16=False, fmt=None, acc_scale=0.0):
+    """tcgen05 convolution on padded 16-bit activations.  ``dims`` = unpadded (z, y, x).
+    ``fmt``: S3_FMT_* (default: from the dtype of ``x_hi``); ``acc_scale``: see fp16c weights."""
     ensure_device(x_hi)
     _, od, oc = spec.out_dims(n, dims)
     cs = spec.out_cstride or oc
@@ -271,6 +288,11 @@ def conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, bias, spec: ConvSpec, n, dims, residua
     if want_map16:   # unpadded 16-bit tensor of the mapped (depth_to_space) geometry
         y_hi = torch.empty(_shape_from(n, od, cs, spec.ndim), device=x_hi.device, dtype=x_hi.dtype)
     t = tune if tune is not None else UmmaTuning()
+    if fmt is not None:
+        t.fmt = fmt
+    elif tune is None:
+        t.fmt = S3_FMT_BF16 if x_hi.dtype == torch.bfloat16 else S3_FMT_FP16
+    t.acc_scale = float(acc_scale)
     bias, residual = _f32(bias), _f32(residual)
     post_scale, post_shift = _f32(post_scale), _f32(post_shift)
     _cabi.call("s3_conv_fwd_umma", C.byref(spec.desc(n, dims)), _p(x_hi), _p(x_lo), _p(w_hi),

@@ -11,7 +11,10 @@ does not match a pattern stays an eager layer step, so every config still runs.
 Precision modes (``SUP3R_B200_PRECISION`` or the ``precision`` argument):
   ``fp32``   every convolution on the fp32 CUDA-core kernel;
   ``bf16``   64-channel 3x3[x3] reflect convolutions on tcgen05 with bf16 operands;
-  ``bf16x3`` same, with hi/lo split operands (hi*hi + lo*hi + hi*lo) ~ fp32-grade results.
+  ``bf16x3`` same, with hi/lo split operands (hi*hi + lo*hi + hi*lo) ~ fp32-grade results;
+  ``fp16c``  fp16 operands + e4m3 correction rows (one fp16 and one e4m3 MMA pass per layer,
+             ~2^-15 relative operand precision): the fastest mode inside the 1e-3 tolerance of
+             the fp32 reference path (sup3r/models/abstract.py:1037-1105 runs fp32 end to end).
 """
 from __future__ import annotations
 
@@ -27,7 +30,8 @@ from .network import (Activation, LeakyReLU, SkipConnection, SpatialExpansion,
                       SpatioTemporalExpansion, Sup3rAdder, Sup3rConcat, FlexiblePadding, _Conv,
                       _Cropping, same_pads, SUP3R_EXO_LAYERS, to_device_tensor)
 
-PRECISIONS = ("fp32", "bf16", "bf16x3")
+PRECISIONS = ("fp32", "bf16", "bf16x3", "fp16c")
+_FMT = {"fp32": 0, "bf16": ops.S3_FMT_BF16, "bf16x3": ops.S3_FMT_BF16, "fp16c": ops.S3_FMT_FP16C}
 
 
 def default_precision():
@@ -181,24 +185,27 @@ def build_steps(layers):
 class Act:
     """An activation tensor held in f32 and / or padded 16-bit (hi, lo) form."""
 
-    __slots__ = ("f32", "hi", "lo", "shape", "b16")
+    __slots__ = ("f32", "hi", "lo", "shape", "b16", "fmt")
 
-    def __init__(self, shape, f32=None, hi=None, lo=None, b16=None):
+    def __init__(self, shape, f32=None, hi=None, lo=None, b16=None, fmt=0):
         self.shape = tuple(shape)
         self.f32, self.hi, self.lo = f32, hi, lo
         self.b16 = b16          # unpadded 16-bit tensor (depth_to_space destination)
+        self.fmt = fmt          # S3_FMT_* of (hi, lo)
 
     def need_f32(self):
         if self.f32 is None:
             if self.b16 is not None:
                 self.f32 = self.b16.float()
             else:
-                self.f32 = ops.unpack_act_pad16(self.hi, self.lo, len(self.shape) - 2)
+                self.f32 = ops.unpack_act_pad16(self.hi, self.lo, len(self.shape) - 2,
+                                                fmt=self.fmt)
         return self.f32
 
-    def need_pad16(self, split):
-        if self.hi is None or (split and self.lo is None):
-            self.hi, self.lo = ops.pack_act_pad16(self.need_f32(), split=split)
+    def need_pad16(self, split, fmt=0):
+        if self.hi is None or (split and self.lo is None) or self.fmt != fmt:
+            self.hi, self.lo = ops.pack_act_pad16(self.need_f32(), split=split, fmt=fmt)
+            self.fmt = fmt
         return self.hi, (self.lo if split else None)
 
 
@@ -226,7 +233,7 @@ def _umma_ok(fc: FusedConv, in_shape, precision):
             return False
         if fc.m > 1 and fc.method == 0:
             return False
-    if in_shape[-1] < 64 and (precision != "bf16" or conv.filters < 32):
+    if in_shape[-1] < 64 and (precision not in ("bf16", "fp16c") or conv.filters < 32):
         return False
     if any(k != 3 for k in conv.kernel_size) or any(s != 1 for s in conv.strides):
         return False
@@ -246,6 +253,7 @@ class Plan:
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.steps = build_steps(net.layers)
+        self.fmt = _FMT[self.precision]
         self._wcache = {}
         self._graphs = {}
 
@@ -259,10 +267,10 @@ class Plan:
                 w = conv.conv_kernel().detach()
                 if w.shape[-2] < 64:     # zero rows for the padded input channels
                     w = torch.nn.functional.pad(w, (0, 0, 0, 64 - w.shape[-2]))
-                hi, lo = ops.pack_weights_umma(w, split=split, ndim=conv.nd)
-            hit = (ver, hi, lo)
+                packed = ops.pack_weights_umma(w, split=split, ndim=conv.nd, fmt=self.fmt)
+            hit = (ver, *packed) if len(packed) == 3 else (ver, *packed, 0.0)
             self._wcache[key] = hit
-        return hit[1], hit[2]
+        return hit[1], hit[2], hit[3]
 
     def invalidate(self):
         self._wcache.clear()
@@ -275,7 +283,7 @@ class Plan:
         (un-normalisation) when the network ends with a fused conv."""
         net = self.net
         exo = exo or {}
-        split = self.precision == "bf16x3"
+        split = self.precision in ("bf16x3", "fp16c")
         if not net.built:
             net.build(tuple(x.shape), {k: v.shape[-1] for k, v in exo.items()})
         cur = Act(x.shape, f32=x)
@@ -357,16 +365,23 @@ class Plan:
         plain = st.r == 1 and st.m == 1 or (st.m > 1 and st.method == 0 and st.r == 1)
         want16 = plain and self._next_wants_pad16(steps, si, out_shape)
         last = si == len(steps) - 1
+        fmt = self.fmt
+        c_mode = self.precision == "fp16c"
+        umma = _umma_ok(st, shp, self.precision)
+        if c_mode:
+            # (hi, corr) pairs are written by the tcgen05 kernels' plain 64-channel epilogues only
+            want16 = (want16 and umma and out_shape[-1] == 64 and min(out_shape[1:-1]) >= 4
+                      and post_scale is None and cin <= 64)
         # SkipConnection caches travel as a 16-bit (hi, lo) pair in the padded layout when the
         # producer writes 16-bit output anyway: hi is the next convolution's operand, hi + lo
         # (~16 mantissa bits) is the addend of the consuming convolution's epilogue
         # (phygnn SkipConnection semantics, call site sup3r/models/abstract.py:1081-1092)
-        pair_skip = (want16 and bool(st.skip_store) and not split
-                     and self._ring16_ok(st, out_shape))
+        pair_skip = (want16 and bool(st.skip_store)
+                     and (c_mode or (not split and self._ring16_ok(st, out_shape))))
         want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
         if os.environ.get("SUP3R_B200_TRACE_PLAN"):
-            route = ("umma" if _umma_ok(st, shp, self.precision) else
+            route = ("umma" if umma else
                      ("small_bf16" if (self.precision == "bf16" and not want16
                                        and ops.small_bf16_ok(spec)) else "direct"))
             print(f"[plan] conv {tuple(shp)} -> cout {conv.filters} r={st.r} m={st.m} "
@@ -376,7 +391,7 @@ class Plan:
         map16 = (self.precision == "bf16" and _umma_ok(st, shp, self.precision) and st.r > 1
                  and st.m == 1 and oc == 8 and res_act is None and not st.skip_store and not last
                  and post_scale is None and self._next_is_small_bf16(steps, si, out_shape))
-        if _umma_ok(st, shp, self.precision) and cin > 64:
+        if umma and cin > 64:
             # split over input-channel groups: direct kernel on the exo channels first (no bias,
             # no activation), then the tensor-core conv on the 64 features adds it pre-activation
             xf = cur.need_f32()
@@ -395,26 +410,28 @@ class Plan:
             y, y_hi, y_lo = ops.conv_fwd_umma(x_hi, x_lo, hit[1], hit[2], bias, sp_main, n, dims,
                                               residual=part, want_f32=want32, want_pad16=want16)
             return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
-        if _umma_ok(st, shp, self.precision):
+        if umma:
             if cin < 64:
                 x_hi, x_lo = ops.pack_act_pad16(
-                    torch.nn.functional.pad(cur.need_f32(), (0, 64 - cin)), split=split)
+                    torch.nn.functional.pad(cur.need_f32(), (0, 64 - cin)), split=split, fmt=fmt)
                 spec = dataclasses.replace(spec, cin=64)
             else:
-                x_hi, x_lo = cur.need_pad16(split)
+                x_hi, x_lo = cur.need_pad16(split, fmt)
             if conv.filters > 256:
                 y = self._run_wide_head(conv, spec, x_hi, x_lo, bias, n, dims, split, out_shape)
                 return self._finish_conv(st, Act(out_shape, f32=y), skips)
-            w_hi, w_lo = self._packed(conv, split)
-            res16 = (res_act is not None and not split and not want32 and want16
+            w_hi, w_lo, acc_scale = self._packed(conv, split)
+            res16 = (res_act is not None and (c_mode or not split) and not want32 and want16
                      and self._ring16_ok(st, out_shape) and post_scale is None
-                     and res_act.hi is not None)
+                     and res_act.hi is not None and res_act.fmt == fmt
+                     and (not c_mode or res_act.lo is not None))
             y, y_hi, y_lo = ops.conv_fwd_umma(
                 x_hi, x_lo, w_hi, w_lo, bias, spec, n, dims,
                 residual=None if (res16 or res_act is None) else res_act.need_f32(),
                 res_hi=res_act.hi if res16 else None, res_lo=res_act.lo if res16 else None,
                 post_scale=post_scale, post_shift=post_shift, want_f32=want32 and not map16,
-                want_pad16=want16, want_lo=pair_skip, want_map16=map16)
+                want_pad16=want16, want_lo=pair_skip or (c_mode and want16), want_map16=map16,
+                fmt=fmt, acc_scale=acc_scale)
             if map16:
                 out = Act(out_shape, b16=y_hi)
                 return out
@@ -433,8 +450,9 @@ class Plan:
                                residual=None if res_act is None else res_act.need_f32(),
                                post_scale=post_scale, post_shift=post_shift,
                                want_pad16=want16, split=split or pair_skip, want_f32=want32)
+            fmt = 0   # (the direct kernel writes bf16 pairs; never asked for in fp16c mode)
             y, y_hi, y_lo = res if want16 else (res, None, None)
-        return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
+        return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo, fmt=fmt), skips)
 
     @staticmethod
     def _finish_conv(st, out, skips):
@@ -454,16 +472,17 @@ class Plan:
                 packs = []
                 for cb in range(0, conv.filters, 256):
                     nc = min(256, conv.filters - cb)
-                    packs.append((cb, nc, *ops.pack_weights_umma(
-                        w[..., cb:cb + nc].contiguous(), split=split, ndim=conv.nd)))
+                    pk = ops.pack_weights_umma(w[..., cb:cb + nc].contiguous(), split=split,
+                                               ndim=conv.nd, fmt=self.fmt)
+                    packs.append((cb, nc, *pk) if len(pk) == 3 else (cb, nc, *pk, 0.0))
             hit = (ver, packs)
             self._wcache[key] = hit
         y = torch.empty(out_shape, device=x_hi.device, dtype=torch.float32)
-        for cb, nc, w_hi, w_lo in hit[1]:
+        for cb, nc, w_hi, w_lo, acc_scale in hit[1]:
             sp = dataclasses.replace(spec, cout=nc, cout_total=conv.filters, cout_base=cb)
             ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo,
                               None if bias is None else bias[cb:cb + nc].contiguous(), sp, n, dims,
-                              out=y)
+                              out=y, fmt=self.fmt, acc_scale=acc_scale)
         return y
 
     def _next_is_small_bf16(self, steps, si, out_shape):

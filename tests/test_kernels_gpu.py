@@ -542,3 +542,153 @@ def test_umma_split_input_channels_pre_activation_residual(cuda):
                                 dataclasses.replace(spec, cin=64, res_pre_act=1), n, dims,
                                 residual=part)
     assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+# --------------------------------------------------------------- fp16c (fp16 + e4m3 correction)
+def _conv_ref64(x, w, b, alpha=None, res=None, rep=1):
+    """float64 torch restatement: reflect-pad-1 3x3x3 conv + bias [+ LeakyReLU] [+ nearest
+    repeat along x] [+ residual]"""
+    import torch.nn.functional as F
+    xc = torch.as_tensor(x, dtype=torch.float64).permute(0, 4, 1, 2, 3)
+    xc = F.pad(xc, (1, 1, 1, 1, 1, 1), mode="reflect")
+    wc = torch.as_tensor(w, dtype=torch.float64).permute(4, 3, 0, 1, 2)
+    y = F.conv3d(xc, wc, torch.as_tensor(b, dtype=torch.float64)).permute(0, 2, 3, 4, 1)
+    if alpha is not None:
+        y = F.leaky_relu(y, alpha)
+    if rep > 1:
+        y = torch.repeat_interleave(y, rep, dim=3)
+    if res is not None:
+        y = y + torch.as_tensor(res, dtype=torch.float64)
+    return y.numpy()
+
+
+def _halo_ok(t, pz=1):
+    """REFLECT halo of a padded (n, z+2, y+2, x+2, c) tensor: plane 0 == plane 2, ..."""
+    t = t.view(torch.int16) if t.dtype != torch.int16 else t
+    ok = bool((t[:, :, 0] == t[:, :, 2]).all() and (t[:, :, -1] == t[:, :, -3]).all()
+              and (t[:, :, :, 0] == t[:, :, :, 2]).all() and (t[:, :, :, -1] == t[:, :, :, -3]).all())
+    if pz:
+        ok = ok and bool((t[:, 0] == t[:, 2]).all() and (t[:, -1] == t[:, -3]).all())
+    return ok
+
+
+def test_fp16c_pack_roundtrip(cuda):
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(5)
+    x = rng_arr(rng, (2, 5, 6, 7, 64), 3.0)
+    hi, corr = ops.pack_act_pad16(dev(x, cuda), split=True, fmt=2)
+    assert hi.dtype == torch.float16 and corr.shape == hi.shape
+    back = ops.unpack_act_pad16(hi, corr, 3, fmt=2).cpu().numpy()
+    # hi (11 bits) + e4m3 residue (4 bits): ~2^-15 relative
+    assert np.abs(back - x).max() <= np.abs(x).max() * 2.0 ** -14
+    assert np.abs(back - x).max() < 0.2 * np.abs(hi[:, 1:-1, 1:-1, 1:-1].float().cpu().numpy() - x).max()
+    assert _halo_ok(hi) and _halo_ok(corr)
+    # corr row layout: [lo8 x 32 | a8 x 32] per 32-channel half; a8 = e4m3(x)
+    row = corr.view(torch.uint8).reshape(*corr.shape[:-1], 2, 2, 32)
+    a8 = row[..., 1, :].reshape(*corr.shape[:-1], 64).view(torch.float8_e4m3fn).float()
+    a8 = a8[:, 1:-1, 1:-1, 1:-1].cpu().numpy()
+    assert np.abs(a8 - x).max() <= np.abs(x).max() * 2.0 ** -4
+
+
+FP16C_CASES = [
+    # n, (z, y, x), variant
+    (1, (16, 16, 24), "pad16"),          # hot shape: straight-line two-pass MMA role, V4 epilogue
+    (2, (8, 16, 40), "pad16"),
+    (1, (16, 16, 24), "res16"),          # (hi, corr) residual pair through the TMA epilogue
+    (2, (4, 13, 21), "res16"),           # ragged y / x tiles
+    (1, (6, 9, 17), "pad16"),            # planes % 4 != 0 -> generic two-pass MMA role
+    (1, (16, 16, 24), "f32"),            # fp32 destination (thread-per-row epilogue)
+    (1, (8, 16, 24), "res_f32"),
+    (1, (8, 16, 8), "rep3"),             # nearest repeat x3 with (hi, corr) output
+]
+
+
+@pytest.mark.parametrize("n,dims,variant", FP16C_CASES)
+def test_umma_conv_fp16c_matches_float64(cuda, n, dims, variant):
+    """tcgen05 64->64 3x3x3 conv in the fp16c format (kind::f16 pass + kind::f8f6f4 correction
+    pass) against a float64 torch restatement on ARBITRARY fp32 operands: the north-star bound
+    is 1e-3 relative; one layer must sit near 2^-15."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(zlib.crc32(repr((n, dims, variant, "c")).encode()))
+    x = rng_arr(rng, (n, *dims, 64))
+    w = rng_arr(rng, (3, 3, 3, 64, 64), 0.05)
+    b = rng_arr(rng, (64,), 0.1)
+    rep = 3 if variant == "rep3" else 1
+    odims = (dims[0], dims[1], dims[2] * rep)
+    res = rng_arr(rng, (n, *odims, 64))
+    xd, wd, bd, rd = dev(x, cuda), dev(w, cuda), dev(b, cuda), dev(res, cuda)
+    has_res = variant.startswith("res")
+    spec = ops.ConvSpec(3, 64, 64, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
+                        act=0 if has_res else 2, alpha=0.2, out_repeat=(1, 1, rep))
+    x_hi, x_c = ops.pack_act_pad16(xd, split=True, fmt=2)
+    w_hi, w_c, acc_scale = ops.pack_weights_umma(wd, ndim=3, fmt=2)
+    r_hi, r_c = ops.pack_act_pad16(rd, split=True, fmt=2)
+    res_eff = None
+    if has_res:
+        res_eff = (res if variant == "res_f32"
+                   else ops.unpack_act_pad16(r_hi, r_c, 3, fmt=2).cpu().numpy())
+    ref = _conv_ref64(x, w, b, None if has_res else 0.2, res_eff, rep)
+    scale = np.abs(ref).max()
+    if variant in ("f32", "res_f32"):
+        y, _, _ = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, bd, spec, n, dims, fmt=2,
+                                    acc_scale=acc_scale, residual=rd if has_res else None)
+        assert np.abs(y.cpu().numpy() - ref).max() < scale * 1e-4
+        return
+    _, y_hi, y_c = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, bd, spec, n, dims, want_f32=False,
+                                     want_pad16=True, want_lo=True, fmt=2, acc_scale=acc_scale,
+                                     res_hi=r_hi if has_res else None,
+                                     res_lo=r_c if has_res else None)
+    got = ops.unpack_act_pad16(y_hi, y_c, 3, fmt=2).cpu().numpy()
+    err = np.abs(got - ref).max() / scale
+    assert err < 1.5e-4, err          # 2^-14 storage + 2^-15 operands
+    # hi alone carries fp16 rounding (2^-12): the correction rows must make a visible difference
+    err_hi = np.abs(y_hi[:, 1:-1, 1:-1, 1:-1].float().cpu().numpy() - ref).max() / scale
+    assert err < 0.5 * err_hi, (err, err_hi)
+    assert _halo_ok(y_hi) and _halo_ok(y_c)
+    # the a8 copy in the corr rows is e4m3(value)
+    row = y_c.view(torch.uint8).reshape(*y_c.shape[:-1], 2, 2, 32)
+    a8 = row[..., 1, :].reshape(*y_c.shape[:-1], 64).view(torch.float8_e4m3fn).float()
+    a8 = a8[:, 1:-1, 1:-1, 1:-1].cpu().numpy()
+    assert np.abs(a8 - ref).max() <= scale * 2.0 ** -4 * 1.01
+
+
+def test_umma_conv_fp16c_2d_and_head(cuda):
+    """fp16c on the tile kernel: a 2-D 64->64 conv with (hi, corr) output and a 3-D 64->200 head
+    with fused 5x depth_to_space into an f32 tensor."""
+    from sup3r_b200 import ops
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    # 2-D
+    n, dims = 3, (1, 12, 20)
+    x = rng_arr(rng, (n, 12, 20, 64))
+    w = rng_arr(rng, (3, 3, 64, 64), 0.05)
+    b = rng_arr(rng, (64,), 0.1)
+    xc = F.pad(torch.as_tensor(x, dtype=torch.float64).permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect")
+    ref = F.conv2d(xc, torch.as_tensor(w, dtype=torch.float64).permute(3, 2, 0, 1),
+                   torch.as_tensor(b, dtype=torch.float64)).permute(0, 2, 3, 1)
+    ref = F.leaky_relu(ref, 0.2).numpy()
+    spec = ops.ConvSpec(2, 64, 64, (1, 3, 3), pad_lo=(0, 1, 1), pad_hi=(0, 1, 1), pad_mode=1,
+                        act=2, alpha=0.2)
+    x_hi, x_c = ops.pack_act_pad16(dev(x, cuda), split=True, fmt=2)
+    w_hi, w_c, sc = ops.pack_weights_umma(dev(w, cuda), ndim=2, fmt=2)
+    _, y_hi, y_c = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, dev(b, cuda), spec, n, dims,
+                                     want_f32=False, want_pad16=True, want_lo=True, fmt=2,
+                                     acc_scale=sc)
+    got = ops.unpack_act_pad16(y_hi, y_c, 2, fmt=2).cpu().numpy()
+    assert np.abs(got - ref).max() < np.abs(ref).max() * 1.5e-4
+    assert _halo_ok(y_hi, pz=0) and _halo_ok(y_c, pz=0)
+    # 3-D head 64 -> 200, depth_to_space 5
+    n, dims = 1, (6, 8, 16)
+    x = rng_arr(rng, (n, *dims, 64))
+    w = rng_arr(rng, (3, 3, 3, 64, 200), 0.05)
+    b = rng_arr(rng, (200,), 0.1)
+    conv = _conv_ref64(x, w, b, 0.2)
+    ref = np.stack([L.depth_to_space(conv[:, :, :, i], 5) for i in range(dims[2])], axis=3)
+    spec = ops.ConvSpec(3, 64, 200, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1,
+                        act=2, alpha=0.2, d2s=5)
+    x_hi, x_c = ops.pack_act_pad16(dev(x, cuda), split=True, fmt=2)
+    w_hi, w_c, sc = ops.pack_weights_umma(dev(w, cuda), ndim=3, fmt=2)
+    y, _, _ = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, dev(b, cuda), spec, n, dims, fmt=2,
+                                acc_scale=sc)
+    assert y.shape == ref.shape
+    assert np.abs(y.cpu().numpy() - ref).max() < np.abs(ref).max() * 1e-4
