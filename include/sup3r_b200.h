@@ -97,8 +97,10 @@ typedef struct s3_umma_tuning {
   int32_t w_stages;         /* weight ring depth */
   int32_t box_x;            /* smem x extent of the activation box (>= 10) */
   int32_t box_y;            /* ring kernel: bit flags for A/B measurements, 0 = product path --
-                               8 no epilogue work, 16 generic MMA role + thread-per-row epilogue,
-                               1024 y-halo rows from registers */
+                               2 / 4 no plane / weight TMA loads after the first item, 8 no
+                               epilogue work, 16 generic MMA role + thread-per-row epilogue,
+                               64 no TMA stores, 1024 y-halo rows from registers (all but 16 and
+                               1024 produce wrong results: timing experiments only) */
   int32_t max_ctas;         /* 0 = SM count */
   int32_t fmt;              /* S3_FMT_* */
   void* trace;              /* optional device buffer of 16 int64: role timings of CTA 0 */

@@ -231,6 +231,7 @@ struct EpiTma {
   uint8_t* stage0;             // generic pointer to the same
   uint32_t bar0;               // load barrier of the box
   uint32_t phase0;
+  int dbg;                     // experiment flags (timing runs only, results are wrong)
 };
 
 // staging box: [32 rows (4 y x 8 x)][32 channels = 64 B], SWIZZLE_64B (16-byte chunk index XOR
@@ -368,7 +369,7 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
           *reinterpret_cast<uint4*>(sb + stage64_off(lane, k)) = hrow[k];
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(et.dbg & 64)) {
           tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord);
           if (mz_planes != 0)
             tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes);
@@ -685,8 +686,12 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       auto load_slab = [&](int s, int pass, int it) {
         mbar_wait_inl(bar(RB_WEMPTY + ws), wph ^ 1, p.dbg, 2, ws, it * 100 + s);
         if (elect_one()) {
-          mbar_expect_tx(bar(RB_WFULL + ws), p.w_bytes);
-          tma_load_3d(w_base + ws * w_slab, pass ? &tm_w2 : &tm_w, bar(RB_WFULL + ws), 0, 0, s);
+          if ((p.dbg_flags & 4) && (it > 0 || pass > 0 || s >= 2)) {   // timing experiment
+            mbar_arrive(bar(RB_WFULL + ws));
+          } else {
+            mbar_expect_tx(bar(RB_WFULL + ws), p.w_bytes);
+            tma_load_3d(w_base + ws * w_slab, pass ? &tm_w2 : &tm_w, bar(RB_WFULL + ws), 0, 0, s);
+          }
         }
         __syncwarp();
         if (++ws == WS) { ws = 0; wph ^= 1; }
@@ -700,9 +705,13 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
             mbar_wait_inl(bar(RB_PEMPTY + head), ((pe_phase >> head) & 1u) ^ 1u, p.dbg, 1, head, i - i0);
             pe_phase ^= 1u << head;
             if (elect_one()) {
-              mbar_expect_tx(bar(RB_PFULL + head), plane_bytes);
-              tma_load_4d(a_base + head * plane_bytes, pass ? &tm_a2 : &tm_a, bar(RB_PFULL + head),
-                          0, c.xb * 8, c.yb * 16, plane0 + ip);
+              if ((p.dbg_flags & 2) && (i > i0 || pass > 0)) {   // timing experiment
+                mbar_arrive(bar(RB_PFULL + head));
+              } else {
+                mbar_expect_tx(bar(RB_PFULL + head), plane_bytes);
+                tma_load_4d(a_base + head * plane_bytes, pass ? &tm_a2 : &tm_a,
+                            bar(RB_PFULL + head), 0, c.xb * 8, c.yb * 16, plane0 + ip);
+              }
             }
             __syncwarp();
             if (++head == P) head = 0;
@@ -833,6 +842,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     et.stage0 = smem_raw + (et.stage_s0 - smem_u32(smem_raw));
     et.bar0 = bar(RB_EPILD + (warp - 4));
     et.phase0 = 0;
+    et.dbg = p.dbg_flags;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
     long long t_wait = 0, t_work = 0;
     for (int i = i0; i < i1; ++i) {
