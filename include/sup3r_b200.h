@@ -138,6 +138,13 @@ int s3_conv_fwd_small_bf16(const s3_conv_desc* d, const float* x, const void* x_
                            const float* post_scale, const float* post_shift, float* y,
                            s3_stream stream);
 
+/* The same with fp16 operands (the S3_FMT_FP16C mode's output layer; x_fp16 = the unpadded fp16
+ * depth_to_space destination of s3_conv_fwd_umma). */
+int s3_conv_fwd_small_fp16(const s3_conv_desc* d, const float* x, const void* x_fp16,
+                           const float* w, const float* bias, const float* residual,
+                           const float* post_scale, const float* post_shift, float* y,
+                           s3_stream stream);
+
 /* Adjoint of the convolution w.r.t. its input: dy in conv-output geometry -> dx (n,z,y,x,cin).
  * Stands in for tape.gradient through keras Conv* (abstract.py:1230-1238). */
 int s3_conv_dgrad_f32(const s3_conv_desc* d, const float* dy, const float* w, float* dx,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "s3_conv_out_dims": (_I, [C.POINTER(ConvDesc), c_i32x3, c_i32x3, C.POINTER(C.c_int32)]),
     "s3_conv_fwd_f32": (_I, [C.POINTER(ConvDesc)] + [_P] * 10),
     "s3_conv_fwd_small_bf16": (_I, [C.POINTER(ConvDesc)] + [_P] * 9),
+    "s3_conv_fwd_small_fp16": (_I, [C.POINTER(ConvDesc)] + [_P] * 9),
     "s3_conv_dgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "s3_conv_wgrad_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "s3_conv_wgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),

@@ -296,6 +296,24 @@ extern "C" int s3_conv_fwd_small_bf16(const s3_conv_desc* d, const float* x, con
   return S3_OK;
 }
 
+extern "C" int s3_conv_fwd_small_fp16(const s3_conv_desc* d, const float* x, const void* x_fp16,
+                                      const float* w, const float* bias, const float* residual,
+                                      const float* post_scale, const float* post_shift, float* y,
+                                      s3_stream stream) {
+  ConvGeom g;
+  int rc = make_geom(d, &g);
+  if (rc) return rc;
+  S3_REQUIRE((x != nullptr) != (x_fp16 != nullptr) && w && y,
+             "s3_conv_fwd_small_fp16: give x (f32) OR x_fp16, and weight / destination");
+  S3_REQUIRE(!x_fp16 || g.cin == 8, "s3_conv_fwd_small_fp16: fp16 input needs exactly 8 channels");
+  Epilogue ep{bias, residual, post_scale, post_shift, y, nullptr, nullptr, kFmtFp16};
+  rc = try_conv_small_mma(g, x, x_fp16, w, ep, as_stream(stream));
+  if (rc < 0) return rc;
+  S3_REQUIRE(rc == 1, "s3_conv_fwd_small_fp16: needs a 3-D 3x3x3 stride-1 pad-1 convolution with "
+             "cin <= 8 and cout <= 8 and a plain output map");
+  return S3_OK;
+}
+
 extern "C" int s3_conv_fwd_f32(const s3_conv_desc* d, const float* x, const float* w,
                                const float* bias, const float* residual, const float* post_scale,
                                const float* post_shift, float* y, void* y_hi, void* y_lo,

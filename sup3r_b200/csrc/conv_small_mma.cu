@@ -13,8 +13,9 @@
 //   * the B fragments (all 14 k-steps, 28 registers) stay in registers for the whole CTA;
 //   * a warp owns one (z, 16-voxel x segment) column of the tile and walks the y rows two at a
 //     time (two independent accumulator sets hide the ldmatrix latency).
-// Used for precision "bf16" only (the operands are rounded to bf16 like every other tensor-core
-// layer of that mode); fp32 / bf16x3 keep the fp32 kernel in conv_small.cu.
+// Used for precision "bf16" (bf16 operands like every other tensor-core layer of that mode) and
+// "fp16c" (fp16 operands: the one layer of that mode without correction rows -- its rounding does
+// not compound through later layers); fp32 / bf16x3 keep the fp32 kernel in conv_small.cu.
 // Replaces FlexiblePadding -> Conv3D -> Cropping3D at the end of
 // sup3r/configs/spatiotemporal/gen_*.json as executed by sup3r/models/abstract.py:1081-1092.
 #include <cuda_bf16.h>
@@ -39,7 +40,10 @@ __device__ __forceinline__ int fold_idx(int q, int n, int mode, bool* ok) {
   return 0;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+// kF16: fp16 operands (the fp16c mode's output layer), else bf16
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_16x2(float a, float b) {
+  if (kF16) return f16x2_sat(a, b);
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
@@ -50,13 +54,21 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
                : "r"(addr));
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                               uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
-      "{%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool kF16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1) {
+  if (kF16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+        "{%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+        "{%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __device__ __noinline__ float act_slow(float v, int act, float alpha) { return apply_act(v, act, alpha); }
@@ -65,7 +77,7 @@ __device__ __noinline__ float act_slow(float v, int act, float alpha) { return a
 // channel) computed from a 4-wide x window (K = 9 x 4 taps x 8 ch = 18 k-steps per voxel pair
 // instead of 2 x 14): the kernel is bound by the legacy HMMA issue rate (~32 cycles per
 // m16n8k16 and SM sub-partition on B200), so fewer MMAs per voxel is the lever.
-template <bool kTwo>
+template <bool kTwo, bool kF16>
 __global__ void __launch_bounds__(M_THREADS, 3)
 conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
                       const uint4* __restrict__ x16, const float* __restrict__ w,
@@ -168,10 +180,10 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
           const int hx = lane + 32 * e;
           if (hx >= MH_X) continue;
           uint4 v;
-          v.x = pack_bf16x2(va[q][e].x, va[q][e].y);
-          v.y = pack_bf16x2(va[q][e].z, va[q][e].w);
-          v.z = pack_bf16x2(vb[q][e].x, vb[q][e].y);
-          v.w = pack_bf16x2(vb[q][e].z, vb[q][e].w);
+          v.x = pack_16x2<kF16>(va[q][e].x, va[q][e].y);
+          v.y = pack_16x2<kF16>(va[q][e].z, va[q][e].w);
+          v.z = pack_16x2<kF16>(vb[q][e].x, vb[q][e].y);
+          v.w = pack_16x2<kF16>(vb[q][e].z, vb[q][e].w);
           sin[r * MH_X + hx] = v;
         }
       }
@@ -207,7 +219,7 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
           if (c0 < cin) v0 = __ldg(w + ((size_t)tap * cin + c0) * cout + grp);
           if (c1 < cin) v1 = __ldg(w + ((size_t)tap * cin + c1) * cout + grp);
         }
-        bf[j][hh] = pack_bf16x2(v0, v1);
+        bf[j][hh] = pack_16x2<kF16>(v0, v1);
       }
     }
   }
@@ -273,7 +285,7 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
         ldmatrix_x4(addr, a[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) mma_bf16_16816(acc[u], a[u], bf[j][0], bf[j][1]);
+      for (int u = 0; u < 2; ++u) mma_16816<kF16>(acc[u], a[u], bf[j][0], bf[j][1]);
     }
     // ---- epilogue: thread holds rows grp and grp + 8, accumulator columns 2 t4, 2 t4 + 1
     if (oz < Z && ec0 < cout) {
@@ -320,6 +332,23 @@ conv_small_mma_kernel(const ConvGeom g, const float* __restrict__ x,
 }  // namespace
 
 // Returns 1 if handled, 0 if the shape is not covered, < 0 on error.
+template <bool kTwo, bool kF16>
+static int launch_small_mma(const ConvGeom& g, const float* x, const void* x16, const float* w,
+                            const Epilogue& ep, unsigned blocks, size_t smem, int tx, int ty, int tz,
+                            cudaStream_t st) {
+  static bool set = false;
+  if (!set) {
+    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel<kTwo, kF16>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  conv_small_mma_kernel<kTwo, kF16><<<blocks, M_THREADS, smem, st>>>(
+      g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
+  S3_CUDA(cudaGetLastError());
+  return 1;
+}
+
+// ep.fmt: 0 = bf16 operands, otherwise fp16
 int try_conv_small_mma(const ConvGeom& g, const float* x, const void* x16, const float* w,
                        const Epilogue& ep, cudaStream_t st) {
   if ((x == nullptr) == (x16 == nullptr)) return 0;
@@ -331,14 +360,6 @@ int try_conv_small_mma(const ConvGeom& g, const float* x, const void* x16, const
     if (g.k[i] != 3 || g.st[i] != 1 || g.pl[i] != 1 || g.ph[i] != 1) return 0;
   if (g.pad_mode == S3_PAD_REFLECT && (g.in[0] < 2 || g.in[1] < 2 || g.in[2] < 2)) return 0;
   const size_t smem = sizeof(uint4) * (M_HALO_VOX + 8);
-  static bool set = false;
-  if (!set) {
-    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    S3_CUDA(cudaFuncSetAttribute(conv_small_mma_kernel<true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
-  }
   const int tx = (g.in[2] + MT_X - 1) / MT_X, ty = (g.in[1] + MT_Y - 1) / MT_Y;
   const int tz = (g.in[0] + MT_Z - 1) / MT_Z;
   const long long blocks = (long long)tx * ty * tz * g.n;
@@ -346,14 +367,12 @@ int try_conv_small_mma(const ConvGeom& g, const float* x, const void* x16, const
     set_error("conv_small_mma: grid too large");
     return S3_ERR_INVALID;
   }
+  const bool f16 = ep.fmt != 0;
   if (g.cout <= 4)
-    conv_small_mma_kernel<true><<<(unsigned)blocks, M_THREADS, smem, st>>>(
-        g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
-  else
-    conv_small_mma_kernel<false><<<(unsigned)blocks, M_THREADS, smem, st>>>(
-        g, x, static_cast<const uint4*>(x16), w, ep, tx, ty, tz);
-  S3_CUDA(cudaGetLastError());
-  return 1;
+    return f16 ? launch_small_mma<true, true>(g, x, x16, w, ep, (unsigned)blocks, smem, tx, ty, tz, st)
+               : launch_small_mma<true, false>(g, x, x16, w, ep, (unsigned)blocks, smem, tx, ty, tz, st);
+  return f16 ? launch_small_mma<false, true>(g, x, x16, w, ep, (unsigned)blocks, smem, tx, ty, tz, st)
+             : launch_small_mma<false, false>(g, x, x16, w, ep, (unsigned)blocks, smem, tx, ty, tz, st);
 }
 
 }  // namespace s3

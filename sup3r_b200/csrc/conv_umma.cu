@@ -160,7 +160,7 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   p.fmt = t.fmt;
   p.XB = t.box_x > 0 ? t.box_x : 10;
   S3_REQUIRE(p.XB >= 10 && p.XB <= 64, "s3_conv_fwd_umma: box_x must be in [10, 64]");
-  const int halves = p.split ? 2 : 1;
+  int halves = p.split ? 2 : 1;
   const int Y = g.in[1], X = g.in[2];
   p.planes = kz == 3 ? g.in[0] : g.n;
   p.nb = kz == 3 ? g.n : 1;
@@ -214,7 +214,22 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     S3_REQUIRE(r_max >= 1, "s3_conv_fwd_umma: npad %d too wide for TMEM", p.npad);
     const double eff_plane = (double)Y / (((Y + 15) / 16) * 16.0);
     const double eff_flat = (double)Y / (Y + 2.0);
-    if (p.split && kz == 3 && t.tiles <= 0 && t.w_stages <= 0) {
+    if (fp16c && p.split && kz == 3 && t.tiles <= 0 && t.w_stages <= 0 && r_max >= 2 &&
+        p.XB == 10 && !(t.box_y & 16)) {
+      // fp16c wide head: the fp16 pass and the e4m3 pass run one after the other through the
+      // same activation box (one operand tensor resident at a time) and a 4-deep weight ring
+      const uint32_t box = 4u * 18u * 10u * 128u;
+      const uint32_t boxs = (box + 1023u) & ~1023u;
+      for (int as = 2; as >= 1 && !found; --as) {
+        if (boxs * as + 4u * w_slab + fixed > kSmemLimit) continue;
+        p.flat = 0; p.R = 2; p.YB = 18; p.ZB = 4; p.TS = 18; p.WS = 4; p.AS = as;
+        p.box_bytes = box; p.box_stride = boxs;
+        p.seq2 = 1;
+        halves = 1;
+        found = true;
+      }
+    }
+    if (!found && p.split && kz == 3 && t.tiles <= 0 && t.w_stages <= 0) {
       // split operands: the weight taps are re-streamed per work item, so more tiles per item
       // beats a deeper weight ring (measured 64 -> 64 body conv: R = 2 / 2 stages 450 us,
       // R = 1 / 4 stages 547 us)
@@ -255,8 +270,8 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   S3_REQUIRE(found, "s3_conv_fwd_umma: no tile shape fits shared memory (Y=%d, npad=%d)", Y, p.npad);
   p.acc_bufs = (2 * p.R * p.npad <= 512) ? 2 : 1;
   if (!zring) p.dbg_flags = t.ring_slots;   // tile kernel: ring_slots carries experiment flags
-  p.tile_fast = (!zcat && kz == 3 && !p.split && !p.flat && p.R == 2 && p.XB == 10 && p.YB == 18 &&
-                 p.WS == 4 && p.ntaps == 27 && !(t.box_y & 16)) ? 1 : 0;
+  p.tile_fast = (!zcat && kz == 3 && (!p.split || p.seq2) && !p.flat && p.R == 2 && p.XB == 10 &&
+                 p.YB == 18 && p.WS == 4 && p.ntaps == 27 && !(t.box_y & 16)) ? 1 : 0;
   if (!p.flat) {
     p.nyb = (Y + 15) / 16;
     p.groups_per_b = (p.planes + p.R - 1) / p.R;

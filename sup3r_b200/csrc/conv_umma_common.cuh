@@ -30,6 +30,8 @@ struct UmmaParams {
   int epi_v4;         // zring 16-bit epilogue: 0 thread-per-row (8 warps), 1 TMA tile I/O (16 warps)
   int epi_row_tma;    // V4: y-halo rows stored by TMA (needs X % 8 == 0)
   int tile_fast;      // tile kernel: straight-line MMA role (3-D plane mode, R = 2, XB = 10, WS = 4)
+  int seq2;           // tile kernel: fp16c as two sequential passes per item through the same
+                      // activation / weight stages (instead of both operand halves resident)
   int ring_fast;      // zring: every item is the hot shape (R = 4, npad = 64, XB = 10, P = 7, WS = 2)
 };
 
@@ -82,7 +84,7 @@ struct SmemMap {
 __device__ __forceinline__ SmemMap carve(const UmmaParams& p, const uint8_t* smem_raw) {
   SmemMap m;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int halves = p.split ? 2 : 1;
+  const int halves = (p.split && !p.seq2) ? 2 : 1;
   m.a_stage_bytes = p.box_stride * halves;
   m.w_slab = (p.w_bytes + 1023u) & ~1023u;
   m.w_stage_bytes = m.w_slab * halves;

@@ -157,10 +157,13 @@ def small_bf16_ok(spec: ConvSpec):
 
 
 def conv_fwd_small_bf16(x, w, bias, spec: ConvSpec, residual=None, post_scale=None,
-                        post_shift=None, out=None):
-    """Narrow 3x3x3 convolution on mma.sync tensor cores (bf16 operands, fp32 accumulate)."""
+                        post_shift=None, out=None, fp16=False):
+    """Narrow 3x3x3 convolution on mma.sync tensor cores (bf16 operands, or fp16 with ``fp16`` /
+    an fp16 input tensor; fp32 accumulate)."""
     x16 = None
-    if x.dtype == torch.bfloat16:
+    if x.dtype == torch.float16:
+        fp16 = True
+    if x.dtype in (torch.bfloat16, torch.float16):
         x16, x = x.contiguous(), None
         ensure_device(x16)
         n, dims, c, ndim = dims3(x16.shape)
@@ -176,7 +179,8 @@ def conv_fwd_small_bf16(x, w, bias, spec: ConvSpec, residual=None, post_scale=No
                                                 dtype=torch.float32)
     w, bias, residual = _f32(w), _f32(bias), _f32(residual)
     post_scale, post_shift = _f32(post_scale), _f32(post_shift)
-    _cabi.call("s3_conv_fwd_small_bf16", C.byref(spec.desc(n, dims)), _p(x), _p(x16), _p(w),
+    _cabi.call("s3_conv_fwd_small_fp16" if fp16 else "s3_conv_fwd_small_bf16",
+               C.byref(spec.desc(n, dims)), _p(x), _p(x16), _p(w),
                _p(bias), _p(residual), _p(post_scale), _p(post_shift), _p(y), _s())
     _count()
     return y

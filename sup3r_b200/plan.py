@@ -388,7 +388,7 @@ class Plan:
                   f"skip_add={st.skip_add} store={st.skip_store} want16={want16} route={route}")
         # depth_to_space head feeding the narrow output convolution: hand the high-resolution
         # tensor over as unpadded bf16 (8-channel voxels = 16 B) instead of f32
-        map16 = (self.precision == "bf16" and _umma_ok(st, shp, self.precision) and st.r > 1
+        map16 = (self.precision in ("bf16", "fp16c") and umma and st.r > 1
                  and st.m == 1 and oc == 8 and res_act is None and not st.skip_store and not last
                  and post_scale is None and self._next_is_small_bf16(steps, si, out_shape))
         if umma and cin > 64:
@@ -435,14 +435,15 @@ class Plan:
             if map16:
                 out = Act(out_shape, b16=y_hi)
                 return out
-        elif (self.precision == "bf16" and not want16 and ops.small_bf16_ok(spec)
+        elif (self.precision in ("bf16", "fp16c") and not want16 and ops.small_bf16_ok(spec)
               and spec.pad_mode == S3_PAD_REFLECT):
-            # narrow high-resolution output convolution: warp-level tensor cores, bf16 operands
+            # narrow high-resolution output convolution: warp-level tensor cores, 16-bit operands
+            # (bf16 / fp16: the last layer's operand rounding does not compound)
             y = ops.conv_fwd_small_bf16(
                 cur.b16 if (cur.b16 is not None and cur.f32 is None and shp[-1] == 8)
                 else cur.need_f32(), conv.conv_kernel().detach(), bias, spec,
                 residual=None if res_act is None else res_act.need_f32(),
-                post_scale=post_scale, post_shift=post_shift)
+                post_scale=post_scale, post_shift=post_shift, fp16=c_mode)
             y_hi = y_lo = None
         else:
             x = cur.need_f32()

@@ -121,10 +121,16 @@ def test_north_star_generator_at_baseline_shape(cuda, batch):
         err, rms = rel_err(got, ref), rms_err(got, ref)
         print(f"north star batch {batch} {precision}: max-rel {err:.2e} rms-rel {rms:.2e}")
         assert err < tol and rms < tol, (precision, err, rms)
-    # element-wise: 99 % of the elements within 1e-2 of their own magnitude in the benchmarked mode
+    # element-wise figures of the benchmarked mode: |d| / |ref| (median) and |d| / max(|ref|,
+    # rms(ref)) (90th / 99th percentile; the floor keeps near-zero reference values meaningful)
     y = m.generate(x, precision="fp16c")[idx]
-    elem = np.abs(y - ref) / np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())
-    assert np.quantile(elem, 0.99) < 1e-2
+    d = np.abs(y.astype(np.float64) - ref)
+    med = float(np.median(d / np.maximum(np.abs(ref), 1e-30)))
+    floored = d / np.maximum(np.abs(ref), np.sqrt(np.mean(ref ** 2)))
+    q90, q99 = (float(np.quantile(floored, q)) for q in (0.90, 0.99))
+    print(f"north star batch {batch} fp16c element-wise: median rel {med:.2e}, floored rel "
+          f"p90 {q90:.2e} p99 {q99:.2e}")
+    assert med < 1e-3 and q90 < 1e-3 and q99 < 2e-3
 
 
 def test_generate_without_exo_raises(cuda):

@@ -1,31 +1,32 @@
-"""Time the 64 -> 200 head conv with fused 5x depth_to_space (bf16 mapped output): args n flags iters"""
+"""Time the 64 -> 200 head convolution (fused 5x depth_to_space) of the north-star generator:
+  python tools/run_head_conv.py [n] [precision bf16|fp16c] [iters]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sup3r_b200 import ops
-from sup3r_b200._cabi import UmmaTuning
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+prec = sys.argv[2] if len(sys.argv) > 2 else "fp16c"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-tiles = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-dims = (16, 16, 288)
+fmt = 2 if prec == "fp16c" else 0
+split = fmt == 2
 dev = torch.device("cuda:0")
-x = torch.randn((n,) + dims + (64,), device=dev)
+dims = (16, 16, 288)
+x = torch.randn((n, *dims, 64), device=dev)
 w = torch.randn((3, 3, 3, 64, 200), device=dev) * 0.03
 b = torch.randn(200, device=dev) * 0.1
-x_hi, _ = ops.pack_act_pad16(x)
-w_hi, _ = ops.pack_weights_umma(w, ndim=3)
-spec = ops.ConvSpec(3, 64, 200, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1, act=2, alpha=0.2, d2s=5)
-t = UmmaTuning(ring_slots=flags, tiles=tiles)
-y16 = torch.empty((n, 80, 80, 288, 8), device=dev, dtype=torch.bfloat16)
-for _ in range(2):
-    ops.conv_fwd_umma(x_hi, None, w_hi, None, b, spec, n, dims, want_f32=False, out_hi=y16, tune=t)
-torch.cuda.synchronize()
+x_hi, x_lo = ops.pack_act_pad16(x, split=split, fmt=fmt)
+pk = ops.pack_weights_umma(w, ndim=3, fmt=fmt)
+w_hi, w_lo = pk[:2]
+acc = pk[2] if len(pk) == 3 else 0.0
+spec = ops.ConvSpec(3, 64, 200, (3, 3, 3), pad_lo=(1, 1, 1), pad_hi=(1, 1, 1), pad_mode=1, act=2,
+                    alpha=0.2, d2s=5)
+kw = dict(want_f32=False, want_map16=True) if prec == "bf16" else {}
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters):
-    ops.conv_fwd_umma(x_hi, None, w_hi, None, b, spec, n, dims, want_f32=False, out_hi=y16, tune=t)
-e1.record(); torch.cuda.synchronize()
-us = e0.elapsed_time(e1) * 1e3 / iters
-print(f"head flags {flags} tiles {tiles}: {us:.1f} us/launch, {2*n*16*16*288*27*64*200/us/1e6:.1f} TF/s")
+for i in range(iters + 2):
+    if i == 2:
+        e0.record()
+    y = ops.conv_fwd_umma(x_hi, x_lo, w_hi, w_lo, b, spec, n, dims, fmt=fmt, acc_scale=acc, **kw)
+e1.record()
+torch.cuda.synchronize()
+print(f"head {prec}: {e0.elapsed_time(e1) * 1e3 / iters:.1f} us/launch")
