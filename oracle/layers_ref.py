@@ -120,7 +120,7 @@ def activation(x, name, alpha=None):
     if name == "relu":
         return np.maximum(x, 0)
     if name == "leaky_relu":
-        a = 0.3 if alpha is None else alpha
+        a = 0.2 if alpha is None else alpha   # keras.activations.leaky_relu: negative_slope 0.2
         return np.where(x >= 0, x, a * x)
     if name == "sigmoid":
         return 1.0 / (1.0 + np.exp(-x))

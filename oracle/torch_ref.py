@@ -26,7 +26,7 @@ def _to_cl(x):
     return x.permute(0, *range(2, nd + 2), 1)
 
 
-def _act(x, name, alpha=0.3):
+def _act(x, name, alpha=0.2):   # keras string activation: negative_slope 0.2
     if name is None or name == "linear":
         return x
     if name == "relu":

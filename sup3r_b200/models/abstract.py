@@ -169,12 +169,13 @@ class AbstractSingleModel(TensorboardMixIn):
         return self._stdevs
 
     def set_norm_stats(self, new_means, new_stdevs):
-        """Set normalisation statistics from a batch handler (abstract.py:133-195): kept from
-        an earlier training run if already present, stored as float32 per feature."""
+        """Set normalisation statistics from a batch handler (abstract.py:133-195): the new
+        values always REPLACE the model's (continued training / transfer learning normalises
+        with the new handler's statistics), stored as float32 per feature."""
         if new_means is not None and new_stdevs is not None:
-            if self._means is not None:
-                logger.info("Model already has normalization stats; keeping them.")
-                return
+            logger.info("Setting new normalization statistics...")
+            logger.info("Model's previous data mean values: %s", self._means)
+            logger.info("Model's previous data stdev values: %s", self._stdevs)
             if not isinstance(new_means, dict) or not isinstance(new_stdevs, dict):
                 msg = ("Means and stdevs need to be dictionaries with keys as feature names but "
                        f"received means of type {type(new_means)} and stdevs of type "

@@ -220,7 +220,6 @@ class Sup3rGan(AbstractSingleModel, AbstractInterface):
                   train_disc=False, compute_disc=False):
         """GAN loss (base.py:830-911).  Returns ``(loss, loss_details)`` with keys
         ``loss_disc, loss_gen, loss_gen_content, loss_gen_advers`` + per-term content names."""
-        from ..autograd import ScaleFn
         hi_res_gen = self._combine_loss_input(hi_res_true, hi_res_gen)
         if tuple(hi_res_gen.shape) != tuple(hi_res_true.shape):
             msg = ("The tensor shapes of the synthetic output {} and true high res {} did not "
@@ -239,13 +238,11 @@ class Sup3rGan(AbstractSingleModel, AbstractInterface):
             loss_gen_content, content_details = self.calc_loss_gen_content(hi_res_true,
                                                                             hi_res_gen)
             loss_gen_advers = self.calc_loss_disc(disc_out_gen, disc_out_true)
-            w = torch.tensor(float(weight_gen_advers), device=loss_gen_advers.device)
             loss = loss_gen_content + ScaleFnScalar.apply(loss_gen_advers, float(weight_gen_advers))
             loss_details["loss_gen"] = loss
             loss_details["loss_gen_content"] = loss_gen_content
             loss_details["loss_gen_advers"] = loss_gen_advers
             loss_details.update(content_details)
-            del w
         elif train_disc:
             loss = loss_details["loss_disc"]
         return loss, loss_details

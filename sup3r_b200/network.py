@@ -34,6 +34,11 @@ logger = logging.getLogger(__name__)
 _GLOBAL_SEED = [0]
 
 
+# slope of the STRING activation 'leaky_relu' (keras.activations.leaky_relu: negative_slope 0.2);
+# the LeakyReLU LAYER carries its own alpha (keras default 0.3)
+KERAS_LEAKY_RELU_SLOPE = 0.2
+
+
 def default_device():
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
         else torch.device("cpu")
@@ -240,7 +245,7 @@ class _Conv(Layer):
             w = w.flip(dims=tuple(range(self.nd))).transpose(-1, -2).contiguous()
         return w
 
-    def spec(self, shp, extra_pad=None, act=None, alpha=0.0, pad_mode=S3_PAD_ZERO):
+    def spec(self, shp, extra_pad=None, act=None, alpha=None, pad_mode=S3_PAD_ZERO):
         """ConvSpec for input shape ``shp``; ``extra_pad``: [(lo, hi)] per conv dim overriding
         the layer's own implicit padding."""
         nd = self.nd
@@ -254,6 +259,8 @@ class _Conv(Layer):
                 extra_pad = [(0, 0)] * nd
         z = 3 - nd
         a = ops.ACT_CODES[self.activation] if act is None else act
+        if alpha is None:
+            alpha = KERAS_LEAKY_RELU_SLOPE if a == S3_ACT_LEAKY else 0.0
         return ops.ConvSpec(nd, int(shp[-1]), self.filters, (1,) * z + self.kernel_size,
                             stride=(1,) * z + self.strides,
                             pad_lo=(0,) * z + tuple(int(p[0]) for p in extra_pad),
@@ -337,7 +344,7 @@ class Activation(Layer):
 
     def forward(self, x):
         code = ops.ACT_CODES[self.activation]
-        return x if code == S3_ACT_NONE else ActFn.apply(x, code, 0.3)
+        return x if code == S3_ACT_NONE else ActFn.apply(x, code, KERAS_LEAKY_RELU_SLOPE)
 
 
 class SkipConnection(Layer):
@@ -492,13 +499,15 @@ class Dense(Layer):
                                f"features but got {k}")
         self.built = True
 
-    def forward(self, x, act=None, alpha=0.0):
+    def forward(self, x, act=None, alpha=None):
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         if self.kernel.shape[0] != x2.shape[1]:
             raise RuntimeError(f'Dense "{self.name}" expects {self.kernel.shape[0]} features, got '
                                f"{x2.shape[1]}")
         code = ops.ACT_CODES[self.activation] if act is None else act
+        if alpha is None:
+            alpha = KERAS_LEAKY_RELU_SLOPE if code == S3_ACT_LEAKY else 0.0
         y = DenseFn.apply(x2, self.kernel.value, self.bias.value if self.bias is not None else None,
                           code, alpha)
         return y.reshape(*lead, self.units)

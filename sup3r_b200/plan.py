@@ -28,7 +28,8 @@ from . import ops
 from ._cabi import S3_ACT_LEAKY, S3_ACT_NONE, S3_PAD_REFLECT, S3_PAD_ZERO
 from .network import (Activation, LeakyReLU, SkipConnection, SpatialExpansion,
                       SpatioTemporalExpansion, Sup3rAdder, Sup3rConcat, FlexiblePadding, _Conv,
-                      _Cropping, same_pads, SUP3R_EXO_LAYERS, to_device_tensor)
+                      _Cropping, same_pads, SUP3R_EXO_LAYERS, to_device_tensor,
+                      KERAS_LEAKY_RELU_SLOPE)
 
 PRECISIONS = ("fp32", "bf16", "bf16x3", "fp16c")
 _FMT = {"fp32": 0, "bf16": ops.S3_FMT_BF16, "bf16x3": ops.S3_FMT_BF16, "fp16c": ops.S3_FMT_FP16C}
@@ -138,7 +139,7 @@ def build_steps(layers):
                 fc = FusedConv(conv, q, mode, first_layer=i)
                 fc.act = ops.ACT_CODES[conv.activation]
                 if fc.act == S3_ACT_LEAKY:
-                    fc.alpha = 0.3
+                    fc.alpha = KERAS_LEAKY_RELU_SLOPE
                 # activation / expansion in either order
                 for _ in range(2):
                     if k < n and fc.act == S3_ACT_NONE and isinstance(layers[k], LeakyReLU):
@@ -147,7 +148,7 @@ def build_steps(layers):
                     elif k < n and fc.act == S3_ACT_NONE and isinstance(layers[k], Activation) \
                             and ops.ACT_CODES[layers[k].activation] != S3_ACT_NONE:
                         fc.act = ops.ACT_CODES[layers[k].activation]
-                        fc.alpha = 0.3
+                        fc.alpha = KERAS_LEAKY_RELU_SLOPE
                         k += 1
                     elif k < n and fc.r == 1 and fc.m == 1 and \
                             isinstance(layers[k], SpatialExpansion) and nd == 2:
@@ -295,10 +296,16 @@ class Plan:
                 try:
                     if isinstance(st, FusedConv):
                         last = si == len(steps) - 1
-                        ps = post_scale if last else None
-                        pf = post_shift if last else None
+                        # the fused affine indexes CONV channels: only for channel-preserving
+                        # output maps (no depth_to_space / depth_to_time)
+                        fuse = last and st.r == 1 and not (st.m > 1 and st.method == 1)
+                        ps = post_scale if fuse else None
+                        pf = post_shift if fuse else None
                         cur = self._run_conv(st, cur, skips, steps, si, split, ps, pf)
-                        applied_post = applied_post or (last and ps is not None)
+                        # (routes that cannot fuse the affine -- channel-split convs, wide
+                        # scatter heads -- leave it to the channel_affine below)
+                        applied_post = applied_post or (last and ps is not None
+                                                        and self._post_fused)
                     elif isinstance(st, SkipStep):
                         if st.store:
                             skips[st.name] = cur
@@ -340,6 +347,7 @@ class Plan:
     def _run_conv(self, st, cur, skips, steps, si, split, post_scale, post_shift):
         conv = st.conv
         shp = cur.shape
+        self._post_fused = True
         if not conv.built:
             raise RuntimeError("network weights are not built")
         if st.pads is None:  # the layer's own padding
@@ -407,6 +415,7 @@ class Plan:
                                                    ndim=conv.nd))
                 self._wcache[key] = hit
             sp_main = dataclasses.replace(spec, cin=64, res_pre_act=1)
+            self._post_fused = False
             y, y_hi, y_lo = ops.conv_fwd_umma(x_hi, x_lo, hit[1], hit[2], bias, sp_main, n, dims,
                                               residual=part, want_f32=want32, want_pad16=want16)
             return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
@@ -418,6 +427,7 @@ class Plan:
             else:
                 x_hi, x_lo = cur.need_pad16(split, fmt)
             if conv.filters > 256:
+                self._post_fused = False
                 y = self._run_wide_head(conv, spec, x_hi, x_lo, bias, n, dims, split, out_shape)
                 return self._finish_conv(st, Act(out_shape, f32=y), skips)
             w_hi, w_lo, acc_scale = self._packed(conv, split)

@@ -190,6 +190,50 @@ def test_normalisation_and_output_features(cuda):
     assert rel_err(y_raw, oracle_out(hl, m.generator.get_weights(), x)) < 1e-4
 
 
+def test_set_norm_stats_overwrites_previous_stats():
+    """abstract.py:133-195: a new batch handler's statistics replace the model's (continued
+    training / transfer learning must not keep stale values)."""
+    from sup3r_b200.models import Sup3rGan
+    m = Sup3rGan(C.spatial_generator(2, (2,), n_blocks=1), C.discriminator(2, "same", (8,)),
+                 means={"u": 1.0, "v": 2.0}, stdevs={"u": 3.0, "v": 4.0},
+                 meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"]})
+    m.set_norm_stats({"u": 10.0, "v": 20.0}, {"u": 30.0, "v": 40.0})
+    assert m.means == {"u": np.float32(10.0), "v": np.float32(20.0)}
+    assert m.stdevs == {"u": np.float32(30.0), "v": np.float32(40.0)}
+    m.set_norm_stats(None, None)
+    assert m.means["u"] == np.float32(10.0)
+    with pytest.raises(TypeError):
+        m.set_norm_stats([1.0], [2.0])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16c"])
+def test_un_normalisation_after_wide_head(cuda, precision):
+    """A generator whose LAST fused step is a wide scatter head (64 -> 768, 12x depth_to_time):
+    that route does not fuse the post affine, so generate() must un-normalise afterwards."""
+    hl = C.sup3rcc_temporal_d2t_generator(2, 12, 32, n_blocks=1)
+    # drop everything after the depth_to_time head so that the head is the last step
+    last = max(i for i, l in enumerate(hl) if l.get("class") == "SpatioTemporalExpansion")
+    hl = hl[:last + 1]
+    means, stds = {"u": 2.0, "v": -3.0}, {"u": 4.0, "v": 0.5}
+    shape = (1, 6, 6, 4, 2)
+    m = make_model(hl, C.discriminator(3, "same", (8,)), shape, means=means, stdevs=stds,
+                   meta={"lr_features": ["u", "v"], "hr_out_features": [f"f{i}" for i in range(64)]})
+    out_c = m.generator.output_shape(shape)[-1]
+    feats = [f"f{i}" for i in range(out_c)]
+    m.meta["hr_out_features"] = feats
+    m.set_norm_stats({**means, **{f: 0.5 + i for i, f in enumerate(feats)}},
+                     {**stds, **{f: 1.0 + 0.1 * i for i, f in enumerate(feats)}})
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(shape) * 3 + 1).astype(np.float32)
+    xn = (x - np.array([2.0, -3.0])) / np.array([4.0, 0.5])
+    ref = oracle_out(hl, m.generator.get_weights(), xn)
+    ref = ref * np.array([1.0 + 0.1 * i for i in range(out_c)]) \
+        + np.array([0.5 + i for i in range(out_c)])
+    y = m.generate(x, precision=precision)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < (5e-2 if precision == "bf16" else 1e-3)
+
+
 def test_discriminate_matches_oracle(cuda):
     hl = C.discriminator(3, "same", (64, 32))
     m = make_model(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1), hl, (1, 4, 4, 4, 2),
