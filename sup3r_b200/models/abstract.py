@@ -405,34 +405,51 @@ class AbstractSingleModel(TensorboardMixIn):
             assert "{epoch}" in out_dir, (
                 "Model output dir for checkpoint models should have {epoch} but did not: "
                 f"{out_dir}")
-            self.save(out_dir.format(epoch=epoch))
+            self._save_rank0(out_dir.format(epoch=epoch))
         stop = False
         if early_stop_on is not None and early_stop_on in self._history:
             stop = self.early_stop(self._history, early_stop_on, threshold=early_stop_threshold,
                                    n_epoch=early_stop_n_epoch)
             if stop:
-                self.save(out_dir.format(epoch=epoch))
+                self._save_rank0(out_dir.format(epoch=epoch))
         if extras is not None:
             for k, v in extras.items():
                 self._history.at[epoch, k] = safe_cast(v)
         return stop
 
+    def _save_rank0(self, out_dir):
+        """Checkpoint from rank 0 only (the weights are replicated across ranks)."""
+        from .. import parallel
+        if parallel.rank() == 0:
+            self.save(out_dir)
+
     # ---- gradient step ---------------------------------------------------------------------
     def run_gradient_descent(self, low_res, hi_res_true, training_weights, optimizer=None,
                              multi_gpu=False, **calc_loss_kwargs):
-        """One optimiser step (abstract.py:843-914).  ``multi_gpu``: when the process group is
-        initialised (one rank per GPU) the batch shard's gradients are SUMMED across ranks
-        with an all-reduce before the (replicated) optimiser step -- the reference's
-        ``_get_parallel_grad`` / ``_sum_parallel_grad`` semantics (abstract.py:785-841)."""
+        """One optimiser step (abstract.py:843-914).  ``multi_gpu`` with an initialised process
+        group (one rank per GPU, every rank fed the SAME batch): the reference's
+        ``_get_parallel_grad`` / ``_sum_parallel_grad`` (abstract.py:785-841) -- the batch is
+        split along axis 0 into world_size equal shards, this rank takes shard ``rank``, the
+        shard gradients are SUMMED with one all-reduce and every rank applies the same step;
+        the returned loss details are the last shard's (see ``parallel``)."""
+        from .. import parallel
         if optimizer is None:
             optimizer = self.optimizer
         t0 = time.time()
-        grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
-                                                  device_name=self.default_device,
-                                                  **calc_loss_kwargs)
-        if multi_gpu:
-            from ..parallel import allreduce_sum_grads
-            allreduce_sum_grads(grad)
+        if multi_gpu and parallel.world_size() > 1:
+            low_res = parallel.shard_batch(low_res)
+            hi_res_true = parallel.shard_batch(hi_res_true)
+            if calc_loss_kwargs.get("mask") is not None:
+                calc_loss_kwargs["mask"] = parallel.shard_batch(calc_loss_kwargs["mask"])
+            grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
+                                                      device_name=self.default_device,
+                                                      **calc_loss_kwargs)
+            grad = parallel.allreduce_sum_grads(grad)
+            loss_details = parallel.broadcast_loss_details(loss_details)
+        else:
+            grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
+                                                      device_name=self.default_device,
+                                                      **calc_loss_kwargs)
         optimizer.apply_gradients(zip(grad, training_weights))
         logger.debug("Finished single gradient descent step in %.4f seconds", time.time() - t0)
         return loss_details

@@ -4,8 +4,14 @@ gloo in CPU tests).
 * inference shards independent chunks over ranks with no data-path collective (the reference
   splits ``node_chunks`` over SLURM nodes, pipeline/strategy.py:363-372) -- the only collective
   is one weight broadcast at start-up;
-* training all-reduces gradients with SUM (not mean), the reference's ``_sum_parallel_grad``
-  semantics (models/abstract.py:785-805), on one flat fp32 bucket per step.
+* training follows the reference's ``_get_parallel_grad`` / ``_sum_parallel_grad``
+  (models/abstract.py:785-841): ONE batch is split along axis 0 into ``world_size`` equal
+  shards (``tf.split`` raises when it does not divide), rank r computes the gradient of shard
+  r (per-shard losses, per-shard relativistic means), the gradients are SUMMED (not averaged)
+  through one persistent flat fp32 arena, and every rank applies the same optimiser step.
+  The loss details that drive the GAN schedule are those of the LAST shard (the reference
+  returns the last future's), broadcast so that every rank takes the same branch and issues
+  the same collectives.
 """
 from __future__ import annotations
 
@@ -37,18 +43,71 @@ def init_from_env(backend=None):
     dist.init_process_group(backend=backend)
 
 
+_arenas = {}
+
+
+def _arena_for(grads):
+    """Persistent flat fp32 buffer + per-tensor views for this list of gradient shapes."""
+    key = (str(grads[0].device), tuple(tuple(g.shape) for g in grads))
+    hit = _arenas.get(key)
+    if hit is None:
+        n = sum(g.numel() for g in grads)
+        flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+        views, off = [], 0
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view(g.shape))
+            off += g.numel()
+        hit = (flat, views)
+        _arenas[key] = hit
+    return hit
+
+
 def allreduce_sum_grads(grads):
-    """In-place SUM all-reduce of a list of gradient tensors through one flat bucket."""
+    """SUM all-reduce of a list of gradient tensors through one persistent flat arena (one
+    collective per step).  Returns the reduced gradients as VIEWS of the arena (no copy back):
+    valid until the next call with the same shapes."""
     if not is_distributed() or world_size() == 1:
         return grads
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat, views = _arena_for(grads)
+    torch._foreach_copy_(views, [g.detach() for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-    return grads
+    return views
+
+
+def shard_batch(x, n_shards=None, index=None):
+    """``tf.split(x, n, axis=0)[index]`` (abstract.py:819-825): equal shards or an error."""
+    n_shards = world_size() if n_shards is None else n_shards
+    index = rank() if index is None else index
+    if x is None or n_shards == 1:
+        return x
+    b = x.shape[0]
+    if b % n_shards:
+        raise ValueError(f"Dimension 0 of a batch of {b} observations is not evenly divisible "
+                         f"by the {n_shards} GPUs (tf.split semantics)")
+    k = b // n_shards
+    return x[index * k:(index + 1) * k]
+
+
+def broadcast_loss_details(loss_details, src=None):
+    """Every rank continues with the loss details of the LAST shard (the reference returns the
+    last future's, abstract.py:791-805): one small broadcast keeps the GAN schedule -- and
+    therefore the sequence of collectives -- identical on all ranks."""
+    if not is_distributed() or world_size() == 1:
+        return loss_details
+    src = world_size() - 1 if src is None else src
+    keys = sorted(loss_details)
+    dev = None
+    for v in loss_details.values():
+        if isinstance(v, torch.Tensor):
+            dev = v.device
+            break
+    if dev is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) \
+            if dist.get_backend() == "nccl" else torch.device("cpu")
+    vals = torch.stack([torch.as_tensor(loss_details[k], dtype=torch.float32).detach()
+                        .reshape(()).to(dev) for k in keys])
+    dist.broadcast(vals, src=src)
+    return {k: vals[i] for i, k in enumerate(keys)}
 
 
 def broadcast_weights(networks, src=0):

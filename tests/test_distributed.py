@@ -33,9 +33,26 @@ def _worker(rank, world, port, q):
         assert parallel.world_size() == world and parallel.rank() == rank
         # gradient all-reduce is a SUM over shards, not a mean
         grads = [torch.full((3, 2), float(rank + 1)), torch.arange(4.0) * (rank + 1)]
-        parallel.allreduce_sum_grads(grads)
-        assert torch.equal(grads[0], torch.full((3, 2), 3.0))
-        assert torch.equal(grads[1], torch.arange(4.0) * 3)
+        red = parallel.allreduce_sum_grads(grads)
+        assert torch.equal(red[0], torch.full((3, 2), 3.0))
+        assert torch.equal(red[1], torch.arange(4.0) * 3)
+        # the reduced gradients are views of ONE persistent flat arena (reused across steps)
+        red2 = parallel.allreduce_sum_grads([torch.ones(3, 2), torch.ones(4)])
+        assert red2[0].data_ptr() == red[0].data_ptr()
+        assert red2[1].data_ptr() == red[0].data_ptr() + 6 * 4
+        assert torch.equal(red2[1], torch.full((4,), 2.0))
+        # tf.split semantics of the batch shards (abstract.py:819-825)
+        batch = torch.arange(8.0).reshape(4, 2)
+        assert torch.equal(parallel.shard_batch(batch), batch[2 * rank:2 * rank + 2])
+        try:
+            parallel.shard_batch(torch.zeros(3, 2))
+            raise AssertionError("uneven batch must raise")
+        except ValueError:
+            pass
+        # loss details of the LAST shard reach every rank (same GAN schedule everywhere)
+        det = parallel.broadcast_loss_details({"loss_gen": torch.tensor(1.0 + rank),
+                                               "loss_disc": 10.0 * (rank + 1)})
+        assert float(det["loss_gen"]) == 2.0 and float(det["loss_disc"]) == 20.0
         # weights differ per rank before the broadcast, are identical to rank 0's afterwards
         CustomNetwork.seed(100 + rank)
         net = CustomNetwork(C.spatial_generator(2, (2,), n_blocks=1), name="g", device="cpu")

@@ -1,0 +1,145 @@
+"""Multi-GPU training on real hardware (NCCL, one process per GPU, world size 2): the split-batch
+gradient step of sup3r/models/abstract.py:785-914 -- ``tf.split`` of ONE batch over the GPUs,
+per-shard losses (incl. per-shard relativistic means, base.py:540-541), SUM of the shard
+gradients, one optimiser step, loss details of the last shard -- must reproduce, step for step,
+a single process that computes the shard gradients one after the other.  Needs >= 2 GPUs
+(``gpurun --gpus 2``); skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from sup3r_b200 import configs as C
+
+pytestmark = pytest.mark.gpu
+
+LR_SHAPE, HR_SHAPE = (4, 6, 6, 4, 2), (4, 12, 12, 8, 2)
+N_STEPS = 3
+
+
+def _model(gpu=0):
+    from sup3r_b200.models import Sup3rGan
+    Sup3rGan.seed(3)
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1),
+                 C.discriminator(3, "same", (16,)), learning_rate=1e-3, learning_rate_disc=2e-3,
+                 default_device=f"/gpu:{gpu}")
+    m.init_weights(LR_SHAPE, HR_SHAPE)
+    return m
+
+
+def _batches():
+    rng = np.random.default_rng(11)
+    return [(rng.standard_normal(LR_SHAPE).astype(np.float32),
+             rng.standard_normal(HR_SHAPE).astype(np.float32)) for _ in range(N_STEPS)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from sup3r_b200 import parallel
+        m = _model(rank)
+        parallel.broadcast_weights([m.generator, m.discriminator])
+        hist = []
+        for lr, hr in _batches():
+            d1 = m.run_gradient_descent(lr, hr, m.generator_weights, optimizer=m.optimizer,
+                                        weight_gen_advers=1e-2, train_gen=True, train_disc=False,
+                                        compute_disc=True, multi_gpu=True)
+            d2 = m.run_gradient_descent(lr, hr, m.discriminator_weights,
+                                        optimizer=m.optimizer_disc, weight_gen_advers=1e-2,
+                                        train_gen=False, train_disc=True, multi_gpu=True)
+            hist.append({**{k: float(v) for k, v in d1.items()},
+                         **{"disc_step_" + k: float(v) for k, v in d2.items()}})
+        # every rank ends with the same weights and the same loss records
+        w = [a for net in (m.generator, m.discriminator) for a in net.get_weights()]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ([a.tobytes() for a in w], hist))
+        assert gathered[0] == gathered[1], "ranks diverged"
+        # timed steps for the record (device time, max over ranks)
+        lr, hr = _batches()[0]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            m.run_gradient_descent(lr, hr, m.generator_weights, optimizer=m.optimizer,
+                                   weight_gen_advers=1e-2, train_gen=True, train_disc=False,
+                                   multi_gpu=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            q.put(("ok", w, hist, float(t.item())))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put(("error", repr(e) + traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_nccl_training_matches_split_batch_reference(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    status, w2, hist2, ms = q.get(timeout=500)
+    for p in procs:
+        p.join(timeout=60)
+    assert status == "ok", w2
+
+    # single-process statement of _get_parallel_grad / _sum_parallel_grad: the shards of each
+    # batch one after the other, gradients summed, one optimiser step, last shard's details
+    from sup3r_b200 import parallel
+    m = _model()
+    hist1 = []
+    for lr, hr in _batches():
+        rec = {}
+        for prefix, weights, opt, kw in (
+                ("", m.generator_weights, m.optimizer,
+                 dict(train_gen=True, train_disc=False, compute_disc=True)),
+                ("disc_step_", m.discriminator_weights, m.optimizer_disc,
+                 dict(train_gen=False, train_disc=True))):
+            total, details = None, None
+            for i in range(2):
+                g, details = m.get_single_grad(parallel.shard_batch(lr, 2, i),
+                                               parallel.shard_batch(hr, 2, i), weights,
+                                               weight_gen_advers=1e-2, **kw)
+                total = g if total is None else [a + b for a, b in zip(total, g)]
+            opt.apply_gradients(zip(total, weights))
+            rec.update({prefix + k: float(v) for k, v in details.items()})
+        hist1.append(rec)
+    w1 = [a for net in (m.generator, m.discriminator) for a in net.get_weights()]
+    # loss trajectory equality (every recorded loss term, every step)
+    for a, b in zip(hist1, hist2):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    for a, b in zip(w1, w2):
+        assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
+    # ... and it is NOT what a full-batch step gives (per-shard relativistic means, SUM of grads)
+    m_full = _model()
+    lr, hr = _batches()[0]
+    d_full = m_full.run_gradient_descent(lr, hr, m_full.generator_weights, optimizer=m_full.optimizer,
+                                         weight_gen_advers=1e-2, train_gen=True, train_disc=False,
+                                         compute_disc=True)
+    assert abs(float(d_full["loss_gen"]) - hist2[0]["loss_gen"]) > 1e-6
+    print(f"2-rank NCCL generator step: {ms:.2f} ms (device, max over ranks); trajectories equal")
