@@ -186,6 +186,12 @@ int s3_pack_weights_umma_c(const float* w, int taps, int cin, int cout, void* w_
  * fmt S3_FMT_FP16C (c == 64): lo receives the e4m3 correction rows (same byte geometry). */
 int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
                       void* lo, int fmt, s3_stream stream);
+/* The same with the halo content chosen: S3_PAD_REFLECT (forward operands) or S3_PAD_ZERO (the
+ * zero-extended output gradient of the tcgen05 dgrad: tape.gradient through the reflect-padded
+ * convolution, sup3r/models/abstract.py:1230-1238, is a zero-padded correlation with the flipped
+ * kernel followed by the adjoint of the reflect pad, s3_pad_bwd). */
+int s3_pack_act_pad16_ex(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
+                         void* lo, int fmt, int halo_mode, s3_stream stream);
 /* inverse (interior only); lo may be NULL.  For tests. */
 int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int n, const int32_t dims[3],
                         int c, float* x, int fmt, s3_stream stream);
@@ -240,6 +246,10 @@ int s3_loss_disc(const float* out_real, const float* out_fake, int b, float weig
 /* keras Adam step over a flat arena (abstract.py:899,912): step is the 1-based iteration. */
 int s3_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
                  float beta2, float eps, int64_t step, s3_stream stream);
+/* y (fp16, saturating) = x: halves the device -> host transfer of the high-resolution result when
+ * the consumer stores 16-bit data anyway (ForwardPass output_dtype, cf. the scaled integer dtypes
+ * of sup3r/writers). */
+int s3_cast_f16(const float* x, void* y, size_t n, s3_stream stream);
 /* out[0] = sum(x), out[1] = sum(|x|), out[2] = #nan-or-inf, out[3] = min, out[4] = max */
 int s3_stats(const float* x, size_t n, float* out5, s3_stream stream);
 /* per-channel min/max + NaN count for ForwardPass._output_check (forward_pass.py:384-425):

@@ -64,6 +64,7 @@ SIGNATURES = {
     "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "s3_pack_weights_umma_c": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P]),
     "s3_pack_act_pad16": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _P]),
+    "s3_pack_act_pad16_ex": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _I, _P]),
     "s3_unpack_act_pad16": (_I, [_P, _P, _I, _I, c_i32x3, _I, _P, _I, _P]),
     "s3_pad_fwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),
     "s3_pad_bwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "s3_content_loss": (_I, [_P, _P, _SZ, _I, _I, _I, _F, _P, _P, _P]),
     "s3_loss_disc": (_I, [_P, _P, _I, _F, _P, _P, _P, _P]),
     "s3_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, C.c_int64, _P]),
+    "s3_cast_f16": (_I, [_P, _P, _SZ, _P]),
     "s3_stats": (_I, [_P, _SZ, _P, _P]),
     "s3_channel_check": (_I, [_P, _SZ, _I, _P, _P]),
 }

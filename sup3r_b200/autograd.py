@@ -52,6 +52,78 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class ConvUmmaFn(torch.autograd.Function):
+    """3x3[x3] stride-1 reflect-pad-1 convolution with cin <= 64 on the tcgen05 kernels in the
+    fp16c operand format (fp16 + e4m3 correction rows, ~2^-15 relative: gradients stay inside
+    the 2e-3 bound of the float64 autograd test) -- forward AND input gradient.  ``w_eff`` is
+    the effective correlation kernel ``(*k, cin, cout)``; ``cache`` a dict owned by the layer
+    for the packed weights (keyed by the weight tensor's version).
+    Stands in for the generator convolutions under ``tf.GradientTape``
+    (sup3r/models/abstract.py:1131-1173, 1230-1238)."""
+
+    @staticmethod
+    def _packed(cache, key, w, ver, nd):
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                wk = w.detach()
+                if wk.shape[-2] < 64:     # zero rows for the padded input channels
+                    wk = torch.nn.functional.pad(wk, (0, 0, 0, 64 - wk.shape[-2]))
+                hit = (ver, *ops.pack_weights_umma(wk, ndim=nd, fmt=ops.S3_FMT_FP16C))
+            cache[key] = hit
+        return hit[1:]
+
+    @staticmethod
+    def forward(ctx, x, w, b, spec, cache):
+        n, dims, cin, nd = ops.dims3(x.shape)
+        ver = (w._version, w.data_ptr())
+        w_hi, w_c, acc = ConvUmmaFn._packed(cache, "fwd", w, ver, nd)
+        xp = x if cin == 64 else torch.nn.functional.pad(x, (0, 64 - cin))
+        x_hi, x_c = ops.pack_act_pad16(xp, split=True, fmt=ops.S3_FMT_FP16C)
+        sp = dataclasses.replace(spec, cin=64)
+        y, _, _ = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, b, sp, n, dims, fmt=ops.S3_FMT_FP16C,
+                                    acc_scale=acc)
+        ctx.spec, ctx.cache, ctx.x_shape = spec, cache, tuple(x.shape)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w, y if spec.act != S3_ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        spec = ctx.spec
+        dy = dy.contiguous()
+        if spec.act != S3_ACT_NONE:
+            dy = ops.act_bwd(y, dy, spec.act, spec.alpha)
+        lin = dataclasses.replace(spec, act=S3_ACT_NONE)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
+        if ctx.needs_input_grad[0]:
+            nd = spec.ndim
+            pads = [(0, 0)] + [(1, 1)] * nd + [(0, 0)]
+            pshape = tuple(s + p[0] + p[1] for s, p in zip(ctx.x_shape, pads))
+            if spec.cout == 64 and spec.cin <= 256 and spec.cin % 16 == 0:
+                # zero-padded correlation of dy with the flipped / transposed kernel on the padded
+                # extent (tensor cores), then the adjoint of the reflect pad folds the halo back
+                ver = (w._version, w.data_ptr())
+                wt = w.detach().flip(dims=tuple(range(nd))).transpose(-1, -2).contiguous()
+                w_hi, w_c, acc = ConvUmmaFn._packed(ctx.cache, "dgrad", wt, ver, nd)
+                dyz = ops.pad_fwd(dy, pads, S3_PAD_ZERO)
+                n, dims, _, _ = ops.dims3(dyz.shape)
+                g_hi, g_c = ops.pack_act_pad16(dyz, split=True, fmt=ops.S3_FMT_FP16C,
+                                               halo=S3_PAD_ZERO)
+                sp = dataclasses.replace(lin, cin=64, cout=spec.cin)
+                dxp, _, _ = ops.conv_fwd_umma(g_hi, g_c, w_hi, w_c, None, sp, n, dims,
+                                              fmt=ops.S3_FMT_FP16C, acc_scale=acc)
+            else:
+                valid = dataclasses.replace(lin, pad_lo=(0, 0, 0), pad_hi=(0, 0, 0),
+                                            pad_mode=S3_PAD_ZERO)
+                dxp = ops.conv_dgrad(dy, w, valid, pshape)
+            dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
+        return dx, dw, db, None, None
+
+
 class PadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, paddings, mode):

@@ -277,7 +277,7 @@ __global__ void channel_affine_kernel(const float* __restrict__ x, float* __rest
 // ------------------------------------------------- 16-bit padded activations / weights
 __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
                                 uint16_t* __restrict__ lo, int pz, int n, int Z, int Y, int X,
-                                int c, int fmt, size_t total) {
+                                int c, int fmt, size_t total, int halo_mode) {
   const int PZ = Z + 2 * pz, PY = Y + 2, PX = X + 2;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -288,9 +288,9 @@ __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restric
     int pzc = (int)(t % PZ);
     int b = (int)(t / PZ);
     bool ok = true;
-    int z = pz ? fold_pad(pzc - 1, Z, S3_PAD_REFLECT, &ok) : pzc;
-    int y = fold_pad(py - 1, Y, S3_PAD_REFLECT, &ok);
-    int xx = fold_pad(px - 1, X, S3_PAD_REFLECT, &ok);
+    int z = pz ? fold_pad(pzc - 1, Z, halo_mode, &ok) : pzc;
+    int y = fold_pad(py - 1, Y, halo_mode, &ok);
+    int xx = fold_pad(px - 1, X, halo_mode, &ok);
     float v = ok ? x[((((size_t)b * Z + z) * Y + y) * X + xx) * c + ch] : 0.f;
     uint16_t h = to16(v, fmt);
     hi[idx] = h;
@@ -721,14 +721,22 @@ extern "C" int s3_channel_affine(const float* x, float* y, size_t nvox, int c, c
 
 extern "C" int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c,
                                  void* hi, void* lo, int fmt, s3_stream stream) {
+  return s3_pack_act_pad16_ex(x, ndim, n, dims, c, hi, lo, fmt, S3_PAD_REFLECT, stream);
+}
+
+extern "C" int s3_pack_act_pad16_ex(const float* x, int ndim, int n, const int32_t dims[3], int c,
+                                    void* hi, void* lo, int fmt, int halo_mode,
+                                    s3_stream stream) {
   S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_pack_act_pad16: bad arguments");
+  S3_REQUIRE(halo_mode == S3_PAD_REFLECT || halo_mode == S3_PAD_ZERO,
+             "s3_pack_act_pad16: halo_mode must be S3_PAD_REFLECT or S3_PAD_ZERO");
   S3_REQUIRE(fmt != kFmtFp16c || !lo || c == 64, "s3_pack_act_pad16: fp16c rows need c == 64");
   const int pz = ndim == 3 ? 1 : 0;
-  S3_REQUIRE(dims[1] >= 2 && dims[2] >= 2 && (!pz || dims[0] >= 2),
+  S3_REQUIRE(halo_mode == S3_PAD_ZERO || (dims[1] >= 2 && dims[2] >= 2 && (!pz || dims[0] >= 2)),
              "s3_pack_act_pad16: reflect halo needs extents >= 2");
   size_t total = (size_t)n * (dims[0] + 2 * pz) * (dims[1] + 2) * (dims[2] + 2) * c;
   pack_act_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
-      x, (uint16_t*)hi, (uint16_t*)lo, pz, n, dims[0], dims[1], dims[2], c, fmt, total);
+      x, (uint16_t*)hi, (uint16_t*)lo, pz, n, dims[0], dims[1], dims[2], c, fmt, total, halo_mode);
   S3_LAUNCH_CHECK("pack_act");
   return S3_OK;
 }
@@ -744,6 +752,30 @@ extern "C" int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int
       (const uint16_t*)hi, (const uint16_t*)lo, x, pz, n, dims[0], dims[1], dims[2], c, fmt,
       total);
   S3_LAUNCH_CHECK("unpack_act");
+  return S3_OK;
+}
+
+__global__ void cast_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, size_t n4,
+                                const float* __restrict__ xs, uint16_t* __restrict__ ys,
+                                size_t tail0, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(f16x2_sat(v.x, v.y), f16x2_sat(v.z, v.w));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = tail0 + threadIdx.x; i < n; i += blockDim.x)
+      ys[i] = (uint16_t)(f16x2_sat(xs[i], 0.f) & 0xffffu);
+}
+
+extern "C" int s3_cast_f16(const float* x, void* y, size_t n, s3_stream stream) {
+  S3_REQUIRE(x && y, "s3_cast_f16: null pointer");
+  if (n == 0) return S3_OK;
+  const size_t n4 = n / 4;
+  cast_f16_kernel<<<grid_for(n4 ? n4 : 1), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n4, x,
+      reinterpret_cast<uint16_t*>(y), n4 * 4, n);
+  S3_LAUNCH_CHECK("cast_f16");
   return S3_OK;
 }
 

@@ -564,7 +564,8 @@ class AbstractSingleModel(TensorboardMixIn):
         """Differentiable generator forward on device tensors (abstract.py:1131-1173).
         ``hi_res_exo``: {feature: tensor} for the exo layers."""
         x = to_device_tensor(low_res, self.torch_device())
-        return self.plan_for(self.generator, "fp32").forward_train(x, hi_res_exo or {})
+        # (generator convolutions: tcgen05 forward + input gradient unless precision == "fp32")
+        return self.plan_for(self.generator, self.precision).forward_train(x, hi_res_exo or {})
 
     def _get_hr_exo_and_loss(self, low_res, hi_res_true, **calc_loss_kwargs):
         """Generator forward + loss (abstract.py:1175-1188)."""

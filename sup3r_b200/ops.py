@@ -249,13 +249,14 @@ def pack_weights_umma(w, split=False, fmt=0, ndim=None):
     return hi, lo
 
 
-def pack_act_pad16(x, split=False, fmt=0):
+def pack_act_pad16(x, split=False, fmt=0, halo=S3_PAD_REFLECT):
     x = _f32(x)
     ensure_device(x)
     n, dims, c, ndim = dims3(x.shape)
     hi = torch.empty(pad16_shape(n, dims, c, ndim), device=x.device, dtype=_dt16(fmt))
     lo = torch.empty_like(hi) if split else None
-    _cabi.call("s3_pack_act_pad16", _p(x), ndim, n, c_i32x3(*dims), c, _p(hi), _p(lo), fmt, _s())
+    _cabi.call("s3_pack_act_pad16_ex", _p(x), ndim, n, c_i32x3(*dims), c, _p(hi), _p(lo), fmt,
+               halo, _s())
     _count()
     return hi, lo
 
@@ -519,6 +520,16 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step):
     _cabi.call("s3_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr),
                float(beta1), float(beta2), float(eps), int(step), _s())
     _count()
+
+
+def cast_f16(x, out=None):
+    """fp32 -> fp16 (saturating) copy for 16-bit result transfers."""
+    x = _f32(x)
+    ensure_device(x)
+    y = out if out is not None else torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _cabi.call("s3_cast_f16", _p(x), _p(y), x.numel(), _s())
+    _count()
+    return y
 
 
 def stats(x):

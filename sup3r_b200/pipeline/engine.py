@@ -17,11 +17,18 @@ class GeneratePipeline:
     a pinned buffer that stays valid until two more batches have been pushed)."""
 
     def __init__(self, model, lr_shape, precision=None, norm_in=True, un_norm_out=True,
-                 slots=2, fresh_host=False, check=False):
+                 slots=2, fresh_host=False, check=False, out_dtype="float32"):
         """``fresh_host``: every result gets its own pinned buffer (from torch's caching
         host allocator) that the caller may keep; ``check``: per-chunk device-side
         (min, max, n_nan) of every output channel (``ForwardPass._output_check``,
-        forward_pass.py:384-425) travels with the result: ``pop()`` -> (array, checks)."""
+        forward_pass.py:384-425) travels with the result: ``pop()`` -> (array, checks);
+        ``out_dtype``: "float32" (the reference's dtype) or "float16" -- the result is cast on
+        the device and leaves as fp16 (half the D2H bytes and half the host memory traffic;
+        for consumers that store 16-bit data anyway)."""
+        if out_dtype not in ("float32", "float16"):
+            raise ValueError(f"out_dtype must be float32 or float16, got {out_dtype!r}")
+        self.out_dtype = out_dtype
+        self._tdt = torch.float16 if out_dtype == "float16" else torch.float32
         self.fresh_host = fresh_host
         self.check = check
         if not torch.cuda.is_available():
@@ -56,7 +63,9 @@ class GeneratePipeline:
                 plan=plan,
                 x_host=torch.empty(self.lr_shape, dtype=torch.float32).pin_memory(),
                 x_dev=torch.empty(self.lr_shape, dtype=torch.float32, device=self.dev),
-                y_host=torch.empty(self.hr_shape, dtype=torch.float32).pin_memory(),
+                y_host=torch.empty(self.hr_shape, dtype=self._tdt).pin_memory(),
+                y16=(torch.empty(self.hr_shape, dtype=torch.float16, device=self.dev)
+                     if out_dtype == "float16" else None),
                 h2d=torch.cuda.Event(), run=torch.cuda.Event(), d2h=torch.cuda.Event(),
                 chk_host=torch.empty((self.hr_shape[0], self.hr_shape[-1], 3),
                                      dtype=torch.float32).pin_memory(),
@@ -64,7 +73,7 @@ class GeneratePipeline:
         self._next = 0
         self._queue = []
         self.h2d_bytes = int(np.prod(self.lr_shape)) * 4
-        self.d2h_bytes = int(np.prod(self.hr_shape)) * 4
+        self.d2h_bytes = int(np.prod(self.hr_shape)) * (2 if out_dtype == "float16" else 4)
         # warm-up: capture the graphs before any timing
         for sl in self.slots:
             with torch.cuda.stream(self.s_run):
@@ -102,9 +111,12 @@ class GeneratePipeline:
                     o = out[k] if crops is None or crops[k] is None else out[k][crops[k]]
                     parts.append(ops.channel_check(o.contiguous()))
                 chk = torch.stack(parts)
+            if sl["y16"] is not None:
+                from .. import ops
+                out = ops.cast_f16(out, out=sl["y16"])
             sl["run"].record(self.s_run)
         if self.fresh_host:
-            sl["y_host"] = torch.empty(self.hr_shape, dtype=torch.float32, pin_memory=True)
+            sl["y_host"] = torch.empty(self.hr_shape, dtype=self._tdt, pin_memory=True)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(sl["run"])
             sl["y_host"].copy_(out, non_blocking=True)

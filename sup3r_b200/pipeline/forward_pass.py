@@ -209,42 +209,48 @@ class ForwardPass:
         model = fwp.model
         if not model.is_5d or strategy.exo_data is not None:
             return cls._run_serial(strategy, node_index)
+        # group the unfinished chunks by padded shape from the slicer alone; the chunks themselves
+        # are sliced / padded lazily, one batch ahead of the GPU (host memory ~ 2 batches)
         groups = {}
         for chunk_index in strategy.node_chunks[node_index]:
             chunk_index = int(chunk_index)
             if strategy.chunk_finished(chunk_index):
                 continue
-            chunk = fwp.get_input_chunk(chunk_index=chunk_index, mode=strategy.pad_mode)
-            cls._check_nan_input(chunk, model)
-            groups.setdefault(chunk.input_data.shape, []).append(chunk)
+            groups.setdefault(strategy.chunk_padded_shape(chunk_index), []).append(chunk_index)
         outputs = {}
         from .engine import GeneratePipeline
         cache = model.__dict__.setdefault("_fwp_pipelines", {})
-        for shape, chunks in groups.items():
+        out_dtype = getattr(strategy, "output_dtype", "float32")
+        for shape, ids in groups.items():
             lr_shape = (batch_size, *shape)
-            key = (lr_shape, model.precision)
+            in_memory = any(strategy.out_files[i] is None for i in ids)
+            key = (lr_shape, model.precision, out_dtype, in_memory)
             pipe = cache.get(key)
             if pipe is None:
                 # pinned buffers, H2D / generator / D2H on three streams, device-side output
-                # check: the host only slices views of the returned arrays
-                pipe = cache[key] = GeneratePipeline(model, lr_shape, check=True)
-            parts = [chunks[i:i + batch_size] for i in range(0, len(chunks), batch_size)]
+                # check; results kept in memory land in their own pinned buffers (no second host
+                # copy), chunk files are written straight from the reused slots
+                pipe = cache[key] = GeneratePipeline(model, lr_shape, check=True,
+                                                     out_dtype=out_dtype, fresh_host=in_memory)
+            parts = [ids[i:i + batch_size] for i in range(0, len(ids), batch_size)]
 
-            def batches():
-                for part in parts:
-                    batch = np.stack([c.input_data for c in part]
-                                     + [part[-1].input_data] * (batch_size - len(part)), axis=0)
-                    yield batch, [c.hr_crop_slice for c in part] + [None] * (batch_size - len(part))
+            def load(part_ids):
+                part = []
+                for ci in part_ids:
+                    chunk = fwp.get_input_chunk(chunk_index=ci, mode=strategy.pad_mode)
+                    cls._check_nan_input(chunk, model)
+                    assert chunk.input_data.shape == shape, (chunk.input_data.shape, shape)
+                    part.append(chunk)
+                batch = np.stack([c.input_data for c in part]
+                                 + [part[-1].input_data] * (batch_size - len(part)), axis=0)
+                crops = [c.hr_crop_slice for c in part] + [None] * (batch_size - len(part))
+                for c in part:
+                    c.input_data = None      # the batch holds the data now
+                return part, batch, crops
 
             def finish(part, hi_res, checks):
                 cls._check_enhancement(hi_res, np.empty(lr_shape), model.s_enhance,
                                        model.t_enhance, 1, 3)
-                if any(c.out_file is None for c in part):
-                    # results kept in memory leave the (reused) pinned slot through one
-                    # multi-threaded copy; chunk files are written straight from the slot
-                    import torch
-                    hi_res = torch.empty(hi_res.shape, dtype=torch.float32).copy_(
-                        torch.from_numpy(hi_res)).numpy()
                 for k, c in enumerate(part):
                     if cls._device_check_failed(checks[k], strategy.allowed_const):
                         raise MemoryError(f"Forward pass for chunk_index {c.index} failed with "
@@ -256,7 +262,8 @@ class ForwardPass:
                         outputs[c.index] = data
 
             pending = []          # chunk lists of the batches in flight, oldest first
-            for part, (batch, crops) in zip(parts, batches()):
+            for part_ids in parts:
+                part, batch, crops = load(part_ids)
                 if len(pipe._queue) == len(pipe.slots):
                     hi_res, checks = pipe.pop()
                     finish(pending.pop(0), hi_res, checks)

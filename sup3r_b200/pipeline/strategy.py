@@ -153,6 +153,7 @@ class ForwardPassStrategy:
     model: Optional[object] = None
     exo_data: Optional[dict] = None
     pad_mode: str = "reflect"
+    output_dtype: str = "float32"   # "float16": results are cast on the device and leave as fp16
 
     def __post_init__(self):
         self.bias_correct_kwargs = self.bias_correct_kwargs or {}
@@ -307,6 +308,18 @@ class ForwardPassStrategy:
                 [lr_pad[0], lr_pad[1], ti_pad])
         data = self.input_handler.get(self.features, lr_pad[0], lr_pad[1], ti_pad)
         return data, exo
+
+    def chunk_padded_shape(self, chunk_index):
+        """(s1, s2, t, features) of the padded input chunk WITHOUT loading it (slice extents +
+        the extra edge padding of forward_pass.py:122-186)."""
+        s_idx, t_idx = self.get_chunk_indices(chunk_index)
+        lr_pad, ti_pad = self.lr_pad_slices[s_idx], self.ti_pad_slices[t_idx]
+        grid = self.input_handler.grid_shape
+        n_t = len(self.input_handler.time_index)
+        ext = [len(range(*sl.indices(n))) for sl, n in zip((lr_pad[0], lr_pad[1], ti_pad),
+                                                           (grid[0], grid[1], n_t))]
+        pw = self.fwp_slicer.extra_padding[chunk_index]
+        return tuple(e + int(p[0]) + int(p[1]) for e, p in zip(ext, pw)) + (len(self.features),)
 
     def init_chunk(self, chunk_index=0):
         s_idx, t_idx = self.fwp_slicer.get_chunk_indices(chunk_index)

@@ -36,7 +36,7 @@ _FMT = {"fp32": 0, "bf16": ops.S3_FMT_BF16, "bf16x3": ops.S3_FMT_BF16, "fp16c": 
 
 
 def default_precision():
-    p = os.environ.get("SUP3R_B200_PRECISION", "bf16x3")
+    p = os.environ.get("SUP3R_B200_PRECISION", "fp16c")
     if p not in PRECISIONS:
         raise ValueError(f"SUP3R_B200_PRECISION must be one of {PRECISIONS}, got {p!r}")
     return p
@@ -515,14 +515,25 @@ class Plan:
         return (len(out_shape) == 5 and out_shape[-1] == 64 and st.r == 1 and st.m == 1
                 and min(out_shape[1:-1]) >= 4)
 
+    @staticmethod
+    def _train_umma_ok(st, in_shape):
+        """Convolutions of the training forward that run on the tcgen05 kernels: 3x3[x3], stride
+        1, reflect-pad-1, cin <= 64 (narrow inputs zero-padded), 32 <= cout <= 256."""
+        conv = st.conv
+        return (st.pads is not None and conv.nd in (2, 3) and in_shape[-1] <= 64
+                and 32 <= conv.filters <= 256 and all(k == 3 for k in conv.kernel_size)
+                and all(s == 1 for s in conv.strides) and st.pad_mode == S3_PAD_REFLECT
+                and all(tuple(p) == (1, 1) for p in st.pads) and min(in_shape[1:-1]) >= 2)
+
     # -- training forward (autograd) -------------------------------------------------
     def forward_train(self, x, exo=None):
         """Differentiable forward on the fp32 kernels: the same fused steps, each wrapped in
         an autograd Function (conv with implicit padding + bias + activation; expansion; skip
         add).  Stands in for ``_tf_generate`` / ``_tf_discriminate`` under a GradientTape
         (abstract.py:1131-1173, base.py:283-313)."""
-        from .autograd import AddFn, ConvFn, ExpandFn
+        from .autograd import AddFn, ConvFn, ConvUmmaFn, ExpandFn
         net = self.net
+        tensor_cores = self.precision != "fp32"
         exo = exo or {}
         if not net.built:
             net.build(tuple(x.shape), {k: v.shape[-1] for k, v in exo.items()})
@@ -538,7 +549,12 @@ class Plan:
                         spec = conv.spec(cur.shape, extra_pad=st.pads, act=st.act,
                                          alpha=st.alpha, pad_mode=st.pad_mode)
                     b = conv.bias.value if conv.bias is not None else None
-                    cur = ConvFn.apply(cur, conv.conv_kernel(), b, spec)
+                    if tensor_cores and self._train_umma_ok(st, tuple(cur.shape)):
+                        # forward + input gradient on tcgen05 (fp16c operands)
+                        cache = conv.__dict__.setdefault("_umma_train_cache", {})
+                        cur = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, spec, cache)
+                    else:
+                        cur = ConvFn.apply(cur, conv.conv_kernel(), b, spec)
                     if st.r > 1 or st.m > 1:
                         cur = ExpandFn.apply(cur, st.r, st.m, st.method, st.roll)
                     if st.skip_add is not None:
