@@ -58,12 +58,14 @@ class TorchRefNet:
         self.dtype = dtype
         self.weights = [torch.as_tensor(np.asarray(w)).to(dtype).clone()
                         .requires_grad_(requires_grad) for w in weights]
+        self.bn_state = []   # [(moving_mean, moving_variance)] per BatchNormalization layer
 
     def __call__(self, x, exo=None):
         x = torch.as_tensor(x).to(self.dtype) if not isinstance(x, torch.Tensor) else x
         wi = iter(self.weights)
         skips = {}
         exo = exo or {}
+        self._bn_i = 0
         for cfg in self.cfg:
             cls = cfg["class"]
             nd = x.dim() - 2
@@ -140,6 +142,28 @@ class TorchRefNet:
                 x = x + torch.as_tensor(exo[cfg["name"]]).to(x.dtype)
             elif cls == "Sup3rConcat":
                 x = torch.cat((x, torch.as_tensor(exo[cfg["name"]]).to(x.dtype)), dim=-1)
+            elif cls == "Sup3rConcatObs":
+                # restated contract (see sup3r_b200/network.py:Sup3rConcatObs): NaNs of the sparse
+                # observation field are filled from channel ``fill_index`` of x, then concatenated
+                obs = exo.get(cfg["name"])
+                if obs is not None:
+                    obs = torch.as_tensor(obs).to(x.dtype)
+                    i0 = int(cfg.get("fill_index") or 0)
+                    fill = x[..., i0:i0 + obs.shape[-1]]
+                    nan = torch.isnan(obs)
+                    x = torch.cat((x, torch.where(nan, fill, obs)), dim=-1)
+                    if cfg.get("include_mask", False):
+                        x = torch.cat((x, (~nan).to(x.dtype)), dim=-1)
+            elif cls == "BatchNormalization":
+                # keras inference mode (the reference never passes training=True); state =
+                # (moving_mean, moving_variance) from ``self.bn_state[layer index]``
+                g = next(wi) if cfg.get("scale", True) else 1.0
+                b = next(wi) if cfg.get("center", True) else 0.0
+                mean, var = self.bn_state[self._bn_i]
+                self._bn_i += 1
+                mean = torch.as_tensor(mean).to(x.dtype)
+                var = torch.as_tensor(var).to(x.dtype)
+                x = (x - mean) / torch.sqrt(var + cfg.get("epsilon", 1e-3)) * g + b
             elif cls == "Flatten":
                 x = x.reshape(x.shape[0], -1)
             elif cls == "Dense":

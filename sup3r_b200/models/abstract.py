@@ -20,7 +20,8 @@ import torch
 from .. import loss_metrics, ops
 from ..exo import ExoData
 from ..network import (CustomNetwork, DeviceArray, SUP3R_EXO_LAYERS, SUP3R_LAYERS,
-                       SUP3R_OBS_LAYERS, default_device, to_device_tensor)
+                       SUP3R_OBS_LAYERS, exo_out_shape, layer_features,
+                       run_exo_layer as _run_exo_layer, default_device, to_device_tensor)
 from ..optimizers import OPTIMIZERS, Adam
 from ..plan import Plan, default_precision
 from ..utilities import VERSION_RECORD, Timer, camel_to_underscore, safe_cast
@@ -476,30 +477,40 @@ class AbstractSingleModel(TensorboardMixIn):
         return hi_res_exo
 
     def _exo_for_layer(self, layer, shape_like, exogenous_data, norm_in):
-        features = getattr(layer, "features", [layer.name])
-        stack = []
-        for feat in features:
-            assert exogenous_data is not None and feat in exogenous_data, (
-                f'exogenous_data is missing required feature "{feat}"')
+        """{feature: normalised, rank-matched array} for the ``features`` (+ ``exo_features``
+        extras) of one exo / obs layer (abstract.py:981-1035).  Observation features that are
+        not in ``exogenous_data`` are skipped with a warning (the layer then runs without them);
+        any other missing feature is an ``AssertionError``."""
+        out = {}
+        feats = layer_features(layer)
+        is_obs = isinstance(layer, SUP3R_OBS_LAYERS)
+        for feat in feats + list(getattr(layer, "exo_features", [])):
+            missing = exogenous_data is None or feat not in exogenous_data
+            if is_obs and feat in feats and missing:
+                logger.warning("%s does not match any features in exogenous_data (%s). Will run "
+                               "without this observation feature.", feat,
+                               list(exogenous_data or {}))
+                continue
+            assert not missing, f'exogenous_data is missing required feature "{feat}"'
             exo = exogenous_data.get_combine_type_data(feat, "layer")
-            stack.append(self._reshape_norm_exo(shape_like, exo, feat, norm_in=norm_in))
-        return np.concatenate(stack, axis=-1) if len(stack) > 1 else stack[0]
+            out[feat] = self._reshape_norm_exo(shape_like, exo, feat, norm_in=norm_in)
+        return out
 
     def run_exo_layer(self, layer, input_array, exogenous_data, norm_in=True):
-        """Run one Sup3rAdder / Sup3rConcat layer from public ``generate`` inputs
+        """Run one Sup3rAdder / Sup3rConcat / observation layer from public ``generate`` inputs
         (abstract.py:981-1035)."""
-        hr_exo = self._exo_for_layer(layer, input_array, exogenous_data, norm_in)
-        return layer(input_array, hr_exo)
+        exo = self._exo_for_layer(layer, input_array, exogenous_data, norm_in)
+        x = to_device_tensor(input_array, self.torch_device())
+        return _run_exo_layer(layer, x, exo).as_subclass(DeviceArray)
 
-    def _hr_shapes_at_exo_layers(self, in_shape):
-        """Tensor shape entering each exo layer for an input of ``in_shape``."""
+    def _hr_shapes_at_exo_layers(self, in_shape, exo_channels=None):
+        """Tensor shape entering each exo / obs layer for an input of ``in_shape``."""
         shp = tuple(in_shape)
         out = {}
         for lyr in self.generator.layers:
-            if isinstance(lyr, SUP3R_EXO_LAYERS):
+            if isinstance(lyr, SUP3R_LAYERS):
                 out[lyr.name] = shp
-                if hasattr(lyr, "out_shape") and type(lyr).__name__ == "Sup3rConcat":
-                    shp = lyr.out_shape(shp, len(getattr(lyr, "features", [lyr.name])))
+                shp = exo_out_shape(lyr, shp, exo_channels)
             else:
                 shp = lyr.out_shape(shp)
         return out
@@ -528,17 +539,22 @@ class AbstractSingleModel(TensorboardMixIn):
         if dev.type != "cuda":
             raise RuntimeError("sup3r_b200 needs a CUDA device to run the generator "
                                "(no CPU fallback)")
-        exo_layers = [lyr for lyr in gen.layers if isinstance(lyr, SUP3R_EXO_LAYERS)]
+        exo_layers = [lyr for lyr in gen.layers if isinstance(lyr, SUP3R_LAYERS)]
         exo_dev = {}
         if exo_layers:
-            shapes = self._hr_shapes_at_exo_layers(low_res.shape)
+            # observation features that are absent make their layer the identity
+            absent = {f: 0 for lyr in exo_layers if isinstance(lyr, SUP3R_OBS_LAYERS)
+                      for f in layer_features(lyr)
+                      if exogenous_data is None or f not in exogenous_data}
+            shapes = self._hr_shapes_at_exo_layers(low_res.shape, absent)
             for lyr in exo_layers:
                 try:
-                    arr = self._exo_for_layer(lyr, np.empty(shapes[lyr.name][:-1] + (0,)),
-                                              exogenous_data, norm_in)
+                    arrs = self._exo_for_layer(lyr, np.empty(shapes[lyr.name][:-1] + (0,)),
+                                               exogenous_data, norm_in)
                 except AssertionError as e:
                     raise RuntimeError(f'Could not run layer "{lyr}": {e}') from e
-                exo_dev[lyr.name] = to_device_tensor(arr, dev)
+                for f, arr in arrs.items():
+                    exo_dev[f] = to_device_tensor(arr, dev)
         x = to_device_tensor(low_res, dev)
         if norm_in and self._means is not None:
             x = self.norm_input(x)

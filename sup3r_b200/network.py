@@ -249,6 +249,11 @@ class _Conv(Layer):
         """ConvSpec for input shape ``shp``; ``extra_pad``: [(lo, hi)] per conv dim overriding
         the layer's own implicit padding."""
         nd = self.nd
+        if self.kernel is not None:
+            cin_built = self.kernel.shape[-1] if self.transposed else self.kernel.shape[-2]
+            if int(shp[-1]) != int(cin_built):
+                raise RuntimeError(f'{type(self).__name__} "{self.name}" was built for {cin_built} '
+                                   f"input channels but got a tensor of shape {tuple(shp)}")
         if extra_pad is None:
             if self.transposed:
                 extra_pad = [(k - 1, k - 1) for k in self.kernel_size]
@@ -457,6 +462,215 @@ class Sup3rConcat(Layer):
         return ConcatFn.apply(x, hi_res_feature)
 
 
+
+class _BatchNormFn(torch.autograd.Function):
+    """y = x * inv + (beta - mean * inv),  inv = gamma / sqrt(var + eps)  (per channel).  The
+    forward and dX are one fused per-channel affine kernel each; the two tiny parameter
+    reductions (dgamma, dbeta: C values) are device tensor reductions."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, eps):
+        rstd = torch.rsqrt(var + eps)
+        inv = gamma * rstd
+        ctx.save_for_backward(x, inv, rstd, mean)
+        return ops.channel_affine(x, inv.contiguous(), (beta - mean * inv).contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, inv, rstd, mean = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.channel_affine(dy, inv.contiguous(), None) if ctx.needs_input_grad[0] else None
+        dgamma = dbeta = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            c = x.shape[-1]
+            d2, x2 = dy.reshape(-1, c), x.reshape(-1, c)
+            dbeta = d2.sum(dim=0)
+            dgamma = ((x2 - mean) * d2).sum(dim=0) * rstd
+        return dx, dgamma, dbeta, None, None, None
+
+
+class BatchNormalization(Layer):
+    """keras ``BatchNormalization`` over the channel axis in INFERENCE mode: the reference calls
+    every layer as ``layer(x)`` without a training flag (sup3r/models/abstract.py:1081-1092,
+    1157-1165), so the moving statistics are used (and never updated) in ``generate`` and in
+    ``_tf_generate`` alike.  gamma / beta are trainable; the moving mean / variance are state."""
+
+    has_weights = True
+
+    def __init__(self, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, name=None,
+                 **_):
+        super().__init__(name)
+        if axis not in (-1,):
+            raise ValueError("BatchNormalization: only the channel axis (-1) is supported")
+        self.momentum, self.epsilon = float(momentum), float(epsilon)
+        self.center, self.scale = bool(center), bool(scale)
+        self.gamma = self.beta = self.moving_mean = self.moving_variance = None
+
+    @property
+    def weights(self):
+        return [v for v, on in ((self.gamma, self.scale), (self.beta, self.center))
+                if v is not None and on]
+
+    def build(self, shp, rng, device):
+        c = int(shp[-1])
+        if self.gamma is None:
+            mk = lambda nm, val: Variable(f"{self.name}/{nm}:0",
+                                          torch.full((c,), val, dtype=torch.float32, device=device))
+            self.gamma, self.beta = mk("gamma", 1.0), mk("beta", 0.0)
+            self.moving_mean, self.moving_variance = mk("moving_mean", 0.0), mk("moving_variance", 1.0)
+        elif self.gamma.shape[0] != c:
+            raise RuntimeError(f'BatchNormalization "{self.name}" was built for '
+                               f"{self.gamma.shape[0]} channels but got {c}")
+        self.built = True
+
+    def restore(self, it, device):
+        vals = {}
+        names = [n for n, on in (("gamma", self.scale), ("beta", self.center)) if on]
+        for n in names:
+            vals[n] = np.asarray(next(it), dtype=np.float32)
+        c = len(next(iter(vals.values()))) if vals else None
+        for n, dflt in (("gamma", 1.0), ("beta", 0.0)):
+            if n in vals:
+                setattr(self, n, Variable(f"{self.name}/{n}:0",
+                                          torch.from_numpy(vals[n].copy()).to(device)))
+        self._restore_c = c
+        self.built = True
+
+    def extra_state(self):
+        if self.moving_mean is None:
+            return {}
+        return {"moving_mean": self.moving_mean.numpy(),
+                "moving_variance": self.moving_variance.numpy()}
+
+    def set_extra_state(self, state, device):
+        for n in ("moving_mean", "moving_variance"):
+            if n in state:
+                setattr(self, n, Variable(f"{self.name}/{n}:0", torch.from_numpy(
+                    np.asarray(state[n], np.float32).copy()).to(device)))
+
+    def _param(self, v, c, val, device):
+        if v is not None:
+            return v.value
+        return torch.full((c,), val, dtype=torch.float32, device=device)
+
+    def forward(self, x):
+        c, dev = x.shape[-1], x.device
+        return _BatchNormFn.apply(x.contiguous(), self._param(self.gamma, c, 1.0, dev),
+                                  self._param(self.beta, c, 0.0, dev),
+                                  self._param(self.moving_mean, c, 0.0, dev),
+                                  self._param(self.moving_variance, c, 1.0, dev), self.epsilon)
+
+
+class _NanFillFn(torch.autograd.Function):
+    """where(isnan(obs), fill, obs): gradient flows to ``fill`` at the unobserved locations."""
+
+    @staticmethod
+    def forward(ctx, obs, fill):
+        m = torch.isnan(obs)
+        ctx.save_for_backward(m)
+        return torch.where(m, fill, obs)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (m,) = ctx.saved_tensors
+        return None, torch.where(m, dy, torch.zeros_like(dy))
+
+
+class Sup3rConcatObs(Layer):
+    """Concatenate sparse observation data (NaN where unobserved) mid-network.  phygnn's source is
+    not vendored in the reference; semantics restated from its call sites
+    (sup3r/models/with_obs.py:18-27, abstract.py:1000-1035, tests/conftest.py:129-130): NaNs are
+    replaced by the gridded estimate the network already carries -- channel ``fill_index`` of
+    ``x`` (default: the obs layer's position among the consecutive obs layers, so ``u_10m_obs``
+    after a (u, v) tensor is filled from u and ``v_10m_obs`` from v) -- and the filled field is
+    appended as a new channel.  ``include_mask`` also appends the 0 / 1 observed mask.  With no
+    observation data the layer is the identity (abstract.py:1004-1013)."""
+
+    def __init__(self, name=None, fill_index=None, include_mask=False, features=None):
+        super().__init__(name)
+        self.fill_index = fill_index
+        self.include_mask = bool(include_mask)
+        if features is not None:
+            self.features = list(features)
+
+    def out_shape(self, shp, n_exo=1):
+        return (*shp[:-1], shp[-1] + n_exo * (2 if self.include_mask else 1))
+
+    def forward(self, x, hi_res_feature=None):
+        if hi_res_feature is None:
+            return x
+        _match_exo(x, hi_res_feature, f'Sup3rConcatObs "{self.name}"')
+        n = hi_res_feature.shape[-1]
+        i0 = int(self.fill_index or 0)
+        if i0 + n > x.shape[-1]:
+            raise RuntimeError(f'Sup3rConcatObs "{self.name}": fill channels {i0}:{i0 + n} exceed '
+                               f"the {x.shape[-1]} channels of the hi-res tensor")
+        crop = [(0, 0)] * (x.dim() - 1) + [(i0, x.shape[-1] - i0 - n)]
+        fill = CropFn.apply(x, crop)
+        out = ConcatFn.apply(x, _NanFillFn.apply(hi_res_feature, fill).contiguous())
+        if self.include_mask:
+            out = ConcatFn.apply(out, (~torch.isnan(hi_res_feature)).to(x.dtype))
+        return out
+
+
+class Sup3rObsModel(Layer):
+    """Observation-embedding sub-network ``layer(x, hi_res_obs[, extras])`` (call protocol of
+    sup3r/models/abstract.py:1026-1035, 1118-1129; ``features`` = observation features,
+    ``exo_features`` = gridded extras such as topography).  NaNs of the observations are filled
+    from the leading channels of ``x``; [filled obs, observed mask, extras] run through the
+    layer's own ``hidden_layers`` and the embedding is concatenated to ``x``.  (phygnn's source is
+    not vendored: the internals are this library's restatement of that contract.)"""
+
+    has_weights = True
+
+    def __init__(self, name=None, features=None, exo_features=None, hidden_layers=None,
+                 fill_index=0):
+        super().__init__(name)
+        self.features = list(features) if features is not None else [self.name]
+        self.exo_features = list(exo_features or [])
+        self.fill_index = int(fill_index)
+        self._net = CustomNetwork(hidden_layers or [], name=f"{self.name}_embed")
+
+    @property
+    def weights(self):
+        return self._net.weights
+
+    def _embed_channels(self, n_obs, n_extra):
+        return 2 * n_obs + n_extra
+
+    def out_shape(self, shp, n_exo=None):
+        n_obs = len(self.features) if n_exo is None else n_exo
+        cin = self._embed_channels(n_obs, len(self.exo_features))
+        return (*shp[:-1], shp[-1] + self._net.output_shape((*shp[:-1], cin))[-1])
+
+    def build(self, shp, rng, device):
+        cin = self._embed_channels(len(self.features), len(self.exo_features))
+        self._net.device = torch.device(device)
+        self._net.build((*shp[:-1], cin))
+        self.built = True
+
+    def restore(self, it, device):
+        self._net.device = torch.device(device)
+        self._net._restore_from(it)
+        self.built = True
+
+    def forward(self, x, hi_res_obs=None, extras=None):
+        if hi_res_obs is None:
+            return x
+        _match_exo(x, hi_res_obs, f'Sup3rObsModel "{self.name}"')
+        n = hi_res_obs.shape[-1]
+        crop = [(0, 0)] * (x.dim() - 1) + [(self.fill_index, x.shape[-1] - self.fill_index - n)]
+        filled = _NanFillFn.apply(hi_res_obs, CropFn.apply(x, crop)).contiguous()
+        z = ConcatFn.apply(filled, (~torch.isnan(hi_res_obs)).to(x.dtype))
+        if extras is not None:
+            z = ConcatFn.apply(z, extras.contiguous())
+        if not self._net.built:
+            self._net.build(tuple(z.shape))
+        for lyr in self._net.layers:
+            z = lyr.forward(z)
+        return ConcatFn.apply(x, z.contiguous())
+
+
 class Flatten(Layer):
     def out_shape(self, shp):
         return (shp[0], int(np.prod(shp[1:])))
@@ -527,11 +741,52 @@ class Dropout(Layer):
 LAYER_CLASSES = {c.__name__: c for c in (
     FlexiblePadding, Conv2D, Conv3D, Conv2DTranspose, Conv3DTranspose, Cropping2D, Cropping3D,
     LeakyReLU, Activation, SkipConnection, SpatialExpansion, SpatioTemporalExpansion, Sup3rAdder,
-    Sup3rConcat, Flatten, Dense, Dropout)}
+    Sup3rConcat, Sup3rConcatObs, Sup3rObsModel, BatchNormalization, Flatten, Dense, Dropout)}
 
 SUP3R_EXO_LAYERS = (Sup3rAdder, Sup3rConcat)
-SUP3R_OBS_LAYERS = ()
+SUP3R_OBS_LAYERS = (Sup3rObsModel, Sup3rConcatObs)   # sup3r/models/utilities.py:23
 SUP3R_LAYERS = (*SUP3R_EXO_LAYERS, *SUP3R_OBS_LAYERS)
+
+
+def layer_features(lyr):
+    """Exogenous feature names an exo / obs layer consumes (default: its own name;
+    sup3r/models/abstract.py:1001-1002)."""
+    return list(getattr(lyr, "features", [lyr.name]))
+
+
+def layer_exo_channels(lyr, exo_channels):
+    ec = exo_channels or {}
+    return int(sum(ec.get(f, 1) for f in layer_features(lyr)))
+
+
+def exo_out_shape(lyr, shp, exo_channels=None):
+    """Shape after an exo / obs layer; an obs layer without data (0 channels) is the identity."""
+    if isinstance(lyr, Sup3rAdder):
+        return tuple(shp)
+    n = layer_exo_channels(lyr, exo_channels)
+    return tuple(shp) if n == 0 else lyr.out_shape(shp, n)
+
+
+def run_exo_layer(lyr, x, exo):
+    """Gather ``features`` (+ ``exo_features`` extras) of one exo / obs layer from ``exo``
+    ({feature name: tensor}) and call it (sup3r/models/abstract.py:1107-1129; obs layers run
+    without a missing observation feature, abstract.py:1004-1013)."""
+    feats = layer_features(lyr)
+    extra_feats = list(getattr(lyr, "exo_features", []))
+    is_obs = isinstance(lyr, SUP3R_OBS_LAYERS)
+    stack, extras = [], []
+    for f in feats + extra_feats:
+        if exo.get(f) is None:
+            if is_obs and f in feats:
+                logger.warning("%s does not match any features in exogenous_data (%s). Will run "
+                               "without this observation feature.", f, list(exo))
+                continue
+            raise RuntimeError(f'exogenous data is missing required feature "{f}"')
+        (stack if f in feats else extras).append(to_device_tensor(exo[f], x.device))
+    hr = None if not stack else (stack[0] if len(stack) == 1 else torch.cat(stack, dim=-1))
+    if extras:
+        return lyr.forward(x, hr, extras[0] if len(extras) == 1 else torch.cat(extras, dim=-1))
+    return lyr.forward(x, hr)
 
 
 def expand_hidden_layers(hidden_layers):
@@ -578,7 +833,8 @@ class CustomNetwork:
                     self._skips[nm] = SkipConnection(nm)
                 self._layers.append(self._skips[nm])
                 continue
-            if cfg.get("name") is None and cls not in ("Sup3rAdder", "Sup3rConcat"):
+            if cfg.get("name") is None and cls not in ("Sup3rAdder", "Sup3rConcat", "Sup3rConcatObs",
+                                                       "Sup3rObsModel"):
                 base = cls.lower()
                 i = used.get(base, 0)
                 used[base] = i + 1
@@ -637,8 +893,8 @@ class CustomNetwork:
                             raise RuntimeError(f'SkipConnection "{lyr.name}" shape mismatch')
                     else:
                         cache[lyr.name] = shp
-                elif isinstance(lyr, Sup3rConcat):
-                    shp = lyr.out_shape(shp, exo_channels.get(lyr.name, 1))
+                elif isinstance(lyr, SUP3R_LAYERS):
+                    shp = exo_out_shape(lyr, shp, exo_channels)
                 else:
                     shp = lyr.out_shape(shp)
             except Exception as e:
@@ -656,8 +912,8 @@ class CustomNetwork:
                 lyr.build(shp, rng, self.device)
             elif not lyr.built:
                 lyr.built = True
-            if isinstance(lyr, Sup3rConcat):
-                shp = lyr.out_shape(shp, exo_channels.get(lyr.name, 1))
+            if isinstance(lyr, SUP3R_LAYERS):
+                shp = exo_out_shape(lyr, shp, exo_channels)
             else:
                 shp = lyr.out_shape(shp)
         self._built_for = tuple(in_shape[1:])
@@ -677,11 +933,8 @@ class CustomNetwork:
         self.reset_skips()
         try:
             for i, lyr in enumerate(self._layers):
-                if isinstance(lyr, SUP3R_EXO_LAYERS):
-                    if lyr.name not in exo:
-                        raise RuntimeError(f'exogenous data is missing required feature '
-                                           f'"{lyr.name}"')
-                    x = lyr.forward(x, to_device_tensor(exo[lyr.name], self.device))
+                if isinstance(lyr, SUP3R_LAYERS):
+                    x = run_exo_layer(lyr, x, exo)
                 else:
                     x = lyr.forward(x)
         except Exception as e:
@@ -714,7 +967,9 @@ class CustomNetwork:
         """Pickle of plain python / numpy objects: config, name and weights."""
         state = {"format": "sup3r_b200.CustomNetwork/1", "name": self.name,
                  "hidden_layers": self.hidden_layers, "built_for": self._built_for,
-                 "weight_names": [v.name for v in self.weights], "weights": self.get_weights()}
+                 "weight_names": [v.name for v in self.weights], "weights": self.get_weights(),
+                 "extra_state": {i: lyr.extra_state() for i, lyr in enumerate(self._layers)
+                                 if hasattr(lyr, "extra_state")}}
         with open(path, "wb") as f:
             pickle.dump(state, f)
 
@@ -727,16 +982,26 @@ class CustomNetwork:
                             "tools/export_phygnn_weights.py run in a TensorFlow environment)")
         net = cls(state["hidden_layers"], name=state.get("name"), device=device)
         net._restore(state["weights"])
+        for i, st in state.get("extra_state", {}).items():
+            net._layers[int(i)].set_extra_state(st, net.device)
         return net
 
     def _restore(self, arrays):
-        """Assign saved weights without knowing input shapes (shapes come from the arrays)."""
-        it = iter(arrays)
+        """Assign saved weights without knowing input shapes (shapes come from the arrays).  A
+        network saved before it was built has no weights: it stays unbuilt."""
+        if len(arrays) == 0:
+            return
+        self._restore_from(iter(arrays))
+
+    def _restore_from(self, it):
         seen = set()
         for lyr in self._layers:
             if not lyr.has_weights or id(lyr) in seen:
                 continue
             seen.add(id(lyr))
+            if hasattr(lyr, "restore"):
+                lyr.restore(it, self.device)
+                continue
             k = np.asarray(next(it), dtype=np.float32)
             lyr.kernel = Variable(f"{lyr.name}/kernel:0", torch.from_numpy(k.copy()).to(self.device))
             if lyr.use_bias:

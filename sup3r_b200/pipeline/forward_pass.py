@@ -207,8 +207,10 @@ class ForwardPass:
         replacement for the reference's ``SpawnProcessPool`` (forward_pass.py:503-580)."""
         fwp = cls(strategy, node_index=node_index)
         model = fwp.model
-        if not model.is_5d or strategy.exo_data is not None:
-            return cls._run_serial(strategy, node_index)
+        if hasattr(model, "models") or not model.is_5d or strategy.exo_data is not None:
+            # 4-D models, exogenous data, multi-step chains: one chunk per generator call,
+            # software-pipelined on the device (see _run_streamed)
+            return cls._run_streamed(strategy, node_index, fwp)
         # group the unfinished chunks by padded shape from the slicer alone; the chunks themselves
         # are sliced / padded lazily, one batch ahead of the GPU (host memory ~ 2 batches)
         groups = {}
@@ -272,6 +274,88 @@ class ForwardPass:
             while pending:
                 hi_res, checks = pipe.pop()
                 finish(pending.pop(0), hi_res, checks)
+        return outputs
+
+    @classmethod
+    def _run_streamed(cls, strategy, node_index, fwp=None):
+        """Chunk-at-a-time driver for everything the stacked-batch path does not cover (4-D
+        models, exogenous data, ``MultiStepGan`` chains; forward_pass.py:122-272, 582-673): the
+        generator output stays on the GPU, the crop and ``_output_check`` run there
+        (``s3_channel_check``), only the cropped interior leaves -- into its own pinned buffer on
+        a copy stream -- while the next chunk is already being generated."""
+        import torch
+        from .. import ops
+        start = dt.now()
+        fwp = fwp or cls(strategy, node_index=node_index)
+        model = fwp.model
+        first = getattr(model, "models", [model])[0]
+        dev = first.torch_device()
+        s_out = torch.cuda.Stream(dev)
+        outputs = {}
+        pending = []
+
+        def finish():
+            chunk, host, chk_host, done = pending.pop(0)
+            done.synchronize()
+            if cls._device_check_failed(chk_host.numpy(), strategy.allowed_const):
+                raise MemoryError(f"Forward pass for chunk_index {chunk.index} failed with "
+                                  "constant output or NaNs.")
+            data = host.numpy()
+            if chunk.out_file is not None:
+                logger.info("Saving forward pass output to %s.", chunk.out_file)
+                cls._write_output(data, chunk, fwp.meta)
+            else:
+                outputs[chunk.index] = data
+
+        chunks = strategy.node_chunks[node_index]
+        for i, chunk_index in enumerate(chunks):
+            chunk_index = int(chunk_index)
+            if strategy.chunk_finished(chunk_index):
+                continue
+            chunk = fwp.get_input_chunk(chunk_index=chunk_index, mode=strategy.pad_mode)
+            cls._check_nan_input(chunk, model)
+            data_chunk, exo, i_lr_t, i_lr_s = cls._reshape_data_chunk(
+                model, chunk.input_data, copy.deepcopy(chunk.exo_data))
+            # exo channels appended to a step's OUTPUT are combined on the host by generate()
+            host_combine = exo is not None and any(
+                st["combine_type"] == "output" for f in exo for st in exo[f]["steps"])
+            try:
+                hi_res = fwp.timer(model.generate, log=True)(
+                    data_chunk, exogenous_data=exo, **({} if host_combine else {"to_numpy": False}))
+            except Exception as e:
+                msg = f"Forward pass failed on chunk with shape {data_chunk.shape}."
+                logger.exception(msg)
+                raise RuntimeError(msg) from e
+            if not isinstance(hi_res, torch.Tensor):
+                # (models that post-process on the host, e.g. SolarCC's temporal padding)
+                hi_res = torch.as_tensor(np.ascontiguousarray(hi_res), device=dev)
+            if hi_res.ndim == 4:
+                hi_res = hi_res.permute(1, 2, 0, 3)[None]
+            cls._check_enhancement(hi_res, data_chunk, model.s_enhance, model.t_enhance, i_lr_s,
+                                   i_lr_t)
+            out = hi_res[0][chunk.hr_crop_slice].contiguous()
+            chk = ops.channel_check(out)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            host = torch.empty(tuple(out.shape), dtype=torch.float32, pin_memory=True)
+            chk_host = torch.empty(tuple(chk.shape), dtype=torch.float32, pin_memory=True)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ready)
+                host.copy_(out, non_blocking=True)
+                chk_host.copy_(chk, non_blocking=True)
+                out.record_stream(s_out)
+                chk.record_stream(s_out)
+                done = torch.cuda.Event()
+                done.record(s_out)
+            chunk.input_data = None
+            pending.append((chunk, host, chk_host, done))
+            if len(pending) > 1:
+                finish()
+            logger.info("Queued forward pass on chunk_index=%s. %d of %d.", chunk_index, i + 1,
+                        len(chunks))
+        while pending:
+            finish()
+        logger.info("Finished forward passes on %d chunks in %s", len(chunks), dt.now() - start)
         return outputs
 
     @staticmethod

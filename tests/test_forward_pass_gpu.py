@@ -1,0 +1,170 @@
+"""``ForwardPass`` on everything the stacked-batch path does not cover: 4-D models, exogenous data
+(tests/forward_pass/test_forward_pass_exo.py of the reference), ``MultiStepGan`` chains -- the
+streamed driver (device-side crop + output check, pinned D2H on a copy stream) must give exactly
+what the serial reference-shaped driver gives -- plus BASELINE configs[2] shapes (sup3rcc wind:
+20x20x72x6 chunk, 24x temporal then 5x spatial with topography) and ``Sup3rAdder``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.torch_ref import TorchRefNet
+from sup3r_b200 import configs as C
+from test_models_gpu import make_model, rel_err, rms_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _spatial_model(f=2, exo=None, s=2, seed=0):
+    hl = (C.sup3rcc_spatial_generator(f, s, 2, exo=exo, filters=16) if exo
+          else C.spatial_generator(f, (s,), n_blocks=1, filters=16))
+    feats = ["u", "v", "w", "x", "y", "z"][:f]
+    return make_model(hl, C.discriminator(2, "same", (8,)), (3, 8, 8, f),
+                      exo={exo: 1} if exo else None, seed=seed,
+                      meta={"lr_features": feats, "hr_out_features": feats,
+                            "s_enhance": s, "t_enhance": 1}), hl
+
+
+def _run_both(make_strategy):
+    from sup3r_b200.pipeline import ForwardPass
+    a = ForwardPass.run(make_strategy(1), 0)
+    b = ForwardPass.run(make_strategy(4), 0)
+    assert sorted(a) == sorted(b) and len(a) > 1
+    for k in a:
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+    return a
+
+
+def test_streamed_driver_4d_model(cuda):
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPassStrategy
+    m, _ = _spatial_model()
+    data = np.random.default_rng(0).standard_normal((12, 12, 6, 2)).astype(np.float32)
+    outs = _run_both(lambda w: ForwardPassStrategy(
+        model=m, input_handler=ArrayInputHandler(data, ["u", "v"]), fwp_chunk_shape=(6, 6, 6),
+        spatial_pad=2, temporal_pad=0, pass_workers=w))
+    assert outs[0].shape == (12, 12, 6, 2)
+
+
+def test_streamed_driver_with_exo_layer_data(cuda):
+    """tests/forward_pass/test_forward_pass_exo.py: hi-res topography enters through a
+    Sup3rConcat layer, sliced and edge-padded per chunk with the step's enhancement."""
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m, hl = _spatial_model(exo="topography")
+    rng = np.random.default_rng(1)
+    data = rng.standard_normal((12, 12, 4, 2)).astype(np.float32)
+    topo = rng.standard_normal((24, 24, 1)).astype(np.float32)
+
+    def exo():
+        return {"topography": {"steps": [{"model": 0, "combine_type": "layer",
+                                          "data": topo.copy(), "s_enhance": 2, "t_enhance": 1}]}}
+
+    outs = _run_both(lambda w: ForwardPassStrategy(
+        model=m, input_handler=ArrayInputHandler(data, ["u", "v"]), fwp_chunk_shape=(6, 6, 4),
+        spatial_pad=1, temporal_pad=0, pass_workers=w, exo_data=exo()))
+    assert outs[0].shape == (12, 12, 4, 2)
+    # one chunk over the whole domain == generate with the full exo field == the oracle
+    strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(data, ["u", "v"]),
+                                fwp_chunk_shape=(12, 12, 4), pass_workers=2, exo_data=exo())
+    out = ForwardPass.run(strat, 0)[0]
+    x = np.transpose(data, (2, 0, 1, 3))
+    topo_t = np.repeat(topo[None], 4, axis=0)
+    direct = m.generate(x, exogenous_data={"topography": {"steps": [
+        {"model": 0, "combine_type": "layer", "data": topo_t}]}})
+    assert np.array_equal(out, np.transpose(direct, (1, 2, 0, 3)))
+    ref = TorchRefNet(hl, m.generator.get_weights(), torch.float64)(
+        torch.tensor(x, dtype=torch.float64), {"topography": topo_t.astype(np.float64)})
+    assert rel_err(direct, ref.numpy()) < 1e-3
+
+
+def test_streamed_driver_multi_step_gan(cuda):
+    """tests/forward_pass/test_multi_step.py through the tiler: 4-D spatial step then 5-D
+    temporal step; device-resident intermediates."""
+    from sup3r_b200.models import MultiStepGan
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPassStrategy
+    m1, _ = _spatial_model()
+    m2 = make_model(C.spatiotemporal_generator(2, 1, (2,), n_blocks=1, head_filters=16, filters=16),
+                    C.discriminator(3, "same", (8,)), (1, 12, 12, 4, 2), seed=3,
+                    meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"],
+                          "s_enhance": 1, "t_enhance": 2})
+    ms = MultiStepGan([m1, m2])
+    data = np.random.default_rng(2).standard_normal((12, 12, 8, 2)).astype(np.float32)
+    outs = _run_both(lambda w: ForwardPassStrategy(
+        model=ms, input_handler=ArrayInputHandler(data, ["u", "v"]), fwp_chunk_shape=(6, 6, 8),
+        spatial_pad=1, temporal_pad=0, pass_workers=w))
+    assert outs[0].shape == (12, 12, 16, 2)
+
+
+def test_streamed_driver_output_check(cuda):
+    """Constant output -> MemoryError from the device-side check (forward_pass.py:384-425)."""
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m, _ = _spatial_model()
+    m.generator.set_weights([np.zeros_like(w) for w in m.generator.get_weights()])
+    data = np.random.default_rng(3).standard_normal((12, 12, 4, 2)).astype(np.float32)
+    strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(data, ["u", "v"]),
+                                fwp_chunk_shape=(6, 6, 4), pass_workers=2)
+    with pytest.raises(MemoryError):
+        ForwardPass.run(strat, 0)
+    strat = ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(data, ["u", "v"]),
+                                fwp_chunk_shape=(6, 6, 4), pass_workers=2, allowed_const=[0])
+    assert len(ForwardPass.run(strat, 0)) == 4
+
+
+def test_sup3r_adder_generator(cuda):
+    """Sup3rAdder (hi-res exo added mid-network) against the float64 restatement, all modes."""
+    hl = [*C._conv_block(2, 64), *C._conv_block(2, 4, act=False),
+          {"class": "SpatialExpansion", "spatial_mult": 2}, {"class": "Sup3rAdder", "name": "topo"},
+          *C._conv_block(2, 64), *C._conv_block(2, 2, act=False)]
+    shape = (2, 9, 7, 3)
+    m = make_model(hl, C.discriminator(2, "same", (8,)), shape, exo={"topo": 1})
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(shape).astype(np.float32)
+    topo = rng.standard_normal((2, 18, 14, 1)).astype(np.float32)
+    ref = TorchRefNet(hl, m.generator.get_weights(), torch.float64)(
+        torch.tensor(x, dtype=torch.float64), {"topo": topo.astype(np.float64)}).numpy()
+    exo = {"topo": {"steps": [{"model": 0, "combine_type": "layer", "data": topo}]}}
+    for precision, tol in (("fp32", 1e-4), ("fp16c", 1e-3), ("bf16x3", 1e-3)):
+        y = m.generate(x, exogenous_data=exo, precision=precision)
+        assert rel_err(y, ref) < tol and rms_err(y, ref) < tol, precision
+
+
+def test_baseline_config2_shapes_sup3rcc_chain(cuda):
+    """BASELINE configs[2]: sup3rcc wind, one (20, 20, 72, 6) chunk -> 24x temporal (5-D,
+    depth_to_time) -> 5x spatial with topography (4-D, Sup3rConcat).  Full-size run in the default
+    precision against the fp32 kernels (themselves oracle-checked at small shapes), and the
+    spatial step against the float64 oracle on two of its 1728 time slices."""
+    from sup3r_b200.models import MultiStepGan
+    f = 6
+    feats = ["u_10m", "v_10m", "u_100m", "v_100m", "t_2m", "rh_2m"]
+    t_hl = C.sup3rcc_temporal_d2t_generator(f, 24, 12, n_blocks=4)
+    s_hl = C.sup3rcc_spatial_generator(f, 5, 4, exo="topography")
+    m1 = make_model(t_hl, C.discriminator(3, "same", (8,)), (1, 20, 20, 72, f),
+                    meta={"lr_features": feats, "hr_out_features": feats, "s_enhance": 1,
+                          "t_enhance": 24})
+    m2 = make_model(s_hl, C.discriminator(2, "same", (8,)), (4, 20, 20, f),
+                    exo={"topography": 1}, seed=5,
+                    meta={"lr_features": feats, "hr_out_features": feats, "s_enhance": 5,
+                          "t_enhance": 1})
+    ms = MultiStepGan([m1, m2])
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((1, 20, 20, 72, f)).astype(np.float32)
+    topo = rng.standard_normal((100, 100, 1)).astype(np.float32)
+
+    def exo(n_t):
+        return {"topography": {"steps": [{"model": 1, "combine_type": "layer",
+                                          "data": np.repeat(topo[None], n_t, axis=0)}]}}
+
+    y = ms.generate(x, exogenous_data=exo(1728))
+    assert y.shape == (1728, 100, 100, f) and np.isfinite(y).all()
+    for mdl in (m1, m2):
+        mdl.precision = "fp32"
+    y32 = ms.generate(x, exogenous_data=exo(1728))
+    assert rel_err(y, y32) < 1e-3 and rms_err(y, y32) < 1e-3, (rel_err(y, y32), rms_err(y, y32))
+    # spatial step vs float64 oracle on two time slices of the temporal step's output
+    mid = m1.generate(x)                                     # (1, 20, 20, 1728, 6)
+    sl = np.ascontiguousarray(np.transpose(mid[0][:, :, [0, 1000]], (2, 0, 1, 3)))
+    e2 = {"topography": {"steps": [{"model": 0, "combine_type": "layer",
+                                    "data": np.repeat(topo[None], 2, axis=0)}]}}
+    got = m2.generate(sl, exogenous_data=e2)
+    ref = TorchRefNet(s_hl, m2.generator.get_weights(), torch.float64)(
+        torch.tensor(sl, dtype=torch.float64),
+        {"topography": np.repeat(topo[None], 2, axis=0).astype(np.float64)}).numpy()
+    assert rel_err(got, ref) < 1e-4
