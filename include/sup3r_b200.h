@@ -256,6 +256,34 @@ int s3_stats(const float* x, size_t n, float* out5, s3_stream stream);
  * out: [c][3] = (min, max, n_nan). */
 int s3_channel_check(const float* x, size_t nvox, int c, float* out, s3_stream stream);
 
+/* ---- chunk pipeline around the generator --------------------------------
+ * Output post-processing of one cropped hi-res chunk, IN PLACE on data (n_spatial, n_t, n_f):
+ * every (pair_u[k], pair_v[k]) channel pair is rotated by the grid angle (cos_sin: (n_spatial, 2) =
+ * cos / sin theta per hi-res grid point) and replaced by (windspeed, winddirection [deg]) --
+ * sup3r/preprocessing/derivers/utilities.py:204-255 invert_uv, writers/base.py:233-295 -- then
+ * every channel is limited to [lo, hi] (clip != 0; utilities/utilities.py:155-220 enforce_limits
+ * without nn_fill).  pair_u, pair_v, lo, hi are HOST arrays (read before the launch); data,
+ * cos_sin and counts are device pointers.  counts[2 f], counts[2 f + 1] (device, overwritten): points of channel f
+ * below lo / above hi before clipping (the reference's warning fractions; the nn_fill trigger). */
+int s3_output_transform(float* data, size_t n_spatial, int n_t, int n_f, const float* cos_sin,
+                        const int* pair_u, const int* pair_v, int n_pairs, const float* lo,
+                        const float* hi, int clip, unsigned long long* counts, s3_stream stream);
+/* Batch production (sup3r/preprocessing/batch_queues/base.py:32-87): hr (n, s1, s2, t, f) ->
+ * lr (n, s1/s, s2/s, t/te, f): (s x s) block mean, then temporal method 0 subsample, 1 average,
+ * 2 total, 3 max, 4 min (utilities/utilities.py:345-523).  4-D tensors: t = te = 1. */
+int s3_coarsen(const float* hr, float* lr, int n, int s1, int s2, int t, int f, int s_enhance,
+               int t_enhance, int method, s3_stream stream);
+/* scipy.ndimage.gaussian_filter(sigma, mode='nearest') over the (s1, s2) planes of x
+ * (n, s1, s2, tf) for the features whose bit is set in feature_mask (channel = index % f);
+ * weights: 2 radius + 1 normalised taps (host-computed); tmp: scratch of the size of x
+ * (sup3r/preprocessing/batch_queues/utilities.py:57-104 smooth_data). */
+int s3_gauss_smooth2d(const float* x, float* tmp, float* y, int n, int s1, int s2, int tf, int f,
+                      unsigned feature_mask, const float* weights, int radius, s3_stream stream);
+/* Sampler: out[b] = data[i0:i0+s1, j0:j0+s2, t0:t0+t, :] for origins (n, 3) int32 on the device
+ * (the device-resident stand-in for sup3r/preprocessing/samplers/base.py get_next). */
+int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int* origins, int n,
+                      int s1, int s2, int t, float* out, s3_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

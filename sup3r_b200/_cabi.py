@@ -86,6 +86,10 @@ SIGNATURES = {
     "s3_cast_f16": (_I, [_P, _P, _SZ, _P]),
     "s3_stats": (_I, [_P, _SZ, _P, _P]),
     "s3_channel_check": (_I, [_P, _SZ, _I, _P, _P]),
+    "s3_output_transform": (_I, [_P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "s3_coarsen": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "s3_gauss_smooth2d": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, C.c_uint32, _P, _I, _P]),
+    "s3_gather_samples": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

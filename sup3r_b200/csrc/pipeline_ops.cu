@@ -1,0 +1,221 @@
+// HBM-bound kernels of the chunk pipeline AROUND the generator:
+//   * s3_output_transform : u / v -> windspeed / winddirection on the rotated grid + physical limits
+//                           (sup3r/writers/base.py:233-346, preprocessing/derivers/utilities.py:204-255,
+//                           utilities/utilities.py:155-220), in place on the cropped chunk
+//   * s3_coarsen          : batch production, hi-res sample -> low-res input: (s x s) block mean then
+//                           temporal subsample / average / total / max / min
+//                           (preprocessing/batch_queues/base.py:32-87, utilities/utilities.py:345-523)
+//   * s3_gauss_smooth2d   : scipy.ndimage.gaussian_filter(sigma, mode='nearest', truncate=4) on the
+//                           (s1, s2) planes of selected features (batch_queues/utilities.py:57-104)
+//   * s3_gather_samples   : random (s1, s2, t) crops of a device-resident hi-res dataset
+// One thread per voxel / output element, channel-fastest coalesced accesses, grids sized to the
+// SM count.  All memory bound: bytes touched once.
+#include "common.cuh"
+
+namespace s3 {
+
+static inline unsigned pgrid(size_t n, int threads = 256) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+constexpr int kMaxF = 32;
+constexpr int kMaxPairs = 8;
+
+struct OutXform {
+  int f, n_pairs, clip;
+  int iu[kMaxPairs], iv[kMaxPairs];
+  float lo[kMaxF], hi[kMaxF];
+};
+
+// data (S1*S2, T, F) in place.  cs: (S1*S2, 2) = (cos theta, sin theta) of the grid rotation.
+// counts[2 f] / counts[2 f + 1]: voxels of feature f below lo / above hi BEFORE clipping (the
+// reference warns with these fractions and, for nn_fill, replaces exactly those points).
+__global__ void output_transform_kernel(float* __restrict__ data, const float* __restrict__ cs,
+                                        size_t n_sp, int T, OutXform p,
+                                        unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int sc[2 * kMaxF];
+  for (int i = threadIdx.x; i < 2 * p.f; i += blockDim.x) sc[i] = 0u;
+  __syncthreads();
+  const size_t total = n_sp * (size_t)T;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    float* row = data + idx * p.f;
+    const size_t sp = idx / T;
+    float v[kMaxF];
+    for (int i = 0; i < p.f; ++i) v[i] = row[i];
+    if (p.n_pairs) {
+      const float c = cs[2 * sp], s = cs[2 * sp + 1];
+      for (int k = 0; k < p.n_pairs; ++k) {
+        const float u = v[p.iu[k]], w = v[p.iv[k]];
+        const float ur = c * u - s * w, vr = s * u + c * w;
+        v[p.iu[k]] = hypotf(ur, vr);
+        float wd = atan2f(ur, vr) * 57.29577951308232f + 360.f;
+        v[p.iv[k]] = fmodf(wd, 360.f);
+      }
+    }
+    for (int i = 0; i < p.f; ++i) {
+      const float x = v[i];
+      if (x < p.lo[i]) atomicAdd(&sc[2 * i], 1u);
+      if (x > p.hi[i]) atomicAdd(&sc[2 * i + 1], 1u);
+      row[i] = p.clip ? fminf(fmaxf(x, p.lo[i]), p.hi[i]) : x;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.f; i += blockDim.x)
+    if (sc[i]) atomicAdd(&counts[i], (unsigned long long)sc[i]);
+}
+
+// method: 0 subsample, 1 average (nansum / t), 2 total (nansum), 3 max, 4 min
+__global__ void coarsen_kernel(const float* __restrict__ hr, float* __restrict__ lr, int B, int S1,
+                               int S2, int T, int F, int s, int t, int method, size_t total) {
+  const int L1 = S1 / s, L2 = S2 / s, LT = T / t;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int f = (int)(r % F); r /= F;
+    const int lt = (int)(r % LT); r /= LT;
+    const int l2 = (int)(r % L2); r /= L2;
+    const int l1 = (int)(r % L1); r /= L1;
+    const int b = (int)r;
+    const int nt = method == 0 ? 1 : t;
+    float acc = method == 3 ? -INFINITY : (method == 4 ? INFINITY : 0.f);
+    bool any_nan = false;
+    for (int dt = 0; dt < nt; ++dt) {
+      const int tt = lt * t + dt;
+      float sum = 0.f;   // the (s x s) block mean of this hi-res time step
+      for (int a = 0; a < s; ++a)
+        for (int c = 0; c < s; ++c)
+          sum += hr[((((size_t)b * S1 + l1 * s + a) * S2 + l2 * s + c) * T + tt) * F + f];
+      const float m = sum / (float)(s * s);
+      if (method == 0) acc = m;
+      else if (method == 1 || method == 2) { if (m == m) acc += m; }     // nansum
+      else if (method == 3) { any_nan |= m != m; acc = fmaxf(acc, m); }
+      else { any_nan |= m != m; acc = fminf(acc, m); }
+    }
+    if (method == 1) acc /= (float)t;
+    if ((method == 3 || method == 4) && any_nan) acc = NAN;             // np.max / np.min
+    lr[idx] = acc;
+  }
+}
+
+// one pass of the separable filter along axis `ax` (0: s1, 1: s2) of x (B, S1, S2, T, F), features
+// with fmask bit set only (others are copied); nearest-edge extension; w: 2 r + 1 weights
+__global__ void gauss1d_kernel(const float* __restrict__ x, float* __restrict__ y, int S1, int S2,
+                               int TF, int F, unsigned fmask, int ax, const float* __restrict__ w,
+                               int r, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t q = idx;
+    const int tf = (int)(q % TF); q /= TF;
+    const int j = (int)(q % S2); q /= S2;
+    const int i = (int)(q % S1); q /= S1;
+    const size_t b = q;
+    const int f = tf % F;
+    if (!((fmask >> f) & 1u)) { y[idx] = x[idx]; continue; }
+    const int n = ax == 0 ? S1 : S2, pos = ax == 0 ? i : j;
+    const size_t stride = ax == 0 ? (size_t)S2 * TF : (size_t)TF;
+    const size_t base = ((b * S1 + (ax == 0 ? 0 : i)) * S2 + (ax == 0 ? j : 0)) * TF + tf;
+    double acc = 0.0;   // scipy's correlate1d accumulates in double
+    for (int k = -r; k <= r; ++k) {
+      int p = pos + k;
+      p = p < 0 ? 0 : (p >= n ? n - 1 : p);
+      acc += (double)w[k + r] * (double)x[base + (size_t)p * stride];
+    }
+    y[idx] = (float)acc;
+  }
+}
+
+// data (S1, S2, T, F) -> out (B, s1, s2, t, F); origins (B, 3) int32 = (i0, j0, t0)
+__global__ void gather_samples_kernel(const float* __restrict__ data, float* __restrict__ out,
+                                      const int* __restrict__ org, int S2, int T, int F, int s1,
+                                      int s2, int t, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t q = idx;
+    const int f = (int)(q % F); q /= F;
+    const int k = (int)(q % t); q /= t;
+    const int j = (int)(q % s2); q /= s2;
+    const int i = (int)(q % s1); q /= s1;
+    const int b = (int)q;
+    const int i0 = org[3 * b], j0 = org[3 * b + 1], t0 = org[3 * b + 2];
+    out[idx] = data[(((size_t)(i0 + i) * S2 + (j0 + j)) * T + (t0 + k)) * F + f];
+  }
+}
+
+}  // namespace s3
+
+using namespace s3;
+
+extern "C" int s3_output_transform(float* data, size_t n_spatial, int n_t, int n_f,
+                                   const float* cos_sin, const int* pair_u, const int* pair_v,
+                                   int n_pairs, const float* lo, const float* hi, int clip,
+                                   unsigned long long* counts, s3_stream stream) {
+  S3_REQUIRE(data && lo && hi && counts, "s3_output_transform: null argument");
+  S3_REQUIRE(n_f >= 1 && n_f <= kMaxF, "s3_output_transform: 1 <= features <= %d, got %d", kMaxF, n_f);
+  S3_REQUIRE(n_pairs >= 0 && n_pairs <= kMaxPairs, "s3_output_transform: at most %d u/v pairs", kMaxPairs);
+  S3_REQUIRE(n_pairs == 0 || (cos_sin && pair_u && pair_v), "s3_output_transform: u/v pairs need cos_sin");
+  OutXform p;
+  p.f = n_f; p.n_pairs = n_pairs; p.clip = clip;
+  for (int k = 0; k < n_pairs; ++k) {
+    S3_REQUIRE(pair_u[k] >= 0 && pair_u[k] < n_f && pair_v[k] >= 0 && pair_v[k] < n_f &&
+                   pair_u[k] != pair_v[k], "s3_output_transform: bad u/v pair %d", k);
+    p.iu[k] = pair_u[k]; p.iv[k] = pair_v[k];
+  }
+  for (int i = 0; i < n_f; ++i) { p.lo[i] = lo[i]; p.hi[i] = hi[i]; }
+  S3_CUDA(cudaMemsetAsync(counts, 0, 2 * n_f * sizeof(unsigned long long), as_stream(stream)));
+  const size_t total = n_spatial * (size_t)n_t;
+  if (total)
+    output_transform_kernel<<<pgrid(total), 256, 0, as_stream(stream)>>>(data, cos_sin, n_spatial,
+                                                                          n_t, p, counts);
+  S3_LAUNCH_CHECK("output_transform");
+  return S3_OK;
+}
+
+extern "C" int s3_coarsen(const float* hr, float* lr, int n, int s1, int s2, int t, int f,
+                          int s_enhance, int t_enhance, int method, s3_stream stream) {
+  S3_REQUIRE(hr && lr, "s3_coarsen: null argument");
+  S3_REQUIRE(s_enhance >= 1 && t_enhance >= 1 && s1 % s_enhance == 0 && s2 % s_enhance == 0 &&
+                 t % t_enhance == 0,
+             "s3_coarsen: extents (%d, %d, %d) must be multiples of the enhancements (%d, %d)", s1,
+             s2, t, s_enhance, t_enhance);
+  S3_REQUIRE(method >= 0 && method <= 4, "s3_coarsen: method must be 0..4");
+  const size_t total = (size_t)n * (s1 / s_enhance) * (s2 / s_enhance) * (t / t_enhance) * f;
+  if (total)
+    coarsen_kernel<<<pgrid(total), 256, 0, as_stream(stream)>>>(hr, lr, n, s1, s2, t, f, s_enhance,
+                                                                 t_enhance, method, total);
+  S3_LAUNCH_CHECK("coarsen");
+  return S3_OK;
+}
+
+extern "C" int s3_gauss_smooth2d(const float* x, float* tmp, float* y, int n, int s1, int s2,
+                                 int tf, int f, unsigned feature_mask, const float* weights,
+                                 int radius, s3_stream stream) {
+  S3_REQUIRE(x && tmp && y && weights && radius >= 0, "s3_gauss_smooth2d: bad arguments");
+  S3_REQUIRE(f >= 1 && f <= 32 && tf % f == 0, "s3_gauss_smooth2d: 1 <= features <= 32");
+  const size_t total = (size_t)n * s1 * s2 * tf;
+  if (total) {
+    // scipy filters axis 0 first, storing the intermediate in the output dtype (float32)
+    gauss1d_kernel<<<pgrid(total), 256, 0, as_stream(stream)>>>(x, tmp, s1, s2, tf, f, feature_mask,
+                                                                 0, weights, radius, total);
+    gauss1d_kernel<<<pgrid(total), 256, 0, as_stream(stream)>>>(tmp, y, s1, s2, tf, f, feature_mask,
+                                                                 1, weights, radius, total);
+  }
+  S3_LAUNCH_CHECK("gauss_smooth2d");
+  return S3_OK;
+}
+
+extern "C" int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int* origins,
+                                 int n, int s1, int s2, int t, float* out, s3_stream stream) {
+  S3_REQUIRE(data && origins && out, "s3_gather_samples: null argument");
+  S3_REQUIRE(s1 <= S1 && s2 <= S2 && t <= T, "s3_gather_samples: sample larger than the data");
+  const size_t total = (size_t)n * s1 * s2 * t * F;
+  if (total)
+    gather_samples_kernel<<<pgrid(total), 256, 0, as_stream(stream)>>>(data, out, origins, S2, T, F,
+                                                                        s1, s2, t, total);
+  S3_LAUNCH_CHECK("gather_samples");
+  return S3_OK;
+}

@@ -551,3 +551,78 @@ def channel_check(x):
     _cabi.call("s3_channel_check", _p(x), x.numel() // c, c, _p(out), _s())
     _count(2)
     return out
+
+
+# ------------------------------------------------------------------ chunk pipeline (8(f)2, 8(f)4)
+def output_transform(data, cos_sin, pairs, lo, hi, clip=True):
+    """In-place u/v -> (windspeed, winddirection) + limits on a device chunk (s1, s2, t, f).
+    ``pairs``: [(u_idx, v_idx)]; ``lo`` / ``hi``: per-feature limits (python floats).  Returns the
+    device tensor (f, 2) int64 of (below, above) counts taken before clipping."""
+    ensure_device(data)
+    if data.dtype != torch.float32 or not data.is_contiguous():
+        raise RuntimeError("output_transform works in place on a contiguous float32 tensor")
+    s1, s2, t, f = data.shape
+    counts = torch.empty((f, 2), device=data.device, dtype=torch.int64)
+    pu = (C.c_int * max(len(pairs), 1))(*[p[0] for p in pairs])
+    pv = (C.c_int * max(len(pairs), 1))(*[p[1] for p in pairs])
+    flo = (C.c_float * f)(*[float(v) for v in lo])
+    fhi = (C.c_float * f)(*[float(v) for v in hi])
+    _cabi.call("s3_output_transform", _p(data), s1 * s2, t, f, _p(cos_sin), pu, pv, len(pairs),
+               flo, fhi, int(bool(clip)), _p(counts), _s())
+    _count()
+    return counts
+
+
+COARSEN_METHODS = {"subsample": 0, "average": 1, "total": 2, "max": 3, "min": 4}
+
+
+def coarsen(hr, s_enhance, t_enhance=1, method="subsample"):
+    """(n, s1, s2, [t,] f) hi-res samples -> low-res (block mean + temporal method)."""
+    hr = _f32(hr)
+    ensure_device(hr)
+    if method not in COARSEN_METHODS:
+        raise ValueError(f"Did not recognize temporal coarsening method \"{method}\"")
+    five = hr.dim() == 5
+    n, s1, s2 = hr.shape[:3]
+    t = hr.shape[3] if five else 1
+    te = t_enhance if five else 1
+    f = hr.shape[-1]
+    shp = (n, s1 // s_enhance, s2 // s_enhance) + ((t // te,) if five else ()) + (f,)
+    lr = torch.empty(shp, device=hr.device, dtype=torch.float32)
+    _cabi.call("s3_coarsen", _p(hr), _p(lr), n, s1, s2, t, f, int(s_enhance), int(te),
+               COARSEN_METHODS[method], _s())
+    _count()
+    return lr
+
+
+def gauss_smooth2d(x, sigma, feature_mask, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(sigma, mode='nearest') over (s1, s2) of the masked features
+    of x (n, s1, s2, [t,] f)."""
+    import numpy as np
+    x = _f32(x)
+    ensure_device(x)
+    radius = int(truncate * float(sigma) + 0.5)
+    k = np.arange(-radius, radius + 1)
+    w = np.exp(-0.5 / (float(sigma) ** 2) * k ** 2)
+    w = (w / w.sum()).astype(np.float32)
+    wd = torch.from_numpy(w).to(x.device)
+    n, s1, s2, f = x.shape[0], x.shape[1], x.shape[2], x.shape[-1]
+    tf = x.numel() // (n * s1 * s2)
+    tmp, y = torch.empty_like(x), torch.empty_like(x)
+    _cabi.call("s3_gauss_smooth2d", _p(x), _p(tmp), _p(y), n, s1, s2, tf, f, int(feature_mask),
+               _p(wd), radius, _s())
+    _count(2)
+    return y
+
+
+def gather_samples(data, origins, sample_shape):
+    """data (S1, S2, T, F) on the device, origins (n, 3) int32 device tensor -> (n, s1, s2, t, F)"""
+    ensure_device(data)
+    S1, S2, T, F = data.shape
+    n = origins.shape[0]
+    s1, s2, t = sample_shape
+    out = torch.empty((n, s1, s2, t, F), device=data.device, dtype=torch.float32)
+    _cabi.call("s3_gather_samples", _p(data), S1, S2, T, F, _p(origins), n, s1, s2, t, _p(out),
+               _s())
+    _count()
+    return out

@@ -207,7 +207,8 @@ class ForwardPass:
         replacement for the reference's ``SpawnProcessPool`` (forward_pass.py:503-580)."""
         fwp = cls(strategy, node_index=node_index)
         model = fwp.model
-        if hasattr(model, "models") or not model.is_5d or strategy.exo_data is not None:
+        if (hasattr(model, "models") or not model.is_5d or strategy.exo_data is not None
+                or strategy.postprocess):
             # 4-D models, exogenous data, multi-step chains: one chunk per generator call,
             # software-pipelined on the device (see _run_streamed)
             return cls._run_streamed(strategy, node_index, fwp)
@@ -334,6 +335,11 @@ class ForwardPass:
             cls._check_enhancement(hi_res, data_chunk, model.s_enhance, model.t_enhance, i_lr_s,
                                    i_lr_t)
             out = hi_res[0][chunk.hr_crop_slice].contiguous()
+            if strategy.postprocess:
+                from .postprocess import transform_output
+                out, chunk.features = transform_output(
+                    out, list(model.hr_out_features), chunk.hr_lat_lon,
+                    invert_uv=bool(strategy.invert_uv), nn_fill=bool(strategy.nn_fill))
             chk = ops.channel_check(out)
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(dev))
@@ -394,7 +400,8 @@ class ForwardPass:
         from ..utilities import safe_cast
         with open(chunk.out_file + ".meta.json", "w") as f:
             json.dump({"meta": meta, "hr_times": np.asarray(chunk.hr_times).tolist(),
-                       "index": chunk.index}, f, default=safe_cast)
+                       "index": chunk.index, "features": getattr(chunk, "features", None)}, f,
+                      default=safe_cast)
 
     @classmethod
     def run_chunk(cls, chunk: ForwardPassChunk, model_kwargs, model_class, allowed_const,

@@ -154,6 +154,10 @@ class ForwardPassStrategy:
     exo_data: Optional[dict] = None
     pad_mode: str = "reflect"
     output_dtype: str = "float32"   # "float16": results are cast on the device and leave as fp16
+    # apply the writer-side transforms (sup3r/writers/base.py:297-346: u/v -> ws/wd when
+    # ``invert_uv``, physical limits with ``nn_fill`` or clipping) on the device before a chunk
+    # leaves the GPU (pipeline/postprocess.py)
+    postprocess: bool = False
 
     def __post_init__(self):
         self.bias_correct_kwargs = self.bias_correct_kwargs or {}

@@ -168,3 +168,38 @@ def test_baseline_config2_shapes_sup3rcc_chain(cuda):
         torch.tensor(sl, dtype=torch.float64),
         {"topography": np.repeat(topo[None], 2, axis=0).astype(np.float64)}).numpy()
     assert rel_err(got, ref) < 1e-4
+
+
+def test_forward_pass_postprocess_on_device(cuda):
+    """strategy.postprocess: writers/base.py:297-346 (u/v -> ws/wd, limits) applied on the GPU
+    before the chunk leaves; equals the numpy restatement applied to the raw chunk output."""
+    import os
+    import json
+    import tempfile
+    import warnings
+    from oracle import postprocess_ref as P
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m, _ = _spatial_model()
+    m.meta["lr_features"] = m.meta["hr_out_features"] = ["u_100m", "v_100m"]
+    data = (np.random.default_rng(5).standard_normal((12, 12, 4, 2)) * 3).astype(np.float32)
+    raw = ForwardPass.run(ForwardPassStrategy(
+        model=m, input_handler=ArrayInputHandler(data, ["u_100m", "v_100m"]),
+        fwp_chunk_shape=(6, 6, 4), spatial_pad=1, pass_workers=2), 0)
+    with tempfile.TemporaryDirectory() as td, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        strat = ForwardPassStrategy(
+            model=m, input_handler=ArrayInputHandler(data, ["u_100m", "v_100m"]),
+            fwp_chunk_shape=(6, 6, 4), spatial_pad=1, pass_workers=2, postprocess=True,
+            invert_uv=True, nn_fill=False, out_pattern=os.path.join(td, "c_{file_id}.npy"))
+        ForwardPass.run(strat, 0)
+        for i in range(strat.n_chunks):
+            got = np.load(strat.out_files[i])
+            chunk = strat.init_chunk(i)
+            ws, names = P.transform_output(raw[i], ["u_100m", "v_100m"], chunk.hr_lat_lon,
+                                           invert=True)
+            assert names == ["windspeed_100m", "winddirection_100m"]
+            meta = json.load(open(strat.out_files[i] + ".meta.json"))
+            assert meta["features"] == names
+            assert np.abs(got[..., 0] - ws[..., 0]).max() < 1e-4
+            dwd = np.abs(got[..., 1] - ws[..., 1])
+            assert np.minimum(dwd, 360 - dwd).max() < 2e-2
