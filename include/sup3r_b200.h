@@ -155,6 +155,20 @@ size_t s3_conv_wgrad_scratch_bytes(const s3_conv_desc* d);
 int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, float* dw,
                       float* dbias, void* scratch, s3_stream stream);
 
+/* Weight gradient on tcgen05 (tape.gradient w.r.t. the conv kernels, abstract.py:1190-1238) of
+ * the 3x3x3 stride-1 reflect-pad-1 convolutions with 64 output channels:
+ *   dw[dz][dy][dx][ci][co] = scale * sum_v x_pad[v + (dz,dy,dx)][ci] * g[v][co]
+ * x_hi: fp16 padded input (n, z+2, y+2, x+2, 64) with its REFLECT halo (s3_pack_act_pad16_ex);
+ * g_hi: fp16 output gradient padded with g_halo (1 or 2) ZERO voxels per side,
+ * (n, z+2h, y+2h, x+2h, 64) -- the tensor the input-gradient convolution consumes has h = 2.
+ * Voxels are the GEMM's K dimension (MN-major SWIZZLE_128B operands straight from the TMA boxes),
+ * split over CTAs; ws (>= s3_conv_wgrad_umma_ws_bytes) holds the partial sums, reduced in a fixed
+ * order.  dw: (3, 3, 3, cin, 64) f32, overwritten; cin <= 64 (channels beyond cin are padding). */
+size_t s3_conv_wgrad_umma_ws_bytes(int n, int z, int y, int x);
+int s3_conv_wgrad_umma(const void* x_hi, const void* g_hi, int g_halo, int n, int z, int y, int x,
+                       int cin, float scale, float* dw, void* ws, size_t ws_bytes,
+                       s3_stream stream);
+
 /* ---- tcgen05 implicit-GEMM convolution (cin == 64, 3x3[x3], stride 1, reflect-1) ---------
  * x_hi/x_lo: padded+mirrored 16-bit activations (lo NULL = single pass; bf16 lo = the 3-pass
  * split-precision product hi*hi + lo*hi + hi*lo; S3_FMT_FP16C lo = e4m3 correction rows, one

@@ -58,6 +58,8 @@ SIGNATURES = {
     "s3_conv_dgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "s3_conv_wgrad_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "s3_conv_wgrad_f32": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "s3_conv_wgrad_umma_ws_bytes": (_SZ, [_I, _I, _I, _I]),
+    "s3_conv_wgrad_umma": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _SZ, _P]),
     "s3_conv_fwd_umma": (_I, [C.POINTER(ConvDesc)] + [_P] * 13 + [C.POINTER(UmmaTuning), _P]),
     "s3_umma_npad": (_I, [_I]),
     "s3_umma_weight_layout": (_I, [_I, _I, _I]),

@@ -5,6 +5,7 @@
 from __future__ import annotations
 
 import dataclasses
+import os
 
 import torch
 
@@ -85,7 +86,12 @@ class ConvUmmaFn(torch.autograd.Function):
                                     acc_scale=acc)
         ctx.spec, ctx.cache, ctx.x_shape = spec, cache, tuple(x.shape)
         ctx.has_bias = b is not None
-        ctx.save_for_backward(x, w, y if spec.act != S3_ACT_NONE else None)
+        # weight gradient on tcgen05: 3-D, 64 output channels -> keep the fp16 padded input (the
+        # forward's own operand) instead of the f32 tensor
+        ctx.wgrad_umma = (nd == 3 and spec.cout == 64 and min(dims) >= 2
+                          and os.environ.get("SUP3R_B200_WGRAD_FP32", "0") != "1")
+        ctx.save_for_backward(x_hi if ctx.wgrad_umma else x, w,
+                              y if spec.act != S3_ACT_NONE else None)
         return y
 
     @staticmethod
@@ -97,10 +103,12 @@ class ConvUmmaFn(torch.autograd.Function):
             dy = ops.act_bwd(y, dy, spec.act, spec.alpha)
         lin = dataclasses.replace(spec, act=S3_ACT_NONE)
         dx = dw = db = None
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        nd = spec.ndim
+        want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        if want_w and not ctx.wgrad_umma:
             dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
+        g_hi, g_halo = None, 0
         if ctx.needs_input_grad[0]:
-            nd = spec.ndim
             pads = [(0, 0)] + [(1, 1)] * nd + [(0, 0)]
             pshape = tuple(s + p[0] + p[1] for s, p in zip(ctx.x_shape, pads))
             if spec.cout == 64 and spec.cin <= 256 and spec.cin % 16 == 0:
@@ -113,6 +121,7 @@ class ConvUmmaFn(torch.autograd.Function):
                 n, dims, _, _ = ops.dims3(dyz.shape)
                 g_hi, g_c = ops.pack_act_pad16(dyz, split=True, fmt=ops.S3_FMT_FP16C,
                                                halo=S3_PAD_ZERO)
+                g_halo = 2
                 sp = dataclasses.replace(lin, cin=64, cout=spec.cin)
                 dxp, _, _ = ops.conv_fwd_umma(g_hi, g_c, w_hi, w_c, None, sp, n, dims,
                                               fmt=ops.S3_FMT_FP16C, acc_scale=acc)
@@ -121,6 +130,17 @@ class ConvUmmaFn(torch.autograd.Function):
                                             pad_mode=S3_PAD_ZERO)
                 dxp = ops.conv_dgrad(dy, w, valid, pshape)
             dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
+        if want_w and ctx.wgrad_umma:
+            # dW = sum_v x_pad[v + tap] (x) dy[v] on tcgen05 (voxels = the GEMM's K dimension);
+            # the zero-halo fp16 gradient tensor of the input-gradient convolution is reused
+            n, dims, _, _ = ops.dims3(dy.shape)
+            if g_hi is None or spec.cin > 64:
+                g_hi, _ = ops.pack_act_pad16(dy, split=False, fmt=ops.S3_FMT_FP16, halo=S3_PAD_ZERO)
+                g_halo = 1
+            dw = ops.conv_wgrad_umma(x, g_hi, g_halo, n, dims, min(spec.cin, 64))
+            if tuple(dw.shape) != tuple(w.shape):
+                dw = dw.reshape(w.shape)
+            db = ops.conv_bias_grad(dy, spec.cout) if ctx.has_bias else None
         return dx, dw, db, None, None
 
 

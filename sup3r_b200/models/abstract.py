@@ -594,16 +594,36 @@ class AbstractSingleModel(TensorboardMixIn):
     def get_single_grad(self, low_res, hi_res_true, training_weights, device_name=None,
                         **calc_loss_kwargs):
         """Gradients of the loss w.r.t. ``training_weights`` (abstract.py:1190-1238): the tape
-        is torch.autograd over Functions whose forward / backward are all our kernels."""
+        is torch.autograd over Functions whose forward / backward are all our kernels.
+
+        The backward pass runs on the loss times a power of two (``grad_loss_scale``) and the
+        gradients are divided by it afterwards: the losses are means over ~1e6 hi-res values, so
+        the raw activation gradients are ~1e-6 -- below the normal range of the fp16 operands the
+        tensor-core input-gradient kernels use.  Exact for the fp32 kernels (power of two)."""
         with torch.enable_grad():
-            loss, loss_details, _, _ = self._get_hr_exo_and_loss(low_res, hi_res_true,
-                                                                 **calc_loss_kwargs)
+            loss, loss_details, hi_res_gen, _ = self._get_hr_exo_and_loss(
+                low_res, hi_res_true, **calc_loss_kwargs)
             tensors = [w.value for w in training_weights]
-            grad = torch.autograd.grad(loss, tensors, allow_unused=True)
+            scale = self.grad_loss_scale(hi_res_gen)
+            if scale != 1.0:
+                from .base import ScaleFnScalar
+                grad = torch.autograd.grad(ScaleFnScalar.apply(loss, scale), tensors,
+                                           allow_unused=True)
+                inv = 1.0 / scale
+                grad = [None if g is None else g.mul_(inv) for g in grad]
+            else:
+                grad = torch.autograd.grad(loss, tensors, allow_unused=True)
         grad = [g if g is not None else torch.zeros_like(t) for g, t in zip(grad, tensors)]
         loss_details = {k: (v.detach() if isinstance(v, torch.Tensor) else v)
                         for k, v in loss_details.items()}
         return grad, loss_details
+
+    def grad_loss_scale(self, hi_res_gen):
+        """Power-of-two loss scale of the backward pass: the number of generated hi-res values
+        (mean-reduced losses have gradients of order 1 / that), 1 in ``fp32`` mode."""
+        if self.precision == "fp32":
+            return 1.0
+        return float(2.0 ** int(np.floor(np.log2(max(hi_res_gen.numel(), 1)))))
 
     def calc_loss(self, hi_res_true, hi_res_gen, weight_gen_advers=0.001, train_gen=True,
                   train_disc=False, compute_disc=False):  # pragma: no cover - abstract

@@ -209,6 +209,44 @@ def conv_wgrad(x, dy, spec: ConvSpec, w_shape, want_bias=True):
     return dw, db
 
 
+def conv_bias_grad(dy, cout):
+    """db[co] = sum over voxels of dy (the bias half of s3_conv_wgrad_f32)."""
+    dy = _f32(dy)
+    ensure_device(dy)
+    n, dims, c, ndim = dims3(dy.shape)
+    db = torch.empty(cout, device=dy.device, dtype=torch.float32)
+    spec = ConvSpec(ndim, cout, cout, (1,) * 3)
+    _cabi.call("s3_conv_wgrad_f32", C.byref(spec.desc(n, dims)), _p(dy), _p(dy), None, _p(db), None,
+               _s())
+    _count()
+    return db
+
+
+_wgrad_ws = {}
+
+
+def conv_wgrad_umma(x_hi, g_hi, g_halo, n, dims, cin, scale=1.0):
+    """Weight gradient (3, 3, 3, cin, 64) of a 3x3x3 stride-1 reflect-pad-1 convolution on tcgen05.
+    ``x_hi``: fp16 padded (REFLECT halo) input of the forward pass, ``g_hi``: fp16 zero-halo
+    padded output gradient with ``g_halo`` halo voxels per side (1, or 2 for the tensor the
+    input-gradient kernel consumes); ``dims``: interior (z, y, x)."""
+    ensure_device(x_hi)
+    if x_hi.dtype != torch.float16 or g_hi.dtype != torch.float16:
+        raise RuntimeError("conv_wgrad_umma needs fp16 padded operands")
+    z, y, x = dims
+    lib = _cabi.load()
+    need = lib.s3_conv_wgrad_umma_ws_bytes(n, z, y, x)
+    key = str(x_hi.device)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() * 4 < need:
+        ws = _wgrad_ws[key] = torch.empty((need + 3) // 4, device=x_hi.device, dtype=torch.float32)
+    dw = torch.empty((3, 3, 3, cin, 64), device=x_hi.device, dtype=torch.float32)
+    _cabi.call("s3_conv_wgrad_umma", _p(x_hi), _p(g_hi), int(g_halo), n, z, y, x, int(cin),
+               float(scale), _p(dw), _p(ws), ws.numel() * 4, _s())
+    _count(2)
+    return dw
+
+
 def umma_npad(cout):
     return _cabi.load().s3_umma_npad(cout)
 

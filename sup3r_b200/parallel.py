@@ -43,6 +43,37 @@ def init_from_env(backend=None):
     dist.init_process_group(backend=backend)
 
 
+def bind_to_gpu_numa(device_index=None):
+    """Restrict this thread to the CPUs NVML names as local to the GPU, so that the pinned host
+    buffers it allocates afterwards (first touch) live on the GPU's NUMA node: with one rank per
+    GPU the device -> host result streams then do not cross the socket interconnect.  Returns the
+    CPU set, or None when NVML / affinity is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        pynvml.nvmlInit()
+        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:   # pragma: no cover - best effort
+        return None
+
+
 _arenas = {}
 
 

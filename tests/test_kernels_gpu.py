@@ -692,3 +692,39 @@ def test_umma_conv_fp16c_2d_and_head(cuda):
                                 acc_scale=sc)
     assert y.shape == ref.shape
     assert np.abs(y.cpu().numpy() - ref).max() < np.abs(ref).max() * 1e-4
+
+
+# ------------------------------------------------------------------ tcgen05 weight gradient
+@pytest.mark.parametrize("n,dims,cin,halo", [(1, (4, 16, 8), 64, 1), (2, (5, 20, 13), 64, 2),
+                                              (1, (2, 7, 30), 6, 1), (3, (9, 33, 17), 64, 2)])
+def test_umma_wgrad_matches_float64(cuda, n, dims, cin, halo):
+    """dW = sum_v x_pad[v + tap] (x) dy[v] with voxels as the K dimension of MN-major tcgen05
+    operands (conv_wgrad_umma.cu) against float64 autograd of the same fp16-rounded operands
+    (tight) and of the unrounded ones (the 2e-3 gradient bound)."""
+    import torch.nn.functional as F
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(n * 100 + cin)
+    x = rng.standard_normal((n, *dims, cin)).astype(np.float32)
+    dy = (rng.standard_normal((n, *dims, 64)) * 0.5).astype(np.float32)
+    xd = torch.as_tensor(x, device=cuda)
+    x_hi, _ = ops.pack_act_pad16(torch.nn.functional.pad(xd, (0, 64 - cin)), split=False,
+                                 fmt=ops.S3_FMT_FP16)
+    gd = torch.as_tensor(dy, device=cuda)
+    if halo == 2:
+        gd = ops.pad_fwd(gd, [(0, 0), (1, 1), (1, 1), (1, 1), (0, 0)], 0)
+    g_hi, _ = ops.pack_act_pad16(gd, split=False, fmt=ops.S3_FMT_FP16, halo=0)
+    got = ops.conv_wgrad_umma(x_hi, g_hi, halo, n, dims, cin).cpu().numpy().astype(np.float64)
+    assert got.shape == (3, 3, 3, cin, 64)
+
+    def ref(xa, ga):
+        xc = torch.tensor(xa, dtype=torch.float64).permute(0, 4, 1, 2, 3)
+        xp = F.pad(xc, (1, 1, 1, 1, 1, 1), mode="reflect")
+        w = torch.zeros((64, cin, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+        y = F.conv3d(xp, w)
+        (dw,) = torch.autograd.grad(y, w, torch.tensor(ga, dtype=torch.float64).permute(0, 4, 1, 2, 3))
+        return dw.permute(2, 3, 4, 1, 0).numpy()
+
+    r16 = ref(x.astype(np.float16).astype(np.float64), dy.astype(np.float16).astype(np.float64))
+    assert np.abs(got - r16).max() < 2e-5 * np.abs(r16).max()
+    rex = ref(x, dy)
+    assert np.abs(got - rex).max() < 2e-3 * np.abs(rex).max()
