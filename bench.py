@@ -146,9 +146,11 @@ def train_step_block(dev, peaks, steps=3):
             "ms_per_step": ms, "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
             "frac_of_bf16_peak": flops / (ms / 1e3) / 1e12 / peak,
             "algorithmic_flops_per_step": flops,
-            "kernels": "generator forward + input gradients (fp16c operands) + weight gradients "
-                       "(fp16, voxels as the K dimension of MN-major operands): tcgen05; the "
-                       "discriminator (strided / > 64-channel convolutions): fp32 CUDA-core kernels"}
+            "kernels": "generator AND discriminator convolutions: forward + input gradients (fp16c "
+                       "operands, 64-channel groups summed through the f32 residual input, stride 2 "
+                       "= sampled stride-1 convolution) + weight gradients (fp16, voxels as the K "
+                       "dimension of MN-major operands) on tcgen05; dense layers, losses, Adam, "
+                       "layers with extents < 2: fp32 CUDA-core kernels"}
 
 
 class ClockSampler:

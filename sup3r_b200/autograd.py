@@ -17,11 +17,21 @@ class ConvFn(torch.autograd.Function):
     """conv (+ implicit zero / reflect / symmetric pad) + bias + activation."""
 
     @staticmethod
-    def forward(ctx, x, w, b, spec):
+    def forward(ctx, x, w, b, spec, tc_wgrad=False):
         y = ops.conv_fwd(x, w, b, spec)
         ctx.spec = spec
         ctx.x_shape = tuple(x.shape)
         ctx.has_bias = b is not None
+        # narrow 3x3x3 stride-1 pad-1 layers (e.g. the hi-res output convolution) keep the fp32
+        # forward / input-gradient kernels, but their weight gradient -- a reduction over every
+        # voxel -- runs on tcgen05 with the channels zero-padded to 64
+        from ._cabi import S3_PAD_REFLECT
+        ctx.tc_wgrad = bool(
+            tc_wgrad and spec.ndim == 3 and tuple(spec.ksize) == (3, 3, 3)
+            and tuple(spec.stride) == (1, 1, 1) and tuple(spec.pad_lo) == (1, 1, 1)
+            and tuple(spec.pad_hi) == (1, 1, 1) and spec.pad_mode in (S3_PAD_REFLECT, S3_PAD_ZERO)
+            and spec.cin <= 64 and spec.cout <= 64 and spec.d2s == 1 and spec.d2t == 1
+            and min(x.shape[1:-1]) >= 2 and x.numel() // x.shape[-1] >= 4096)
         ctx.save_for_backward(x, w, y if spec.act != S3_ACT_NONE else None)
         return y
 
@@ -35,7 +45,21 @@ class ConvFn(torch.autograd.Function):
         lin = dataclasses.replace(spec, act=S3_ACT_NONE)
         dx = dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
+            if ctx.tc_wgrad:
+                n, dims, cin, _ = ops.dims3(x.shape)
+                pad64 = torch.nn.functional.pad
+                x_hi, _ = ops.pack_act_pad16(pad64(x, (0, 64 - cin)) if cin < 64 else x,
+                                             split=False, fmt=ops.S3_FMT_FP16, halo=spec.pad_mode)
+                g_hi, _ = ops.pack_act_pad16(
+                    pad64(dy, (0, 64 - spec.cout)) if spec.cout < 64 else dy, split=False,
+                    fmt=ops.S3_FMT_FP16, halo=S3_PAD_ZERO)
+                dw = ops.conv_wgrad_umma(x_hi, g_hi, 1, n, dims, cin)
+                if spec.cout < 64:
+                    dw = dw[..., :spec.cout].contiguous()
+                dw = dw.reshape(w.shape)
+                db = ops.conv_bias_grad(dy, spec.cout) if ctx.has_bias else None
+            else:
+                dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
         if ctx.needs_input_grad[0]:
             if spec.pad_mode == S3_PAD_ZERO:
                 dx = ops.conv_dgrad(dy, w, lin, ctx.x_shape)
@@ -50,98 +74,191 @@ class ConvFn(torch.autograd.Function):
                                             pad_mode=S3_PAD_ZERO)
                 dxp = ops.conv_dgrad(dy, w, valid, pshape)
                 dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class ConvUmmaFn(torch.autograd.Function):
-    """3x3[x3] stride-1 reflect-pad-1 convolution with cin <= 64 on the tcgen05 kernels in the
-    fp16c operand format (fp16 + e4m3 correction rows, ~2^-15 relative: gradients stay inside
-    the 2e-3 bound of the float64 autograd test) -- forward AND input gradient.  ``w_eff`` is
-    the effective correlation kernel ``(*k, cin, cout)``; ``cache`` a dict owned by the layer
-    for the packed weights (keyed by the weight tensor's version).
-    Stands in for the generator convolutions under ``tf.GradientTape``
-    (sup3r/models/abstract.py:1131-1173, 1230-1238)."""
+    """3x3[x3] stride-1 pad-1 convolution on the tcgen05 kernels -- forward, input gradient AND
+    weight gradient.  ``halo`` selects the padding the fp16 operand tensors carry: REFLECT (the
+    generator's FlexiblePadding -> Conv -> Cropping runs) or ZERO (keras ``padding='same'``, the
+    discriminator).  Channels: cin <= 64 (zero-padded to 64) or a multiple of 64 -- the kernels
+    contract 64 input channels per launch, wider inputs are summed over 64-channel groups through
+    the f32 residual input; cout <= 256 per launch, wider outputs in slices.  Forward / input
+    gradient use the fp16c operand format (fp16 + e4m3 correction rows, ~2^-15 relative); the
+    weight gradient fp16 operands with the voxels as the GEMM's K dimension (its rounding errors
+    average out over K).  ``w`` is the effective correlation kernel ``(*k, cin, cout)``;
+    ``cache`` a dict owned by the layer for the packed weights (keyed by the weight version).
+    Stands in for the convolutions under ``tf.GradientTape``
+    (sup3r/models/abstract.py:1131-1173, 1230-1238; base.py:283-313)."""
 
     @staticmethod
-    def _packed(cache, key, w, ver, nd):
+    def _pack_w(cache, key, ver, make, nd):
         hit = cache.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():
-                wk = w.detach()
+                wk = make()
                 if wk.shape[-2] < 64:     # zero rows for the padded input channels
                     wk = torch.nn.functional.pad(wk, (0, 0, 0, 64 - wk.shape[-2]))
-                hit = (ver, *ops.pack_weights_umma(wk, ndim=nd, fmt=ops.S3_FMT_FP16C))
+                hit = (ver, *ops.pack_weights_umma(wk.contiguous(), ndim=nd,
+                                                   fmt=ops.S3_FMT_FP16C))
             cache[key] = hit
         return hit[1:]
 
     @staticmethod
-    def forward(ctx, x, w, b, spec, cache):
+    def _kernel_spec(spec, nd, **kw):
+        """The tcgen05 kernel's view: 64 input channels, pad 1 per convolved dim, halo already in
+        the operand tensor (pad_mode REFLECT is the kernel's name for "use the stored halo")."""
+        from ._cabi import S3_PAD_REFLECT
+        z = 3 - nd
+        one = (0,) * z + (1,) * nd
+        return dataclasses.replace(spec, cin=64, stride=(1, 1, 1), pad_lo=one, pad_hi=one,
+                                   pad_mode=S3_PAD_REFLECT, **kw)
+
+    @staticmethod
+    def _groups(c):
+        return 1 if c <= 64 else c // 64
+
+    @staticmethod
+    def supported(cin, cout):
+        return (cin <= 64 or cin % 64 == 0) and (cout <= 256 or cout % 64 == 0)
+
+    @staticmethod
+    def forward(ctx, x, w, b, spec, cache, halo=None):
+        from ._cabi import S3_PAD_REFLECT
+        halo = S3_PAD_REFLECT if halo is None else halo
         n, dims, cin, nd = ops.dims3(x.shape)
+        cout = spec.cout
         ver = (w._version, w.data_ptr())
-        w_hi, w_c, acc = ConvUmmaFn._packed(cache, "fwd", w, ver, nd)
-        xp = x if cin == 64 else torch.nn.functional.pad(x, (0, 64 - cin))
-        x_hi, x_c = ops.pack_act_pad16(xp, split=True, fmt=ops.S3_FMT_FP16C)
-        sp = dataclasses.replace(spec, cin=64)
-        y, _, _ = ops.conv_fwd_umma(x_hi, x_c, w_hi, w_c, b, sp, n, dims, fmt=ops.S3_FMT_FP16C,
-                                    acc_scale=acc)
-        ctx.spec, ctx.cache, ctx.x_shape = spec, cache, tuple(x.shape)
+        gin = ConvUmmaFn._groups(cin)
+        xs = []
+        for gi in range(gin):
+            xg = x if gin == 1 else x[..., 64 * gi:64 * gi + 64].contiguous()
+            if xg.shape[-1] < 64:
+                xg = torch.nn.functional.pad(xg, (0, 64 - xg.shape[-1]))
+            xs.append(ops.pack_act_pad16(xg, split=True, fmt=ops.S3_FMT_FP16C, halo=halo))
+        fuse_act = gin == 1
+        outs = []
+        for c0 in range(0, cout, 256):
+            c1 = min(cout, c0 + 256)
+            y = None
+            for gi in range(gin):
+                w_hi, w_c, acc = ConvUmmaFn._pack_w(
+                    cache, ("fwd", gi, c0), ver,
+                    lambda: w.detach()[..., 64 * gi:64 * gi + 64, c0:c1] if gin > 1
+                    else w.detach()[..., c0:c1], nd)
+                sp = ConvUmmaFn._kernel_spec(spec, nd, cout=c1 - c0)
+                if not fuse_act:
+                    sp = dataclasses.replace(sp, act=S3_ACT_NONE, alpha=0.0)
+                bias = b[c0:c1].contiguous() if (b is not None and gi == 0) else None
+                if b is not None and gi == 0 and c0 == 0 and c1 == cout:
+                    bias = b
+                y, _, _ = ops.conv_fwd_umma(xs[gi][0], xs[gi][1], w_hi, w_c, bias, sp, n, dims,
+                                            residual=y, fmt=ops.S3_FMT_FP16C, acc_scale=acc)
+            outs.append(y)
+        y = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+        if not fuse_act and spec.act != S3_ACT_NONE:
+            y = ops.act_fwd(y, spec.act, spec.alpha)
+        ctx.spec, ctx.cache, ctx.x_shape, ctx.halo = spec, cache, tuple(x.shape), halo
         ctx.has_bias = b is not None
-        # weight gradient on tcgen05: 3-D, 64 output channels -> keep the fp16 padded input (the
-        # forward's own operand) instead of the f32 tensor
-        ctx.wgrad_umma = (nd == 3 and spec.cout == 64 and min(dims) >= 2
+        # weight gradient on tcgen05: 3-D, output channels in blocks of 64 -> keep the fp16 padded
+        # inputs (the forward's own operands) instead of the f32 tensor
+        ctx.wgrad_umma = (nd == 3 and min(dims) >= 2
                           and os.environ.get("SUP3R_B200_WGRAD_FP32", "0") != "1")
-        ctx.save_for_backward(x_hi if ctx.wgrad_umma else x, w,
-                              y if spec.act != S3_ACT_NONE else None)
+        ctx.gin = gin
+        keep = [t[0] for t in xs] if ctx.wgrad_umma else [x]
+        ctx.save_for_backward(w, y if spec.act != S3_ACT_NONE else None, *keep)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
-        spec = ctx.spec
+        from ._cabi import S3_PAD_REFLECT
+        w, y, *xs = ctx.saved_tensors
+        spec, halo, cache = ctx.spec, ctx.halo, ctx.cache
         dy = dy.contiguous()
         if spec.act != S3_ACT_NONE:
             dy = ops.act_bwd(y, dy, spec.act, spec.alpha)
-        lin = dataclasses.replace(spec, act=S3_ACT_NONE)
+        lin = dataclasses.replace(spec, act=S3_ACT_NONE, alpha=0.0)
         dx = dw = db = None
-        nd = spec.ndim
+        nd, cin, cout = spec.ndim, spec.cin, spec.cout
+        reflect = halo == S3_PAD_REFLECT
+        fp32 = lin if reflect else dataclasses.replace(lin, pad_mode=S3_PAD_ZERO)
         want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         if want_w and not ctx.wgrad_umma:
-            dw, db = ops.conv_wgrad(x, dy, lin, w.shape, want_bias=ctx.has_bias)
-        g_hi, g_halo = None, 0
+            dw, db = ops.conv_wgrad(xs[0], dy, fp32, w.shape, want_bias=ctx.has_bias)
+        n, dims, _, _ = ops.dims3(dy.shape)
+        # output channels in blocks of 64 (a ragged last block is zero-padded)
+        gout = (cout + 63) // 64
+        dy_p = dy if cout % 64 == 0 else torch.nn.functional.pad(dy, (0, 64 * gout - cout))
+        g_parts, g_halo = None, 0       # fp16 zero-halo gradient tensors per 64-channel block
+        pads = [(0, 0)] + [(1, 1)] * nd + [(0, 0)]
         if ctx.needs_input_grad[0]:
-            pads = [(0, 0)] + [(1, 1)] * nd + [(0, 0)]
-            pshape = tuple(s + p[0] + p[1] for s, p in zip(ctx.x_shape, pads))
-            if spec.cout == 64 and spec.cin <= 256 and spec.cin % 16 == 0:
-                # zero-padded correlation of dy with the flipped / transposed kernel on the padded
-                # extent (tensor cores), then the adjoint of the reflect pad folds the halo back
+            if gout:
+                # correlation of dy with the flipped / transposed kernel on tensor cores, summed
+                # over the 64-channel blocks of dy.  REFLECT: on the padded extent, then the
+                # adjoint of the reflect pad folds the halo back; ZERO ('same'): directly.
                 ver = (w._version, w.data_ptr())
-                wt = w.detach().flip(dims=tuple(range(nd))).transpose(-1, -2).contiguous()
-                w_hi, w_c, acc = ConvUmmaFn._packed(ctx.cache, "dgrad", wt, ver, nd)
-                dyz = ops.pad_fwd(dy, pads, S3_PAD_ZERO)
-                n, dims, _, _ = ops.dims3(dyz.shape)
-                g_hi, g_c = ops.pack_act_pad16(dyz, split=True, fmt=ops.S3_FMT_FP16C,
-                                               halo=S3_PAD_ZERO)
-                g_halo = 2
-                sp = dataclasses.replace(lin, cin=64, cout=spec.cin)
-                dxp, _, _ = ops.conv_fwd_umma(g_hi, g_c, w_hi, w_c, None, sp, n, dims,
-                                              fmt=ops.S3_FMT_FP16C, acc_scale=acc)
-            else:
+                gsrc = ops.pad_fwd(dy_p, pads, S3_PAD_ZERO) if reflect else dy_p
+                gn, gdims, _, _ = ops.dims3(gsrc.shape)
+                g_parts, g_halo = [], (2 if reflect else 1)
+                for go in range(gout):
+                    blk = gsrc if gout == 1 else gsrc[..., 64 * go:64 * go + 64].contiguous()
+                    g_parts.append(ops.pack_act_pad16(blk, split=True, fmt=ops.S3_FMT_FP16C,
+                                                      halo=S3_PAD_ZERO))
+                cin_p = (cin + 15) // 16 * 16
+                slices = []
+                for c0 in range(0, cin_p, 256):
+                    c1 = min(cin_p, c0 + 256)
+                    dxp = None
+                    for go in range(gout):
+                        def make(go=go, c0=c0, c1=c1):
+                            wt = w.detach()[..., 64 * go:64 * go + 64]
+                            if wt.shape[-1] < 64:
+                                wt = torch.nn.functional.pad(wt, (0, 64 - wt.shape[-1]))
+                            wt = wt.flip(dims=tuple(range(nd))).transpose(-1, -2)
+                            if cin_p != cin:
+                                wt = torch.nn.functional.pad(wt, (0, cin_p - cin))
+                            return wt[..., c0:c1]
+                        w_hi, w_c, acc = ConvUmmaFn._pack_w(cache, ("dgrad", go, c0), ver, make, nd)
+                        sp = ConvUmmaFn._kernel_spec(lin, nd, cout=c1 - c0)
+                        dxp, _, _ = ops.conv_fwd_umma(g_parts[go][0], g_parts[go][1], w_hi, w_c,
+                                                      None, sp, gn, gdims, residual=dxp,
+                                                      fmt=ops.S3_FMT_FP16C, acc_scale=acc)
+                    slices.append(dxp)
+                dxp = slices[0] if len(slices) == 1 else torch.cat(slices, dim=-1)
+                if cin_p != cin:
+                    dxp = dxp[..., :cin].contiguous()
+                dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode) if reflect else dxp
+            elif reflect:
+                pshape = tuple(s + p[0] + p[1] for s, p in zip(ctx.x_shape, pads))
                 valid = dataclasses.replace(lin, pad_lo=(0, 0, 0), pad_hi=(0, 0, 0),
                                             pad_mode=S3_PAD_ZERO)
                 dxp = ops.conv_dgrad(dy, w, valid, pshape)
-            dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
+                dx = ops.pad_bwd(dxp, ctx.x_shape, pads, spec.pad_mode)
+            else:
+                dx = ops.conv_dgrad(dy, w, fp32, ctx.x_shape)
         if want_w and ctx.wgrad_umma:
-            # dW = sum_v x_pad[v + tap] (x) dy[v] on tcgen05 (voxels = the GEMM's K dimension);
-            # the zero-halo fp16 gradient tensor of the input-gradient convolution is reused
-            n, dims, _, _ = ops.dims3(dy.shape)
-            if g_hi is None or spec.cin > 64:
-                g_hi, _ = ops.pack_act_pad16(dy, split=False, fmt=ops.S3_FMT_FP16, halo=S3_PAD_ZERO)
-                g_halo = 1
-            dw = ops.conv_wgrad_umma(x, g_hi, g_halo, n, dims, min(spec.cin, 64))
+            # dW = sum_v x_pad[v + tap] (x) dy[v] on tcgen05 (voxels = the GEMM's K dimension), one
+            # launch per (input group, output block); the zero-halo fp16 gradient tensors of the
+            # input-gradient convolution are reused
+            if g_parts is None:
+                g_parts, g_halo = [], 1
+                for go in range(gout):
+                    blk = dy_p if gout == 1 else dy_p[..., 64 * go:64 * go + 64].contiguous()
+                    g_parts.append(ops.pack_act_pad16(blk, split=False, fmt=ops.S3_FMT_FP16,
+                                                      halo=S3_PAD_ZERO))
+            rows = []
+            for gi in range(ctx.gin):
+                cg = min(cin, 64)
+                cols = [ops.conv_wgrad_umma(xs[gi], g_parts[go][0], g_halo, n, dims, cg)
+                        for go in range(gout)]
+                rows.append(cols[0] if gout == 1 else torch.cat(cols, dim=-1))
+            dw = rows[0] if ctx.gin == 1 else torch.cat(rows, dim=-2)
+            if dw.shape[-1] != cout:
+                dw = dw[..., :cout].contiguous()
             if tuple(dw.shape) != tuple(w.shape):
                 dw = dw.reshape(w.shape)
-            db = ops.conv_bias_grad(dy, spec.cout) if ctx.has_bias else None
-        return dx, dw, db, None, None
+            db = ops.conv_bias_grad(dy, cout) if ctx.has_bias else None
+        return dx, dw, db, None, None, None
 
 
 class PadFn(torch.autograd.Function):

@@ -604,7 +604,7 @@ class AbstractSingleModel(TensorboardMixIn):
             loss, loss_details, hi_res_gen, _ = self._get_hr_exo_and_loss(
                 low_res, hi_res_true, **calc_loss_kwargs)
             tensors = [w.value for w in training_weights]
-            scale = self.grad_loss_scale(hi_res_gen)
+            scale = self.grad_loss_scale(hi_res_gen, calc_loss_kwargs.get("train_gen", True))
             if scale != 1.0:
                 from .base import ScaleFnScalar
                 grad = torch.autograd.grad(ScaleFnScalar.apply(loss, scale), tensors,
@@ -618,12 +618,15 @@ class AbstractSingleModel(TensorboardMixIn):
                         for k, v in loss_details.items()}
         return grad, loss_details
 
-    def grad_loss_scale(self, hi_res_gen):
-        """Power-of-two loss scale of the backward pass: the number of generated hi-res values
-        (mean-reduced losses have gradients of order 1 / that), 1 in ``fp32`` mode."""
+    def grad_loss_scale(self, hi_res_gen, train_gen=True):
+        """Power-of-two loss scale of the backward pass (1 in ``fp32`` mode) that brings the
+        top-level gradient to order one: the generator loss is a mean over the generated hi-res
+        values (gradients ~ 1 / their number); the discriminator loss a mean over the 2 x batch
+        logits."""
         if self.precision == "fp32":
             return 1.0
-        return float(2.0 ** int(np.floor(np.log2(max(hi_res_gen.numel(), 1)))))
+        n = hi_res_gen.numel() if train_gen else 2 * hi_res_gen.shape[0]
+        return float(2.0 ** int(np.floor(np.log2(max(n, 1)))))
 
     def calc_loss(self, hi_res_true, hi_res_gen, weight_gen_advers=0.001, train_gen=True,
                   train_disc=False, compute_disc=False):  # pragma: no cover - abstract

@@ -108,7 +108,9 @@ class Sup3rGan(AbstractSingleModel, AbstractInterface):
     def _tf_discriminate(self, hi_res):
         """Differentiable discriminator forward on device tensors (base.py:283-313)."""
         x = to_device_tensor(hi_res, self.torch_device())
-        return self.plan_for(self.discriminator, "fp32").forward_train(x)
+        # (64-channel-block 'same' convolutions run on tcgen05 unless precision == "fp32")
+        prec = "fp32" if self.precision == "fp32" else "fp16c"
+        return self.plan_for(self.discriminator, prec).forward_train(x)
 
     # ---- optimisers --------------------------------------------------------------------------
     @property

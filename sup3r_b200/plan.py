@@ -533,6 +533,23 @@ class Plan:
                 and all(s == 1 for s in conv.strides) and st.pad_mode == S3_PAD_REFLECT
                 and all(tuple(p) == (1, 1) for p in st.pads) and min(in_shape[1:-1]) >= 2)
 
+    @staticmethod
+    def _train_umma_same_ok(st, in_shape):
+        """keras ``padding='same'`` 3x3[x3] convolutions (the discriminator) on tcgen05: stride 1,
+        or stride 2 on every dim; cin <= 64 or a multiple of 64, 64 | cout <= 512."""
+        conv = st.conv
+        if st.pads is not None or conv.transposed or conv.padding != "same":
+            return False
+        if st.r > 1 or st.m > 1:
+            return False
+        strides = tuple(conv.strides)
+        if not (all(s == 1 for s in strides) or all(s == 2 for s in strides)):
+            return False
+        cin = in_shape[-1]
+        return (conv.nd in (2, 3) and (cin <= 64 or (cin % 64 == 0 and cin <= 512))
+                and conv.filters % 64 == 0 and conv.filters <= 512
+                and all(k == 3 for k in conv.kernel_size) and min(in_shape[1:-1]) >= 2)
+
     # -- training forward (autograd) -------------------------------------------------
     def forward_train(self, x, exo=None):
         """Differentiable forward on the fp32 kernels: the same fused steps, each wrapped in
@@ -558,11 +575,27 @@ class Plan:
                                          alpha=st.alpha, pad_mode=st.pad_mode)
                     b = conv.bias.value if conv.bias is not None else None
                     if tensor_cores and self._train_umma_ok(st, tuple(cur.shape)):
-                        # forward + input gradient on tcgen05 (fp16c operands)
+                        # forward + input / weight gradients on tcgen05 (fp16c operands)
                         cache = conv.__dict__.setdefault("_umma_train_cache", {})
                         cur = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, spec, cache)
+                    elif tensor_cores and self._train_umma_same_ok(st, tuple(cur.shape)):
+                        # keras padding='same' (the discriminator): zero-halo operands.  Stride 2
+                        # = the stride-1 convolution sampled at the positions TF's asymmetric
+                        # 'same' padding selects (the tensor cores redo 8x the work of the strided
+                        # convolution and are still far faster than the fp32 kernel)
+                        cache = conv.__dict__.setdefault("_umma_train_cache", {})
+                        nd = conv.nd
+                        one = (0,) * (3 - nd) + (1,) * nd
+                        sp1 = dataclasses.replace(spec, stride=(1, 1, 1), pad_lo=one, pad_hi=one,
+                                                  pad_mode=S3_PAD_ZERO)
+                        full = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, sp1, cache, S3_PAD_ZERO)
+                        if any(s > 1 for s in conv.strides):
+                            idx = (slice(None),) + tuple(
+                                slice(1 - (n % 2), None, 2) for n in cur.shape[1:-1]) + (slice(None),)
+                            full = full[idx].contiguous()
+                        cur = full
                     else:
-                        cur = ConvFn.apply(cur, conv.conv_kernel(), b, spec)
+                        cur = ConvFn.apply(cur, conv.conv_kernel(), b, spec, tensor_cores)
                     if st.r > 1 or st.m > 1:
                         cur = ExpandFn.apply(cur, st.r, st.m, st.method, st.roll)
                     if st.skip_add is not None:

@@ -25,7 +25,7 @@ kw = dict(weight_gen_advers=1e-3, train_gen=True, train_disc=False)
 def grads(precision, scaled):
     m.precision = precision
     if not scaled:
-        m.grad_loss_scale = lambda hi: 1.0
+        m.grad_loss_scale = lambda hi, tg=True: 1.0
     elif "grad_loss_scale" in m.__dict__:
         del m.__dict__["grad_loss_scale"]
     g, det = m.get_single_grad(lr, hr, m.generator_weights, **kw)
