@@ -150,7 +150,9 @@ int s3_conv_fwd_small_fp16(const s3_conv_desc* d, const float* x, const void* x_
 int s3_conv_dgrad_f32(const s3_conv_desc* d, const float* dy, const float* w, float* dx,
                       s3_stream stream);
 /* Weight / bias gradients: dw (kz,ky,kx,cin,cout), dbias [cout] (either may be NULL).
- * Results OVERWRITE the destinations.  scratch: >= s3_conv_wgrad_scratch_bytes() or NULL. */
+ * Results OVERWRITE the destinations.  Deterministic: the voxels are split over CTAs, every split
+ * writes its partial dw to `scratch` (>= s3_conv_wgrad_scratch_bytes(); may be NULL when that is
+ * 0) and a second kernel adds the splits in a fixed order; the bias gradient likewise. */
 size_t s3_conv_wgrad_scratch_bytes(const s3_conv_desc* d);
 int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy, float* dw,
                       float* dbias, void* scratch, s3_stream stream);

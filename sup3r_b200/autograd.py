@@ -123,12 +123,15 @@ class ConvUmmaFn(torch.autograd.Function):
         return (cin <= 64 or cin % 64 == 0) and (cout <= 256 or cout % 64 == 0)
 
     @staticmethod
-    def forward(ctx, x, w, b, spec, cache, halo=None):
+    def forward(ctx, x, w, b, spec, cache, halo=None, wver=None):
+        """``wver``: version stamp of the weight (``Variable.version``): the optimiser kernel
+        updates weights through raw pointers, which torch's own ``_version`` does not see."""
         from ._cabi import S3_PAD_REFLECT
         halo = S3_PAD_REFLECT if halo is None else halo
         n, dims, cin, nd = ops.dims3(x.shape)
         cout = spec.cout
-        ver = (w._version, w.data_ptr())
+        ver = (wver, w._version, w.data_ptr())
+        ctx.ver = ver
         gin = ConvUmmaFn._groups(cin)
         xs = []
         for gi in range(gin):
@@ -196,7 +199,7 @@ class ConvUmmaFn(torch.autograd.Function):
                 # correlation of dy with the flipped / transposed kernel on tensor cores, summed
                 # over the 64-channel blocks of dy.  REFLECT: on the padded extent, then the
                 # adjoint of the reflect pad folds the halo back; ZERO ('same'): directly.
-                ver = (w._version, w.data_ptr())
+                ver = ctx.ver
                 gsrc = ops.pad_fwd(dy_p, pads, S3_PAD_ZERO) if reflect else dy_p
                 gn, gdims, _, _ = ops.dims3(gsrc.shape)
                 g_parts, g_halo = [], (2 if reflect else 1)
@@ -258,7 +261,7 @@ class ConvUmmaFn(torch.autograd.Function):
             if tuple(dw.shape) != tuple(w.shape):
                 dw = dw.reshape(w.shape)
             db = ops.conv_bias_grad(dy, cout) if ctx.has_bias else None
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class PadFn(torch.autograd.Function):

@@ -184,7 +184,7 @@ conv_direct_kernel(const ConvGeom g, const float* __restrict__ src, const float*
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_wgrad_kernel(const ConvGeom g, const float* __restrict__ x, const float* __restrict__ dy,
-                  float* __restrict__ dw, int vox_per_split) {
+                  float* __restrict__ dw, int vox_per_split, size_t dw_split_stride) {
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
@@ -263,8 +263,20 @@ conv_wgrad_kernel(const ConvGeom g, const float* __restrict__ x, const float* __
     for (int j = 0; j < TN; ++j) {
       const int ci = m0 + ty * TM + i, co = n0 + tx * TN + j;
       if (ci < g.cin && co < g.cout)
-        atomicAdd(dw + ((size_t)tap * g.cin + ci) * g.cout + co, acc[i][j]);
+        dw[(size_t)blockIdx.z * dw_split_stride + ((size_t)tap * g.cin + ci) * g.cout + co] =
+            acc[i][j];
     }
+}
+
+// dw[i] = sum over the voxel splits, fixed order (deterministic second stage of the split-K wgrad)
+__global__ void wgrad_split_reduce_kernel(const float* __restrict__ part, int splits, size_t n,
+                                          float* __restrict__ dw) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[(size_t)k * n + i];
+    dw[i] = s;
+  }
 }
 
 int launch_colsum(const float* x, long long rows, int cols, float* out, cudaStream_t st);
@@ -365,10 +377,37 @@ extern "C" int s3_conv_dgrad_f32(const s3_conv_desc* d, const float* dy, const f
   return S3_OK;
 }
 
-extern "C" size_t s3_conv_wgrad_scratch_bytes(const s3_conv_desc*) { return 0; }
+static long long wgrad_splits(const ConvGeom& g, int* vps_out) {
+  const long long V = (long long)g.n * g.od[0] * g.od[1] * g.od[2];
+  const int ntaps = g.k[0] * g.k[1] * g.k[2];
+  // enough splits to fill the machine, at least 256 voxels each
+  const int tiles = ntaps * ((g.cin + 63) / 64) * ((g.cout + 63) / 64);
+  long long want = (4LL * sm_count() + tiles - 1) / tiles;
+  long long max_splits = (V + 255) / 256;
+  long long splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  int vps = (int)((V + splits - 1) / splits);
+  vps = (vps + 15) / 16 * 16;
+  if (vps < 16) vps = 16;
+  splits = (V + vps - 1) / vps;
+  if (splits < 1) splits = 1;
+  *vps_out = vps;
+  return splits;
+}
+
+/* Scratch of the deterministic split-K weight gradient: one partial dw per voxel split. */
+extern "C" size_t s3_conv_wgrad_scratch_bytes(const s3_conv_desc* d) {
+  ConvGeom g;
+  if (make_geom(d, &g)) return 0;
+  int vps;
+  const long long splits = wgrad_splits(g, &vps);
+  const size_t n = (size_t)g.k[0] * g.k[1] * g.k[2] * g.cin * g.cout;
+  return splits > 1 ? (size_t)splits * n * sizeof(float) : 0;
+}
 
 extern "C" int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const float* dy,
-                                 float* dw, float* dbias, void*, s3_stream stream) {
+                                 float* dw, float* dbias, void* scratch, s3_stream stream) {
   ConvGeom g;
   int rc = make_geom(d, &g);
   if (rc) return rc;
@@ -377,19 +416,22 @@ extern "C" int s3_conv_wgrad_f32(const s3_conv_desc* d, const float* x, const fl
   const long long V = (long long)g.n * g.od[0] * g.od[1] * g.od[2];
   const int ntaps = g.k[0] * g.k[1] * g.k[2];
   if (dw) {
-    S3_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * ntaps * g.cin * g.cout, st));
-    // enough splits to fill the machine, at least 256 voxels each
-    const int tiles = ntaps * ((g.cin + 63) / 64) * ((g.cout + 63) / 64);
-    long long want = (4LL * sm_count() + tiles - 1) / tiles;
-    long long max_splits = (V + 255) / 256;
-    long long splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-    if (splits > 65535) splits = 65535;
-    int vps = (int)((V + splits - 1) / splits);
-    vps = (vps + 15) / 16 * 16;
-    splits = (V + vps - 1) / vps;
+    int vps;
+    const long long splits = wgrad_splits(g, &vps);
+    const size_t n = (size_t)ntaps * g.cin * g.cout;
+    S3_REQUIRE(splits == 1 || scratch, "s3_conv_wgrad_f32: this geometry splits the voxels %lld "
+               "ways and needs s3_conv_wgrad_scratch_bytes() of scratch", splits);
     dim3 grid(ntaps * ((g.cin + 63) / 64), (g.cout + 63) / 64, (unsigned)splits);
-    conv_wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(g, x, dy, dw, vps);
+    float* dst = splits == 1 ? dw : static_cast<float*>(scratch);
+    conv_wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(g, x, dy, dst, vps,
+                                                                splits == 1 ? 0 : n);
     S3_LAUNCH_CHECK("conv_wgrad_kernel");
+    if (splits > 1) {
+      unsigned blocks = (unsigned)((n + 255) / 256);
+      if (blocks > 4096u) blocks = 4096u;
+      wgrad_split_reduce_kernel<<<blocks, 256, 0, st>>>(dst, (int)splits, n, dw);
+      S3_LAUNCH_CHECK("wgrad_split_reduce_kernel");
+    }
   }
   if (dbias) {
     rc = launch_colsum(dy, V, g.cout, dbias, st);

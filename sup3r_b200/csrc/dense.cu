@@ -11,7 +11,7 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
              int M, int N, int K, long long sam, long long sak, long long sbk, long long sbn,
-             int k_per_split, int atomic) {
+             int k_per_split, size_t split_stride) {
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
@@ -61,8 +61,8 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
     for (int j = 0; j < TN; ++j) {
       const int m = m0 + ty * TM + i, n = n0 + tx * TN + j;
       if (m < M && n < N) {
-        if (atomic) atomicAdd(C + (size_t)m * N + n, acc[i][j]);
-        else C[(size_t)m * N + n] = acc[i][j];
+        // (split K: every split writes its own partial C, reduced in a fixed order afterwards)
+        C[(size_t)blockIdx.z * split_stride + (size_t)m * N + n] = acc[i][j];
       }
     }
 }
@@ -76,9 +76,11 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
   }
 }
 
-// out[c] += sum_r x[r, c]; out must be zeroed.  32 channels x 8 row lanes per block.
+// Column sums out[c] = sum_r x[r, c], DETERMINISTIC: every block writes its partial sums to
+// part[block][c] (out itself when there is one block), a second kernel adds the blocks in a
+// fixed order.  32 channels x 8 row lanes per block.
 __global__ void colsum_kernel(const float* __restrict__ x, long long rows, int cols,
-                              float* __restrict__ out) {
+                              float* __restrict__ part) {
   const int c = blockIdx.y * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5, lanes = blockDim.x >> 5;
   float s = 0.f;
@@ -91,20 +93,73 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long rows, int c
   __syncthreads();
   if (lane == 0 && c < cols) {
     for (int i = 1; i < lanes; ++i) s += sh[i][threadIdx.x & 31];
-    atomicAdd(out + c, s);
+    part[(size_t)blockIdx.x * cols + c] = s;
   }
 }
 
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int nblk, int cols,
+                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * cols + c];
+  out[c] = s;
+}
+
+// partial-sum scratch of the column sums: grown on demand, one per device (the only allocation
+// the library makes after s3_init; stream-ordered use, freed with the context)
+static size_t gemm_scratch_offset() { return (size_t)1 << 18; }   // floats reserved for colsum
+
+static float* colsum_scratch(size_t floats) {
+  static float* buf[16] = {nullptr};
+  static size_t cap[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (cap[dev] < floats) {
+    if (buf[dev]) {
+      cudaDeviceSynchronize();
+      cudaFree(buf[dev]);
+    }
+    size_t want = floats < (1u << 18) ? (1u << 18) : floats;
+    if (cudaMalloc(&buf[dev], want * sizeof(float)) != cudaSuccess) {
+      buf[dev] = nullptr; cap[dev] = 0;
+      return nullptr;
+    }
+    cap[dev] = want;
+  }
+  return buf[dev];
+}
+
 int launch_colsum(const float* x, long long rows, int cols, float* out, cudaStream_t st) {
-  S3_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
-  if (rows == 0) return S3_OK;
+  if (rows == 0) {
+    S3_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+    return S3_OK;
+  }
   long long bx = (rows + 7) / 8;
   long long cap = (long long)sm_count() * 8 / ((cols + 31) / 32) + 1;
   if (bx > cap) bx = cap;
+  if (rows <= 4096) bx = 1;     // small reductions (dense layers): one block, no second stage
   dim3 grid((unsigned)bx, (cols + 31) / 32);
-  colsum_kernel<<<grid, 256, 0, st>>>(x, rows, cols, out);
+  if (bx == 1) {
+    colsum_kernel<<<grid, 256, 0, st>>>(x, rows, cols, out);
+  } else {
+    float* part = colsum_scratch((size_t)bx * cols);
+    S3_REQUIRE(part != nullptr, "colsum: cannot allocate %lld x %d partial sums", bx, cols);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, rows, cols, part);
+    colsum_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>(part, (int)bx, cols, out);
+  }
   S3_CUDA(cudaGetLastError());
   return S3_OK;
+}
+
+__global__ void split_reduce_kernel(const float* __restrict__ part, int splits, size_t n,
+                                    float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[(size_t)k * n + i];
+    out[i] = s;
+  }
 }
 
 static int launch_gemm(const float* A, const float* B, float* C, int M, int N, int K,
@@ -118,11 +173,23 @@ static int launch_gemm(const float* A, const float* B, float* C, int M, int N, i
   int kps = (K + splits - 1) / splits;
   kps = (kps + 15) / 16 * 16;
   splits = (K + kps - 1) / kps;
-  if (splits > 1) S3_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+  const size_t n = (size_t)M * N;
+  float* dst = C;
+  if (splits > 1) {   // deterministic split K: partial products, then a fixed-order reduction
+    dst = colsum_scratch((size_t)splits * n + gemm_scratch_offset());
+    S3_REQUIRE(dst != nullptr, "gemm: cannot allocate %d x %zu partial sums", splits, n);
+    dst += gemm_scratch_offset();
+  }
   dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-  sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, kps,
-                                                      splits > 1 ? 1 : 0);
+  sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(A, B, dst, M, N, K, sam, sak, sbk, sbn, kps,
+                                                      splits > 1 ? n : 0);
   S3_CUDA(cudaGetLastError());
+  if (splits > 1) {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 2048u) blocks = 2048u;
+    split_reduce_kernel<<<blocks, 256, 0, st>>>(dst, splits, n, C);
+    S3_CUDA(cudaGetLastError());
+  }
   return S3_OK;
 }
 

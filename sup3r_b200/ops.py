@@ -203,10 +203,26 @@ def conv_wgrad(x, dy, spec: ConvSpec, w_shape, want_bias=True):
     n, dims, c, ndim = dims3(x.shape)
     dw = torch.empty(tuple(w_shape), device=x.device, dtype=torch.float32)
     db = torch.empty(spec.cout, device=x.device, dtype=torch.float32) if want_bias else None
-    _cabi.call("s3_conv_wgrad_f32", C.byref(spec.desc(n, dims)), _p(x), _p(dy), _p(dw), _p(db),
-               None, _s())
+    desc = spec.desc(n, dims)
+    need = _cabi.load().s3_conv_wgrad_scratch_bytes(C.byref(desc))
+    scratch = _scratch(x.device, need) if need else None
+    _cabi.call("s3_conv_wgrad_f32", C.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(scratch),
+               _s())
     _count(4 if want_bias else 2)
     return dw, db
+
+
+_scratch_bufs = {}
+
+
+def _scratch(device, nbytes):
+    """Cached device scratch (stream-ordered reuse) for the split-K partial sums."""
+    key = str(device)
+    buf = _scratch_bufs.get(key)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = _scratch_bufs[key] = torch.empty((nbytes + 3) // 4, device=device,
+                                               dtype=torch.float32)
+    return buf
 
 
 def conv_bias_grad(dy, cout):

@@ -162,7 +162,10 @@ class ForwardPassStrategy:
     def __post_init__(self):
         self.bias_correct_kwargs = self.bias_correct_kwargs or {}
         if self.bias_correct_kwargs:
-            raise NotImplementedError("bias correction hooks are out of scope (SURVEY 8(f))")
+            from ..bias import METHODS
+            if self.bias_correct_method not in METHODS:
+                raise KeyError(f'bias_correct_method "{self.bias_correct_method}" is not one of '
+                               f"{sorted(METHODS)}")
         self.input_handler_kwargs = dict(self.input_handler_kwargs or {})
         self.timer = Timer()
         model = self.get_model()
@@ -311,6 +314,15 @@ class ForwardPassStrategy:
             exo = self.timer(self.exo_data.get_chunk, log=True, call_id=chunk_index)(
                 [lr_pad[0], lr_pad[1], ti_pad])
         data = self.input_handler.get(self.features, lr_pad[0], lr_pad[1], ti_pad)
+        if self.bias_correct_kwargs:
+            # strategy.py:502-517: bias-correct the low-res chunk before it goes to the model
+            from ..bias import bias_correct_features
+            logger.info("Bias correcting data for chunk_index=%s, with shape=%s", chunk_index,
+                        data.shape)
+            data = bias_correct_features(
+                np.array(data, dtype=np.float32, copy=True), self.features,
+                self.input_handler.lat_lon[lr_pad[0], lr_pad[1]], self.bias_correct_method,
+                self.bias_correct_kwargs, lr_padded_slice=(lr_pad[0], lr_pad[1], ti_pad))
         return data, exo
 
     def chunk_padded_shape(self, chunk_index):

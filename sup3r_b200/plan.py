@@ -577,7 +577,8 @@ class Plan:
                     if tensor_cores and self._train_umma_ok(st, tuple(cur.shape)):
                         # forward + input / weight gradients on tcgen05 (fp16c operands)
                         cache = conv.__dict__.setdefault("_umma_train_cache", {})
-                        cur = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, spec, cache)
+                        cur = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, spec, cache, None,
+                                               conv.kernel.version)
                     elif tensor_cores and self._train_umma_same_ok(st, tuple(cur.shape)):
                         # keras padding='same' (the discriminator): zero-halo operands.  Stride 2
                         # = the stride-1 convolution sampled at the positions TF's asymmetric
@@ -588,7 +589,8 @@ class Plan:
                         one = (0,) * (3 - nd) + (1,) * nd
                         sp1 = dataclasses.replace(spec, stride=(1, 1, 1), pad_lo=one, pad_hi=one,
                                                   pad_mode=S3_PAD_ZERO)
-                        full = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, sp1, cache, S3_PAD_ZERO)
+                        full = ConvUmmaFn.apply(cur, conv.conv_kernel(), b, sp1, cache, S3_PAD_ZERO,
+                                                conv.kernel.version)
                         if any(s > 1 for s in conv.strides):
                             idx = (slice(None),) + tuple(
                                 slice(1 - (n % 2), None, 2) for n in cur.shape[1:-1]) + (slice(None),)

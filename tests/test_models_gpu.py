@@ -529,3 +529,37 @@ def test_forward_pass_output_check_on_device(cuda):
     assert not ForwardPass._device_check_failed(chk, allowed_const=True)
     chk[0, 2] = 3.0
     assert ForwardPass._device_check_failed(chk, allowed_const=[2.0])
+
+
+def test_training_forward_sees_optimizer_updates(cuda):
+    """The optimiser kernel updates weights through raw pointers (torch's tensor version does not
+    move): the packed tensor-core weights of the training path must be re-packed after every
+    step -- the tape forward after a step equals a fresh model carrying the updated weights, and
+    differs from the pre-step forward."""
+    gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
+    disc_hl = C.discriminator(3, "same", (16,))
+    lr_shape, hr_shape = (2, 4, 4, 4, 2), (2, 8, 8, 8, 2)
+    m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, learning_rate=1e-2)
+    rng = np.random.default_rng(5)
+    lr = rng.standard_normal(lr_shape).astype(np.float32)
+    hr = rng.standard_normal(hr_shape).astype(np.float32)
+    with torch.no_grad():
+        before = m._tf_generate(lr).cpu().numpy()
+        d_before = m._tf_discriminate(hr).cpu().numpy()
+    m.run_gradient_descent(lr, hr, m.generator_weights, weight_gen_advers=1e-2, train_gen=True,
+                           train_disc=False)
+    m.run_gradient_descent(lr, hr, m.discriminator_weights, optimizer=m.optimizer_disc,
+                           weight_gen_advers=1e-2, train_gen=False, train_disc=True)
+    with torch.no_grad():
+        after = m._tf_generate(lr).cpu().numpy()
+        d_after = m._tf_discriminate(hr).cpu().numpy()
+    fresh = make_model(gen_hl, disc_hl, lr_shape, hr_shape)
+    fresh.generator.set_weights(m.generator.get_weights())
+    fresh.discriminator.set_weights(m.discriminator.get_weights())
+    with torch.no_grad():
+        want = fresh._tf_generate(lr).cpu().numpy()
+        d_want = fresh._tf_discriminate(hr).cpu().numpy()
+    assert np.array_equal(after, want) and np.array_equal(d_after, d_want)
+    assert np.abs(after - before).max() > 1e-3 and np.abs(d_after - d_before).max() > 1e-6
+    # and the inference plan (CUDA graph) follows as well
+    assert np.allclose(m.generate(lr), fresh.generate(lr), rtol=0, atol=0)

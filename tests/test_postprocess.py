@@ -148,3 +148,63 @@ def test_device_batch_handler_trains_a_gan(cuda):
     assert bh.stopped and np.isfinite(tl).all() and tl[-1] < tl[0]
     assert m.meta["smoothing"] == 0.6 and m.meta["lr_features"] == ["u", "v"]
     assert abs(m.means["u"] - float(data[..., 0].mean())) < 1e-3
+
+
+# ------------------------------------------------------------------------------ bias correction
+def test_bias_transforms_match_reference(tmp_path):
+    """sup3r_b200.bias vs golden outputs of the reference function bodies (tests/golden/bias.npz)."""
+    import warnings
+    from sup3r_b200 import bias
+    g = np.load(os.path.join(HERE, "golden", "bias.npz"))
+    fp = str(tmp_path / "bc.npz")
+    np.savez(fp, u_scalar=g["scalar"], u_adder=g["adder"])
+    d = g["data"]
+    sl = (slice(1, 5), slice(0, 4), slice(None))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert np.array_equal(bias.global_linear_bc(d, 1.1, -0.3, out_range=(-1, 1)), g["global"])
+        assert np.array_equal(bias.local_linear_bc(d, None, "u", fp, smoothing=0.8,
+                                                   out_range=(-2, 2)), g["local"])
+        assert np.array_equal(bias.local_linear_bc(d[sl[0], sl[1]], None, "u", fp,
+                                                   lr_padded_slice=sl), g["local_slice"])
+        assert np.array_equal(bias.monthly_local_linear_bc(
+            d, None, "u", fp, months=g["months"], temporal_avg=True, scalar_range=(0.8, 1.2)),
+            g["monthly_avg"])
+        assert np.array_equal(bias.monthly_local_linear_bc(
+            d, None, "u", fp, months=g["months"], temporal_avg=False, smoothing=0.5,
+            adder_range=(-1, 1)), g["monthly"])
+    with pytest.raises(RuntimeError):
+        bias.bias_correct_features(np.zeros((6, 5, 8, 1), np.float32), ["v"], None,
+                                   "local_linear_bc", {"v": {"bias_fp": fp}})
+    with pytest.raises(KeyError):
+        bias.bias_correct_features(np.zeros((6, 5, 8, 1), np.float32), ["u"], None, "local_qdm_bc",
+                                   {"u": {}})
+
+
+@pytest.mark.gpu
+def test_forward_pass_bias_correction_hook(cuda, tmp_path):
+    """strategy.py:502-517: the chunk is bias-corrected before the generator sees it."""
+    from sup3r_b200 import configs as C
+    from sup3r_b200.models import Sup3rGan
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    Sup3rGan.seed(0)
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1, filters=16),
+                 C.discriminator(3, "same", (8,)),
+                 meta={"lr_features": ["u", "v"], "hr_out_features": ["u", "v"], "s_enhance": 2,
+                       "t_enhance": 2})
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((8, 8, 6, 2)).astype(np.float32)
+    fp = str(tmp_path / "bc.npz")
+    scalar = (1 + 0.3 * rng.standard_normal((8, 8))).astype(np.float32)
+    adder = rng.standard_normal((8, 8)).astype(np.float32)
+    np.savez(fp, u_scalar=scalar, u_adder=adder)
+    mk = lambda d, **kw: ForwardPassStrategy(model=m, input_handler=ArrayInputHandler(d, ["u", "v"]),
+                                             fwp_chunk_shape=(4, 4, 6), spatial_pad=1, **kw)
+    got = ForwardPass.run(mk(data, bias_correct_method="local_linear_bc",
+                             bias_correct_kwargs={"u": {"bias_fp": fp}}), 0)
+    corrected = data.copy()
+    corrected[..., 0] = data[..., 0] * scalar[..., None] + adder[..., None]
+    want = ForwardPass.run(mk(corrected), 0)
+    assert sorted(got) == sorted(want) == [0, 1, 2, 3]
+    for k in got:
+        assert np.array_equal(got[k], want[k])

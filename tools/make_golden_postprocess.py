@@ -77,3 +77,46 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def bias_golden():
+    """Linear bias-correction transforms: the reference function bodies with the h5 factor reader
+    (`_get_spatial_bc_factors`, rex) replaced by in-memory arrays -> tests/golden/bias.npz"""
+    from unittest.mock import MagicMock as MM
+    src = open(os.path.join(REF, "sup3r/bias/bias_transforms.py")).read()
+    rng = np.random.default_rng(3)
+    s1, s2, t = 6, 5, 8
+    fac = {"scalar": (1 + 0.2 * rng.standard_normal((s1, s2, 12))).astype(np.float32),
+           "adder": rng.standard_normal((s1, s2, 12)).astype(np.float32)}
+    months = np.array([1, 1, 1, 2, 2, 2, 2, 2])
+
+    class TI:
+        class month:
+            values = months
+
+            @staticmethod
+            def unique():
+                return np.unique(months)
+
+    ns = {"np": np, "logger": MM(), "warn": lambda *a, **k: None, "gaussian_filter": gaussian_filter,
+          "_get_spatial_bc_factors": lambda *a, **k: {k2: v.copy() for k2, v in fac.items()},
+          "make_time_index_from_kws": lambda kw: TI}
+    for fn in ("global_linear_bc", "local_linear_bc", "monthly_local_linear_bc"):
+        grab(src, fn, ns)
+    data = rng.standard_normal((s1, s2, t)).astype(np.float32)
+    sl = (slice(1, 5), slice(0, 4), slice(None))
+    res = {"data": data, "scalar": fac["scalar"], "adder": fac["adder"], "months": months,
+           "global": ns["global_linear_bc"](data, 1.1, -0.3, out_range=(-1, 1)),
+           "local": ns["local_linear_bc"](data, None, "u", "fp", smoothing=0.8, out_range=(-2, 2)),
+           "local_slice": ns["local_linear_bc"](data[sl[0], sl[1]], None, "u", "fp",
+                                                lr_padded_slice=sl),
+           "monthly_avg": ns["monthly_local_linear_bc"](data, None, "u", "fp", {}, temporal_avg=True,
+                                                        scalar_range=(0.8, 1.2)),
+           "monthly": ns["monthly_local_linear_bc"](data, None, "u", "fp", {}, temporal_avg=False,
+                                                    smoothing=0.5, adder_range=(-1, 1))}
+    np.savez_compressed(os.path.join(OUT, "bias.npz"), **res)
+    print("written", os.path.join(OUT, "bias.npz"))
+
+
+if __name__ == "__main__":
+    bias_golden()

@@ -13,6 +13,7 @@ from sup3r_b200 import configs as C
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
+ap.add_argument("--precision", default="fp16c")
 ap.add_argument("--max-hr-gb", type=float, default=24.0, help="skip cases whose fp32 HR output exceeds this")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -20,7 +21,7 @@ peaks, src = bench.load_peaks()
 peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
 hl = bench.gen_config()
 Sup3rGan.seed(0)
-model = Sup3rGan(hl, C.discriminator(3, "same", (2048, 1024)), precision="bf16")
+model = Sup3rGan(hl, C.discriminator(3, "same", (2048, 1024)), precision=a.precision)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 rows = []
 for chunk in [(8, 8, 12), (16, 16, 24), (32, 32, 48), (64, 64, 96)]:
@@ -32,7 +33,7 @@ for chunk in [(8, 8, 12), (16, 16, 24), (32, 32, 48), (64, 64, 96)]:
             continue
         try:
             x = torch.randn((B, *chunk, 4), device=dev)
-            plan = model.plan_for(model.generator, "bf16")
+            plan = model.plan_for(model.generator, a.precision)
             plan.invalidate()
             for _ in range(2):
                 plan.run_graphed(x)
@@ -54,7 +55,7 @@ for chunk in [(8, 8, 12), (16, 16, 24), (32, 32, 48), (64, 64, 96)]:
             plan.invalidate()
             torch.cuda.empty_cache()
 if a.out:
-    out = ["# r01 sweep: north-star generator (5x/12x/4f), precision bf16, one B200", "",
+    out = [f"# sweep (BASELINE configs[4]): north-star generator (5x/12x/4f), precision {a.precision}, one B200", "",
            f"Device-timed (CUDA events around one CUDA-graph replay, 256 MiB L2 flush before each, median of 5). "
            f"Algorithmic FLOPs per chunk as in bench.py; peak = {peak} TF/s ({src} sustained bf16).", "",
            "| LR chunk | batch | ms / step | M LR voxels/s | algorithmic TF/s | % of peak | fp32 HR output (GB) |",
