@@ -222,8 +222,9 @@ def _umma_ok(fc: FusedConv, in_shape, precision):
     if in_shape[-1] > 64:
         # 64 feature channels + a few Sup3rConcat exo channels (2-D): tensor cores for the 64,
         # the fp32 kernel for the rest, summed before the activation
-        if not (nd == 2 and in_shape[-1] <= 72 and conv.filters == 64 and precision == "bf16"
-                and fc.r == 1 and fc.m == 1 and fc.skip_add is None):
+        if not (nd == 2 and in_shape[-1] <= 72 and conv.filters == 64
+                and precision in ("bf16", "fp16c") and fc.r == 1 and fc.m == 1
+                and fc.skip_add is None):
             return False
     if conv.filters > 256:
         # wide scatter heads (e.g. 64 -> 1600 with 5x depth_to_space, 64 -> 768 with 24x
@@ -383,8 +384,10 @@ class Plan:
         # producer writes 16-bit output anyway: hi is the next convolution's operand, hi + lo
         # (~16 mantissa bits) is the addend of the consuming convolution's epilogue
         # (phygnn SkipConnection semantics, call site sup3r/models/abstract.py:1081-1092)
-        pair_skip = (want16 and bool(st.skip_store)
-                     and (c_mode or (not split and self._ring16_ok(st, out_shape))))
+        # (only the 3-D ring kernel's epilogue takes the pair back as a residual: elsewhere the
+        # cache is written as f32 next to the 16-bit operand tensor)
+        pair_skip = (want16 and bool(st.skip_store) and self._ring16_ok(st, out_shape)
+                     and (c_mode or not split))
         want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
         if os.environ.get("SUP3R_B200_TRACE_PLAN"):
@@ -405,19 +408,21 @@ class Plan:
             w = conv.conv_kernel().detach()
             sp_rem = dataclasses.replace(spec, cin=cin - 64, act=S3_ACT_NONE, alpha=0.0)
             part = ops.conv_fwd(xf[..., 64:].contiguous(), w[..., 64:, :].contiguous(), None, sp_rem)
-            x_hi, x_lo = ops.pack_act_pad16(xf[..., :64].contiguous(), split=split)
-            key = (id(conv), split, "main64")
+            x_hi, x_lo = ops.pack_act_pad16(xf[..., :64].contiguous(), split=split, fmt=fmt)
+            key = (id(conv), split, "main64", fmt)
             ver = (conv.kernel.version, conv.kernel.value.data_ptr())
             hit = self._wcache.get(key)
             if hit is None or hit[0] != ver:
                 hit = (ver, *ops.pack_weights_umma(w[..., :64, :].contiguous(), split=split,
-                                                   ndim=conv.nd))
+                                                   ndim=conv.nd, fmt=fmt))
                 self._wcache[key] = hit
             sp_main = dataclasses.replace(spec, cin=64, res_pre_act=1)
             self._post_fused = False
             y, y_hi, y_lo = ops.conv_fwd_umma(x_hi, x_lo, hit[1], hit[2], bias, sp_main, n, dims,
-                                              residual=part, want_f32=want32, want_pad16=want16)
-            return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo), skips)
+                                              residual=part, want_f32=want32, want_pad16=want16,
+                                              want_lo=c_mode and want16, fmt=fmt,
+                                              acc_scale=hit[3] if len(hit) > 3 else 0.0)
+            return self._finish_conv(st, Act(out_shape, f32=y, hi=y_hi, lo=y_lo, fmt=fmt), skips)
         if umma:
             if cin < 64:
                 x_hi, x_lo = ops.pack_act_pad16(

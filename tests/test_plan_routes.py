@@ -58,6 +58,8 @@ def test_wide_scatter_heads_and_concat_conv_routes():
     concat = [r for r in routes if r[0] == 65]
     assert concat and concat[0][4]                            # 64 + exo channel: split conv
     assert routes[0][:2] == (6, 64) and routes[0][4]          # narrow 2-D input, padded route
+    _, routes_c = _routes(hl, (4, 20, 20, 6), "fp16c")        # the benchmarked mode too
+    assert [r for r in routes_c if r[0] == 65][0][4]
     hl_t = C.sup3rcc_temporal_d2t_generator(6, 24, 12)
     _, routes_t = _routes(hl_t, (1, 20, 20, 72, 6), "bf16")
     d2t = [r for r in routes_t if r[3] == 24]

@@ -59,3 +59,26 @@ tot = sum(v[1] for v in agg.values())
 print(f"device time {tot/1e3:.1f} ms")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
     print(f"  {k:60s} n={v[0]:4d} {v[1]/1e3:8.2f} ms")
+
+# ---- the tiler on a domain of several such chunks (streamed driver: device-side crop + output
+# check, pinned D2H on a copy stream overlapped with the next chunk's generator pass)
+from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+dom = rng.standard_normal((40, 40, 72, 6)).astype(np.float32)
+topo_dom = rng.standard_normal((200, 200, 1)).astype(np.float32)
+def exo_dom():
+    return {"topography": {"steps": [{"model": 1, "combine_type": "layer", "data": topo_dom.copy(),
+                                      "s_enhance": 5, "t_enhance": 24}]}}
+for workers in (1, 2):
+    dts = []
+    for _ in range(2):
+        strat = ForwardPassStrategy(model=ms, input_handler=ArrayInputHandler(dom, feats),
+                                    fwp_chunk_shape=(20, 20, 72), spatial_pad=0, temporal_pad=0,
+                                    pass_workers=workers, exo_data=exo_dom())
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        outs = ForwardPass.run(strat, 0)
+        torch.cuda.synchronize(); dts.append(time.perf_counter() - t0)
+    n = strat.n_chunks
+    print(f"ForwardPass.run, {n} chunks of 20x20x72 (+ topography), pass_workers={workers} "
+          f"({'serial reference-shaped driver' if workers == 1 else 'streamed driver'}): "
+          f"{min(dts) / n * 1e3:.1f} ms wall per chunk -> {dom[..., 0].size / min(dts) / 1e3:.1f} k LR voxels/s")
+    del outs
