@@ -99,8 +99,13 @@ class ConvUmmaFn(torch.autograd.Function):
                 wk = make()
                 if wk.shape[-2] < 64:     # zero rows for the padded input channels
                     wk = torch.nn.functional.pad(wk, (0, 0, 0, 64 - wk.shape[-2]))
-                hit = (ver, *ops.pack_weights_umma(wk.contiguous(), ndim=nd,
-                                                   fmt=ops.S3_FMT_FP16C))
+                # cache["wmax"]: max |w| of the whole kernel for this weight version (set by
+                # Plan.forward_train for all layers with ONE host read per step); slices and
+                # flipped views share it (their own maximum can only be smaller)
+                wmax = cache.get("wmax")
+                hit = (ver, *ops.pack_weights_umma(
+                    wk.contiguous(), ndim=nd, fmt=ops.S3_FMT_FP16C,
+                    wmax=wmax[1] if (wmax is not None and wmax[0] == ver[0]) else None))
             cache[key] = hit
         return hit[1:]
 

@@ -186,9 +186,13 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
     S3_REQUIRE(ws >= 2 && ws <= 4, "s3_conv_fwd_umma: zring needs w_stages in [2, 4]");
     const uint32_t plane = 18u * (uint32_t)p.XB * 128u;
     // coalescing 16-bit epilogue: 8 warps x 2 KiB staging (see conv_umma_zring.cu)
+    // (nearest repeat along x, rep <= 4: the TMA epilogue stores every tile once per replica;
+    //  needs the y-halo rows by TMA, i.e. full 8-voxel x tiles)
+    const int xrep = g.rep[2];
+    const bool rep_ok = g.rep[0] == 1 && g.rep[1] == 1 && xrep >= 1 && xrep <= 4 &&
+                        (xrep == 1 || (g.in[2] % 8 == 0 && !(t.box_y & 1024) && !res_hi));
     const bool v2_shape = g.cout == 64 && g.cstride == 64 && g.coff == 0 && g.r == 1 && g.m == 1 &&
-                          g.rep[0] * g.rep[1] * g.rep[2] == 1 && g.fd[0] >= 4 && g.fd[1] >= 4 &&
-                          g.fd[2] >= 4 && !post_scale;
+                          rep_ok && g.fd[0] >= 4 && g.fd[1] >= 4 && g.in[2] >= 4 && !post_scale;
     p.epi_v4 = (v2_shape && y_hi && !y && !residual && !(t.box_y & 16) && (t.tiles <= 0 || t.tiles == 4) &&
                 p.planes >= 4) ? 1 : 0;
     S3_REQUIRE(!res_hi || p.epi_v4, "s3_conv_fwd_umma: a 16-bit residual pair needs the plain "
@@ -328,8 +332,29 @@ extern "C" int s3_conv_fwd_umma(const s3_conv_desc* d, const void* x_hi, const v
   if (zring) {
     CUtensorMap em[6];
     memset(em, 0, sizeof(em));
-    p.epi_row_tma = (p.epi_v4 && g.fd[2] % 8 == 0 && !(t.box_y & 1024)) ? 1 : 0;
-    if (p.epi_v4) {
+    p.epi_row_tma = (p.epi_v4 && g.in[2] % 8 == 0 && !(t.box_y & 1024)) ? 1 : 0;
+    if (p.epi_v4 && g.rep[2] > 1) {
+      // 5-D views: channel | replica rx | conv x | y | plane, output x = x * rep + rx.  Interior
+      // view (tiles) and a view whose y axis is the padded one (y-halo rows); both start one voxel
+      // into the padded x axis.
+      const int rep = g.rep[2];
+      const uint64_t row_pitch = (uint64_t)(g.fd[2] + 2) * 128;
+      const uint64_t estr[4] = {128, (uint64_t)rep * 128, row_pitch, (uint64_t)(g.fd[1] + 2) * row_pitch};
+      const uint64_t edims[5] = {64, (uint64_t)rep, (uint64_t)g.in[2], (uint64_t)g.fd[1], total_planes};
+      const uint64_t rdims[5] = {64, (uint64_t)rep, (uint64_t)g.in[2], (uint64_t)g.fd[1] + 2, total_planes};
+      const uint32_t ebox[5] = {32, 1, 8, 4, 1}, rbox[5] = {32, 1, 8, 1, 1};
+      const size_t shift = (size_t)row_pitch + 128, rshift = 128;
+      void* outs[2] = {y_hi, y_lo};
+      for (int i = 0; i < 2; ++i) {
+        if (!outs[i]) continue;
+        if ((rc = encode_map_strided(&em[2 + i], static_cast<uint8_t*>(outs[i]) + shift, t.fmt, 5,
+                                     edims, estr, ebox, CU_TENSOR_MAP_SWIZZLE_64B)))
+          return rc;
+        if ((rc = encode_map_strided(&em[4 + i], static_cast<uint8_t*>(outs[i]) + rshift, t.fmt, 5,
+                                     rdims, estr, rbox, CU_TENSOR_MAP_SWIZZLE_64B)))
+          return rc;
+      }
+    } else if (p.epi_v4) {
       // interior views (x + 1, y + 1) of the padded tensors: tile coordinates are plain voxel
       // indices, ragged tiles are clipped by the map extents
       const uint64_t edims[4] = {64, (uint64_t)g.fd[2], (uint64_t)g.fd[1], total_planes};

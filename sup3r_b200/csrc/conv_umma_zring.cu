@@ -26,7 +26,7 @@ namespace s3 {
 
 constexpr int kRingThreads = 384;    // WG0: TMA + MMA (+2 idle warps); WG1, WG2: epilogue
 constexpr int kRingThreadsV4 = 640;  // ... WG1..WG4: sixteen epilogue warps (EPI_V4)
-__host__ __device__ constexpr int ring_threads(int epi) { return epi == EPI_V4 ? kRingThreadsV4 : kRingThreads; }
+__host__ __device__ constexpr int ring_threads(int epi) { return epi_is_v4(epi) ? kRingThreadsV4 : kRingThreads; }
 constexpr int kRingMaxP = 8;
 constexpr int kRingMaxWS = 4;
 constexpr int RB_PFULL = 0;
@@ -246,7 +246,7 @@ __device__ __forceinline__ uint32_t stage64_off(int row, int k) {
 // residual hi, residual lo (TMA loads), output hi, output lo (TMA stores).  In the fp16c format
 // the "lo" 64 bytes of a 32-channel half are [lo8 x 32 | a8 x 32] (common.cuh), so the same
 // boxes and tensor maps serve both formats.
-template <bool kRes>
+template <bool kRes, bool kRep>
 __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const Epilogue& ep,
                                                       const float* sbias, uint32_t t_addr,
                                                       const TileGeom& tg, int plane_coord,
@@ -254,7 +254,11 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
                                                       bool prefetched) {
   const int fmt = ep.fmt;
   const bool corr = fmt == kFmtFp16c;
-  const int FY = g.fd[1], FX = g.fd[2];
+  // nearest repeat along x (SpatioTemporalExpansion, temporal_method "nearest"): conv voxel x
+  // becomes output voxels x * rep + rx; the tile is stored once per replica through 5-D maps
+  // whose x axis is split into (x, rx)
+  const int rep = kRep ? g.rep[2] : 1;
+  const int FY = g.fd[1], FX = g.in[2];
   const int yl = lane >> 3, xl = lane & 7;
   const int y = tg.y0 + yl, x = tg.x0 + xl;
   const bool row_valid = y < FY && x < FX;
@@ -280,9 +284,22 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
     if (kRes) issue_res(0, 0);
   }
 
-  const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * 128;
+  const long long row_off = tg.base + (long long)yl * tg.sy + (long long)xl * rep * 128;
   const long long my = y == 1 ? -2 * tg.sy : (y == FY - 2 ? 2 * tg.sy : 0);
-  const long long mx = x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL);
+  // REFLECT halo in x: output voxel 1 -> -1 and FX_out - 2 -> FX_out.  With a repeat >= 2 those
+  // are replicas of the first / last conv voxel: its row goes one voxel before its first /
+  // after its last replica.
+  const long long mx = !kRep ? (x == 1 ? -256LL : (x == FX - 2 ? 256LL : 0LL))
+                             : (x == 0 ? -128LL : (x == FX - 1 ? 128LL * rep : 0LL));
+  auto store_tile = [&](const CUtensorMap* m, uint32_t src, int c, int xc, int yc, int pc,
+                        bool padded_x) {
+    if (!kRep) {
+      tma_store_4d(m, src, c, xc + (padded_x ? 1 : 0), yc, pc);
+    } else {
+#pragma unroll 1
+      for (int rx = 0; rx < rep; ++rx) tma_store_5d(m, src, c, rx, xc, yc, pc);
+    }
+  };
   const long long mzb = (long long)mz_planes * tg.sz;
 
 #pragma unroll
@@ -370,9 +387,9 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(et.dbg & 64)) {
-          tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord);
+          store_tile(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord, false);
           if (mz_planes != 0)
-            tma_store_4d(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes);
+            store_tile(et.out[op], sbs, 32 * c2, tg.x0, tg.y0, plane_coord + mz_planes, false);
           if (row_tma) {
             // REFLECT halo rows y = -1 (copy of y = 1) and y = FY (copy of FY - 2): one 8-voxel
             // row of the box each, stored at the padded row index (and its z mirror)
@@ -382,9 +399,9 @@ __device__ __forceinline__ void ring_epilogue_warp_v4(const ConvGeom& g, const E
               if (yy >= tg.y0 && yy < tg.y0 + 4) {
                 const uint32_t src = sbs + (uint32_t)(yy - tg.y0) * 512u;
                 const int ypad = e == 0 ? 0 : FY + 1;
-                tma_store_4d(et.row[op], src, 32 * c2, tg.x0 + 1, ypad, plane_coord);
+                store_tile(et.row[op], src, 32 * c2, tg.x0, ypad, plane_coord, true);
                 if (mz_planes != 0)
-                  tma_store_4d(et.row[op], src, 32 * c2, tg.x0 + 1, ypad, plane_coord + mz_planes);
+                  store_tile(et.row[op], src, 32 * c2, tg.x0, ypad, plane_coord + mz_planes, true);
               }
             }
           }
@@ -646,7 +663,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(RB_ACCFULL + i), 1);
-      mbar_init(bar(RB_ACCEMPTY + i), EPI == EPI_V4 ? 16 : 8);
+      mbar_init(bar(RB_ACCEMPTY + i), epi_is_v4(EPI) ? 16 : 8);
     }
     for (int i = 0; i < 16; ++i) mbar_init(bar(RB_EPILD + i), 1);
     fence_barrier_init();
@@ -829,8 +846,8 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
   } else {
     // ------------------------------------------------------------------------------ epilogue
-    if (EPI == EPI_V4) reg_inc<104>(); else reg_inc<216>();
-    constexpr int kWgs = EPI == EPI_V4 ? 4 : 2;   // epilogue warpgroups
+    if (epi_is_v4(EPI)) reg_inc<104>(); else reg_inc<216>();
+    constexpr int kWgs = epi_is_v4(EPI) ? 4 : 2;   // epilogue warpgroups
     const int wg = (warp - 4) >> 2, q = warp & 3;
     int ab = 0, abph = 0;
     EpiTma et;
@@ -849,7 +866,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       const RingItem c = ring_decode(p, i, i0, i1);
       long long c0 = tr ? clock64() : 0;
       bool prefetched = false;
-      if (EPI == EPI_V4 && wg < c.ri && !(p.dbg_flags & 8)) {
+      if (epi_is_v4(EPI) && wg < c.ri && !(p.dbg_flags & 8)) {
         // the residual tile does not depend on the accumulator: start its first TMA load (and
         // retire the previous tile's stores) before waiting for the MMAs of this item
         if (lane == 0) tma_store_wait_read();
@@ -866,7 +883,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
       long long c1 = tr ? clock64() : 0;
       if (tr) t_wait += c1 - c0;
       tc_fence_after();
-      if (EPI == EPI_V4) {
+      if (epi_is_v4(EPI)) {
         if (!(p.dbg_flags & 8)) {
           const ConvGeom& g = p.g;
           TileGeom tg;
@@ -878,21 +895,24 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
             const int z = c.pl0 + r;
             const int plane_coord = c.b * (g.fd[0] + 2) + z + 1;
             tg.base = (((long long)plane_coord * (g.fd[1] + 2) + tg.y0 + 1) * (g.fd[2] + 2) +
-                       tg.x0 + 1) * 128;
+                       (long long)tg.x0 * (EPI == EPI_V4R ? g.rep[2] : 1) + 1) * 128;
             const int mzp = z == 1 ? -2 : (z == g.fd[0] - 2 ? 2 : 0);
             const uint32_t ta = tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)) +
                                 ((uint32_t)(q * 32) << 16);
-            if (p.ep.res_hi)
-              ring_epilogue_warp_v4<true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
-                                          prefetched);
+            if (EPI == EPI_V4R)
+              ring_epilogue_warp_v4<false, true>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
+                                                 prefetched);
+            else if (p.ep.res_hi)
+              ring_epilogue_warp_v4<true, false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
+                                                 prefetched);
             else
-              ring_epilogue_warp_v4<false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
-                                           prefetched);
+              ring_epilogue_warp_v4<false, false>(g, p.ep, sbias, ta, tg, plane_coord, mzp, et, lane,
+                                                  prefetched);
           }
         }
       } else if (!(p.dbg_flags & 8)) {
         for (int r = wg; r < c.ri; r += 2)
-          ring_epilogue_tile<EPI == EPI_V4 ? EPI_PLAIN : EPI>(
+          ring_epilogue_tile<epi_is_v4(EPI) ? EPI_PLAIN : EPI>(
               p, sbias, c, r, tmem_base + (uint32_t)(ab * R * npad + npad * (R - 1 - r)), q, lane);
       }
       tc_fence_before();
@@ -903,7 +923,7 @@ conv_umma_zring_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
     // the staging boxes must outlive the TMA stores that read them: retire this thread's bulk
     // groups before the CTA (and its shared memory) goes away
-    if (EPI == EPI_V4 && lane == 0) tma_store_wait_read();
+    if (epi_is_v4(EPI) && lane == 0) tma_store_wait_read();
     if (tr) { p.trace[8] = t_wait; p.trace[9] = t_work; }
   }
   tc_fence_before();
@@ -935,6 +955,8 @@ int launch_umma_zring(const UmmaParams& p, const CUtensorMap* maps /* a, w, a2, 
     em.res_hi = epi_maps[0]; em.res_lo = epi_maps[1]; em.y_hi = epi_maps[2]; em.y_lo = epi_maps[3];
     em.row_hi = epi_maps[4]; em.row_lo = epi_maps[5];
   }
+  if (p.epi_v4 && p.R == 4 && p.g.rep[2] > 1)
+    return launch_zring_t<4, EPI_V4R>(p, maps, em, ctas, smem, st);
   if (p.epi_v4 && p.R == 4) return launch_zring_t<4, EPI_V4>(p, maps, em, ctas, smem, st);
   if (epi == EPI_PLAIN && p.R == 4) return launch_zring_t<4, EPI_PLAIN>(p, maps, em, ctas, smem, st);
   if (epi == EPI_PLAIN) return launch_zring_t<0, EPI_PLAIN>(p, maps, em, ctas, smem, st);

@@ -11,7 +11,9 @@ namespace s3 {
 
 // epilogue specialisations (one per kernel instantiation keeps the SASS small: the generic
 // scatter is ~10x the code of the fast paths and would thrash the instruction cache)
-enum { EPI_PLAIN = 0, EPI_D2S = 1, EPI_GENERIC = 2, EPI_V2 = 3, EPI_V3 = 4, EPI_D2S16 = 5, EPI_V4 = 6 };  // zring: V2 LSU-coalescing, V3 TMA tile I/O
+enum { EPI_PLAIN = 0, EPI_D2S = 1, EPI_GENERIC = 2, EPI_V2 = 3, EPI_V3 = 4, EPI_D2S16 = 5, EPI_V4 = 6,
+       EPI_V4R = 7 };   // V4R: V4 with nearest repeat along x (one TMA store per replica)
+__host__ __device__ constexpr bool epi_is_v4(int epi) { return epi == EPI_V4 || epi == EPI_V4R; }  // zring: V2 LSU-coalescing, V3 TMA tile I/O
 
 struct RowPlan {
   bool valid, slow;

@@ -271,7 +271,7 @@ def _dt16(fmt):
     return torch.bfloat16 if fmt == S3_FMT_BF16 else torch.float16
 
 
-def pack_weights_umma(w, split=False, fmt=0, ndim=None):
+def pack_weights_umma(w, split=False, fmt=0, ndim=None, wmax=None):
     """keras kernel ``(*k, 64, cout)`` f32 -> packed 16-bit (hi, lo|None) in the layout the
     tcgen05 kernel wants for this rank / cout (``s3_umma_weight_layout``).  ``fmt`` 2 (fp16c):
     -> (hi, corr, acc_scale): fp16 weights scaled by a power of two S with max|w| S in
@@ -286,7 +286,9 @@ def pack_weights_umma(w, split=False, fmt=0, ndim=None):
     if fmt == S3_FMT_FP16C:
         import math
         layout = _cabi.load().s3_umma_weight_layout(ndim, cout, 0)
-        wmax = float(w.abs().max())
+        # (``wmax``: max |w| when the caller already knows it -- the reduction + host read is a
+        #  device sync, which the training step pays once per network instead of once per layer)
+        wmax = float(w.abs().max()) if wmax is None else float(wmax)
         scale = 2.0 ** math.floor(math.log2(16383.0 / wmax)) if wmax > 0 else 1.0
         scale = min(max(scale, 2.0 ** -24), 2.0 ** 24)
         hi = torch.empty((taps, npad, cin), device=w.device, dtype=torch.float16)

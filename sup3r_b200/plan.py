@@ -386,8 +386,9 @@ class Plan:
         # (phygnn SkipConnection semantics, call site sup3r/models/abstract.py:1081-1092)
         # (only the 3-D ring kernel's epilogue takes the pair back as a residual: elsewhere the
         # cache is written as f32 next to the 16-bit operand tensor)
-        pair_skip = (want16 and bool(st.skip_store) and self._ring16_ok(st, out_shape)
-                     and (c_mode or not split))
+        pair_ok = (len(out_shape) == 5 and out_shape[-1] == 64 and st.r == 1
+                   and (st.m == 1 or st.method == 0) and min(out_shape[1:-1]) >= 4)
+        pair_skip = want16 and bool(st.skip_store) and pair_ok and (c_mode or not split)
         want32 = (not want16) or last or (bool(st.skip_store) and not pair_skip)
         bias = conv.bias.value.detach() if conv.bias is not None else None
         if os.environ.get("SUP3R_B200_TRACE_PLAN"):
@@ -555,6 +556,23 @@ class Plan:
                 and conv.filters % 64 == 0 and conv.filters <= 512
                 and all(k == 3 for k in conv.kernel_size) and min(in_shape[1:-1]) >= 2)
 
+    def _refresh_weight_maxima(self):
+        """max |w| of every convolution kernel whose weights changed since the last call, with ONE
+        device -> host read for the whole network (the fp16c weight packing needs it to pick its
+        power-of-two scale; per layer it would be a sync per layer and step)."""
+        stale = []
+        for st in self.steps:
+            if isinstance(st, FusedConv) and st.conv.built:
+                cache = st.conv.__dict__.setdefault("_umma_train_cache", {})
+                hit = cache.get("wmax")
+                if hit is None or hit[0] != st.conv.kernel.version:
+                    stale.append((st.conv, cache))
+        if stale:
+            with torch.no_grad():
+                vals = torch.stack([c.kernel.value.detach().abs().max() for c, _ in stale]).cpu()
+            for (conv, cache), v in zip(stale, vals.tolist()):
+                cache["wmax"] = (conv.kernel.version, float(v))
+
     # -- training forward (autograd) -------------------------------------------------
     def forward_train(self, x, exo=None):
         """Differentiable forward on the fp32 kernels: the same fused steps, each wrapped in
@@ -567,6 +585,8 @@ class Plan:
         exo = exo or {}
         if not net.built:
             net.build(tuple(x.shape), {k: v.shape[-1] for k, v in exo.items()})
+        if tensor_cores:
+            self._refresh_weight_maxima()
         skips = {}
         cur = x
         for st in self.steps:

@@ -599,7 +599,10 @@ FP16C_CASES = [
     (1, (6, 9, 17), "pad16"),            # planes % 4 != 0 -> generic two-pass MMA role
     (1, (16, 16, 24), "f32"),            # fp32 destination (thread-per-row epilogue)
     (1, (8, 16, 24), "res_f32"),
-    (1, (8, 16, 8), "rep3"),             # nearest repeat x3 with (hi, corr) output
+    (1, (8, 16, 8), "rep3"),             # nearest repeat x3 with (hi, corr) output (TMA epilogue,
+    (2, (16, 16, 24), "rep2"),           #   one store per replica through 5-D maps)
+    (1, (4, 20, 16), "rep2"),            # ragged y tile
+    (1, (6, 16, 12), "rep3"),            # x % 8 != 0 / planes % 4 != 0 -> thread-per-row epilogue
 ]
 
 
@@ -613,7 +616,7 @@ def test_umma_conv_fp16c_matches_float64(cuda, n, dims, variant):
     x = rng_arr(rng, (n, *dims, 64))
     w = rng_arr(rng, (3, 3, 3, 64, 64), 0.05)
     b = rng_arr(rng, (64,), 0.1)
-    rep = 3 if variant == "rep3" else 1
+    rep = int(variant[3:]) if variant.startswith("rep") else 1
     odims = (dims[0], dims[1], dims[2] * rep)
     res = rng_arr(rng, (n, *odims, 64))
     xd, wd, bd, rd = dev(x, cuda), dev(w, cuda), dev(b, cuda), dev(res, cuda)
