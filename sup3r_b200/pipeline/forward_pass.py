@@ -35,9 +35,9 @@ class ForwardPass:
         self.model = strategy.get_model()
         self.node_index = node_index
         out = strategy.out_pattern
-        assert out is None or out.endswith(".npy"), (
-            f"Received bad output type {out}: sup3r_b200 writes .npy chunk files (h5 / nc "
-            "writers are out of scope)")
+        assert out is None or out.endswith((".npy", ".nc")), (
+            f"Received bad output type {out}: sup3r_b200 writes .npy or .nc chunk files (the h5 "
+            "writer is out of scope)")
 
     def get_input_chunk(self, chunk_index=0, mode="reflect"):
         """Chunk with its extra edge padding applied (forward_pass.py:67-74)."""
@@ -51,7 +51,9 @@ class ForwardPass:
         return {"node_index": self.node_index,
                 "creation_date": dt.now().strftime("%d/%m/%Y %H:%M:%S"),
                 "model_meta": self.model.meta, "gan_params": self.model.model_params,
-                "strategy_meta": self.strategy.meta}
+                "strategy_meta": self.strategy.meta,
+                "model_meta_features": list(self.model.hr_out_features),
+                "full_hr_shape": [int(v) for v in self.strategy.hr_lat_lon.shape[:2]]}
 
     def _get_step_enhance(self, step):
         """Enhancement of an exo step's data relative to the low-res input
@@ -395,6 +397,17 @@ class ForwardPass:
 
     @staticmethod
     def _write_output(data, chunk, meta):
+        if chunk.out_file.endswith(".nc"):
+            # writers/nc.py:19-100 (the device-side transforms already ran when
+            # strategy.postprocess is set: ``chunk.features`` then holds the renamed features)
+            from .writers import OutputHandlerNC
+            feats = getattr(chunk, "features", None) or meta["model_meta_features"]
+            attrs = {k: v for k, v in meta.items() if k != "model_meta_features"}
+            attrs["full_hr_shape"] = meta.get("full_hr_shape")
+            OutputHandlerNC._write_output(np.asarray(data, np.float32), feats, chunk.hr_lat_lon,
+                                          chunk.hr_times, chunk.out_file, meta_data=attrs,
+                                          gids=chunk.gids, transform=False)
+            return
         np.save(chunk.out_file, data)
         import json
         from ..utilities import safe_cast
