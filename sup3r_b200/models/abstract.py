@@ -609,8 +609,9 @@ class AbstractSingleModel(TensorboardMixIn):
                 from .base import ScaleFnScalar
                 grad = torch.autograd.grad(ScaleFnScalar.apply(loss, scale), tensors,
                                            allow_unused=True)
-                inv = 1.0 / scale
-                grad = [None if g is None else g.mul_(inv) for g in grad]
+                have = [g for g in grad if g is not None]
+                if have:
+                    torch._foreach_mul_(have, 1.0 / scale)     # one multi-tensor launch
             else:
                 grad = torch.autograd.grad(loss, tensors, allow_unused=True)
         grad = [g if g is not None else torch.zeros_like(t) for g, t in zip(grad, tensors)]

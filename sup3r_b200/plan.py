@@ -568,8 +568,10 @@ class Plan:
                 if hit is None or hit[0] != st.conv.kernel.version:
                     stale.append((st.conv, cache))
         if stale:
-            with torch.no_grad():
-                vals = torch.stack([c.kernel.value.detach().abs().max() for c, _ in stale]).cpu()
+            with torch.no_grad():   # multi-tensor inf-norm: a couple of launches for all kernels
+                norms = torch._foreach_norm([c.kernel.value.detach() for c, _ in stale],
+                                            float("inf"))
+                vals = torch.stack([n.reshape(()) for n in norms]).cpu()
             for (conv, cache), v in zip(stale, vals.tolist()):
                 cache["wmax"] = (conv.kernel.version, float(v))
 
