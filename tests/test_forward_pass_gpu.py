@@ -203,3 +203,75 @@ def test_forward_pass_postprocess_on_device(cuda):
             assert np.abs(got[..., 0] - ws[..., 0]).max() < 1e-4
             dwd = np.abs(got[..., 1] - ws[..., 1])
             assert np.minimum(dwd, 360 - dwd).max() < 2e-2
+
+
+def test_three_step_chain_sup3rwind_shape(cuda):
+    """BASELINE configs[3](i) / tests/forward_pass/test_multi_step.py:61-127: 3x spatial (4-D) ->
+    5x spatial (4-D) -> 12x temporal (5-D), 6 features, as one MultiStepGan."""
+    from sup3r_b200.models import MultiStepGan
+    feats = [f"f{i}" for i in range(6)]
+    meta = lambda s, t: {"lr_features": feats, "hr_out_features": feats, "s_enhance": s,
+                         "t_enhance": t}
+    m1 = make_model(C.spatial_generator(6, (3,), n_blocks=1, filters=16),
+                    C.discriminator(2, "same", (8,)), (4, 4, 4, 6), meta=meta(3, 1))
+    m2 = make_model(C.sup3rcc_spatial_generator(6, 5, 2, filters=16),
+                    C.discriminator(2, "same", (8,)), (4, 12, 12, 6), seed=2, meta=meta(5, 1))
+    m3 = make_model(C.spatiotemporal_generator(6, 1, (2, 2, 3), n_blocks=1, head_filters=16,
+                                               filters=16),
+                    C.discriminator(3, "same", (8,)), (1, 60, 60, 4, 6), seed=4, meta=meta(1, 12))
+    ms = MultiStepGan([m1, m2, m3])
+    assert ms.s_enhance == 15 and ms.t_enhance == 12
+    assert ms.s_enhancements == [3, 5, 1] and ms.t_enhancements == [1, 1, 12]
+    x = np.random.default_rng(0).standard_normal((4, 4, 4, 6)).astype(np.float32)
+    y = ms.generate(x)
+    assert y.shape == (1, 60, 60, 48, 6) and y.dtype == np.float32 and np.isfinite(y).all()
+    a = m2.generate(m1.generate(x))
+    want = m3.generate(np.ascontiguousarray(np.transpose(a, (1, 2, 0, 3))[None]))
+    assert np.array_equal(y, want)
+
+
+def test_end_to_end_train_save_load_forward_pass_collect(cuda, tmp_path):
+    """tests/training/test_end_to_end.py + tests/pipeline/test_pipeline.py in miniature, every
+    stage on this library: on-device batch handler -> train 2 epochs -> save -> load ->
+    ForwardPass over a chunked domain with device-side post-processing -> .nc chunk files ->
+    collection; the collected field follows generate() on the whole (unchunked) domain."""
+    import os
+    import warnings
+    from sup3r_b200.batch import DeviceBatchHandler
+    from sup3r_b200.models import Sup3rGan
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    from sup3r_b200.pipeline.writers import CollectorNC, read_nc
+    rng = np.random.default_rng(3)
+    feats = ["temperature_2m", "relativehumidity_2m"]
+    base = rng.standard_normal((6, 6, 8, 2))
+    hr = (np.repeat(np.repeat(np.repeat(base, 4, 0), 4, 1), 4, 2) * [5, 10] + [15, 50]).astype(np.float32)
+    bh = DeviceBatchHandler(hr, feats, sample_shape=(12, 12, 8), batch_size=4, n_batches=3,
+                            s_enhance=2, t_enhance=2, temporal_coarsening_method="average")
+    Sup3rGan.seed(0)
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1, filters=16),
+                 C.discriminator(3, "same", (8,)), learning_rate=2e-3)
+    out_dir = str(tmp_path / "gan_{epoch}")
+    m.train(bh, {"spatial": "8km", "temporal": "60min"}, n_epoch=2, weight_gen_advers=1e-3,
+            train_gen=True, train_disc=True, disc_loss_bounds=(-1.0, 100.0), out_dir=out_dir)
+    loaded = Sup3rGan.load(out_dir.format(epoch=1))
+    assert loaded.means["temperature_2m"] == pytest.approx(float(hr[..., 0].mean()), rel=1e-4)
+    assert loaded.meta["s_enhance"] == 2 and loaded.meta["t_enhance"] == 2
+    lr = (rng.standard_normal((12, 12, 16, 2)) * [5, 10] + [15, 50]).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        strat = ForwardPassStrategy(
+            model=loaded, input_handler=ArrayInputHandler(lr, feats), fwp_chunk_shape=(6, 6, 16),
+            spatial_pad=3, temporal_pad=0, pass_workers=2, postprocess=True, nn_fill=False,
+            out_pattern=str(tmp_path / "fwp_{file_id}.nc"), pad_mode="reflect")
+        ForwardPass.run(strat, 0)
+    assert strat.n_chunks == 4 and all(os.path.exists(f) for f in strat.out_files)
+    full = read_nc(CollectorNC.collect(str(tmp_path / "fwp_*.nc"), str(tmp_path / "full.nc")))
+    t2m = full["features"]["temperature_2m"]
+    assert t2m.shape == (32, 24, 24) and np.isfinite(t2m).all()
+    whole = loaded.generate(lr[None])[0]                       # (24, 24, 32, 2), unchunked
+    whole = np.clip(whole, [-200, 0], [100, 100])              # the writer-side limits
+    got = np.transpose(t2m, (1, 2, 0))
+    # (the 3-voxel halo is shorter than this generator's receptive field, so chunked and unchunked
+    #  fields agree on average, not voxel by voxel: the exact statement is
+    #  test_forward_pass_chunked_close_to_unchunked)
+    assert np.abs(got - whole[..., 0]).mean() < 0.05 * np.abs(whole[..., 0]).mean()
