@@ -132,4 +132,6 @@ def check(rc, what=""):
 
 def call(name, *args):
     """Call ``name`` and raise on a non-zero status."""
-    check(getattr(load(), name)(*args), name)
+    rc = getattr(_lib or load(), name)(*args)
+    if rc != 0:
+        check(rc, name)

@@ -45,7 +45,14 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _s():
+    """The current CUDA stream of the current device as a cudaStream_t (every launch takes it:
+    the raw-handle query is ~20x cheaper than building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
