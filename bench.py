@@ -504,8 +504,15 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r02_body_conv_traffic.json" if c_mode
                           else "r01_body_conv_traffic.json")
+        traffic_note = None
         if os.path.exists(tp):
+            # ncu --set full capture of a launch over 8 chunks (profiles/): DRAM bytes are
+            # linear in the voxels of a launch -> scaled to this launch's n chunks
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            if traffic is not None:
+                traffic = float(traffic) * n / 8.0
+                traffic_note = ("dram__bytes_read + write of the 8-chunk ncu capture x n / 8 "
+                                "(launch mix 17 plain + 16 residual)")
         kname = ("conv_umma_zring_kernel<4, EPI_V4> (fp16 pass + e4m3 correction pass)" if c_mode
                  else ("conv_umma_tile_kernel (split operands, 3 MMA passes)" if split
                        else "conv_umma_zring_kernel<4, EPI_V4>"))
@@ -513,6 +520,10 @@ def main():
                 f"conv, {n}x16x16x288 voxels, 16-bit padded in/out; launch mix of the model step: "
                 f"{n_plain} plain + {n_res} residual launches)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": float(n) * np.prod(dims) * (
+                    (256 + 256) * n_plain + (256 + 256 + 256) * n_res) / (n_plain + n_res)
+                if c_mode else None,
                 "peak_source": f"{peaks_src} bf16_tflops (burst: kernel timed in isolation)",
                 "frac_of_sustained_peak": achieved / peak_sus, "kernel_ms": k_ms,
                 "kernel_ms_plain": ms_plain, "kernel_ms_residual": ms_res,
