@@ -299,6 +299,13 @@ int s3_gauss_smooth2d(const float* x, float* tmp, float* y, int n, int s1, int s
  * (the device-resident stand-in for sup3r/preprocessing/samplers/base.py get_next). */
 int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int* origins, int n,
                       int s1, int s2, int t, float* out, s3_stream stream);
+/* Gradient SUM over NVLink peer memory (sup3r/models/abstract.py:785-805 _sum_parallel_grad):
+ * out[i] = peer_ptrs[0][i] + peer_ptrs[1][i] + ... in RANK ORDER (deterministic, identical on
+ * every rank).  peer_ptrs: HOST array of `world` device pointers, one per rank, to the ranks' flat
+ * fp32 arenas in symmetric (peer-mapped) memory; the caller brackets the call with cross-GPU
+ * barriers (arenas written / arenas read).  n: floats, a multiple of 4. */
+int s3_peer_sum_f32(const void* const* peer_ptrs, int world, size_t n, float* out,
+                    s3_stream stream);
 
 #ifdef __cplusplus
 }

@@ -219,3 +219,47 @@ extern "C" int s3_gather_samples(const float* data, int S1, int S2, int T, int F
   S3_LAUNCH_CHECK("gather_samples");
   return S3_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Gradient all-reduce over NVLink peer memory (sup3r/models/abstract.py:785-805 _sum_parallel_grad:
+// the SUM of the per-GPU gradients).  Every rank's flat fp32 gradient arena lives in symmetric
+// memory (peer-mapped through NVSwitch); after a cross-GPU barrier each rank reads ALL arenas with
+// plain P2P loads and adds them IN RANK ORDER -- the same order on every rank, so the result is
+// bit-identical everywhere and equals the reference's sequential sum over the shards.
+namespace s3 {
+
+struct PeerPtrs {
+  const float4* p[16];
+};
+
+__global__ void peer_sum_kernel(PeerPtrs pp, int world, size_t n4, float4* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = __ldcg(pp.p[0] + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 v = __ldcg(pp.p[r] + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
+
+}  // namespace s3
+
+extern "C" int s3_peer_sum_f32(const void* const* peer_ptrs, int world, size_t n, float* out,
+                               s3_stream stream) {
+  S3_REQUIRE(peer_ptrs && out && world >= 1 && world <= 16, "s3_peer_sum_f32: 1 <= world <= 16");
+  S3_REQUIRE(n % 4 == 0, "s3_peer_sum_f32: n must be a multiple of 4 floats (pad the arena)");
+  s3::PeerPtrs pp;
+  for (int r = 0; r < world; ++r) {
+    S3_REQUIRE(peer_ptrs[r] && (reinterpret_cast<uintptr_t>(peer_ptrs[r]) & 15) == 0,
+               "s3_peer_sum_f32: peer pointer %d is null or not 16-byte aligned", r);
+    pp.p[r] = static_cast<const float4*>(peer_ptrs[r]);
+  }
+  const size_t n4 = n / 4;
+  if (n4)
+    s3::peer_sum_kernel<<<s3::pgrid(n4), 256, 0, as_stream(stream)>>>(
+        pp, world, n4, reinterpret_cast<float4*>(out));
+  S3_LAUNCH_CHECK("peer_sum");
+  return S3_OK;
+}

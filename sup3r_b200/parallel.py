@@ -93,12 +93,80 @@ def _arena_for(grads):
     return hit
 
 
+_peer_arenas = {}
+_peer_state = {"enabled": None}
+
+
+class PeerArena:
+    """Flat fp32 gradient arena in symmetric (NVLink peer-mapped) memory + a local result buffer.
+    ``torch.distributed._symmetric_memory`` only does the plumbing (allocation, exchange of the
+    peer mappings, the cross-GPU barrier on its signal pads); the reduction itself is this
+    library's kernel (``s3_peer_sum_f32``): every rank reads all arenas over NVLink and adds them
+    in rank order -- deterministic and bit-identical on all ranks."""
+
+    def __init__(self, grads):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = grads[0].device
+        n = sum(g.numel() for g in grads)
+        self.n = (n + 3) // 4 * 4
+        self.arena = symm_mem.empty(self.n, dtype=torch.float32, device=dev)
+        self.arena.zero_()
+        self.handle = symm_mem.rendezvous(self.arena, dist.group.WORLD)
+        self.world = self.handle.world_size
+        ptrs = list(self.handle.buffer_ptrs)
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.out = torch.empty(self.n, device=dev, dtype=torch.float32)
+        self.in_views, self.out_views, off = [], [], 0
+        for g in grads:
+            self.in_views.append(self.arena[off:off + g.numel()].view(g.shape))
+            self.out_views.append(self.out[off:off + g.numel()].view(g.shape))
+            off += g.numel()
+
+    def allreduce(self, grads):
+        from . import _cabi, ops
+        torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
+        self.handle.barrier(channel=0)          # every rank's arena is written
+        _cabi.call("s3_peer_sum_f32", self._ptrs, self.world, self.n,
+                   ops._p(self.out), ops._s())
+        ops._count()
+        self.handle.barrier(channel=1)          # every rank has read every arena
+        return self.out_views
+
+
+def peer_allreduce_enabled():
+    """NVLink peer-memory gradient reduction: on for the NCCL backend unless
+    ``SUP3R_B200_PEER_ALLREDUCE=0`` (falls back to ``dist.all_reduce`` when symmetric memory
+    cannot be set up, e.g. no P2P access between the GPUs)."""
+    import os
+    if _peer_state["enabled"] is None:
+        _peer_state["enabled"] = (os.environ.get("SUP3R_B200_PEER_ALLREDUCE", "1") != "0"
+                                  and is_distributed() and dist.get_backend() == "nccl")
+    return _peer_state["enabled"]
+
+
 def allreduce_sum_grads(grads):
     """SUM all-reduce of a list of gradient tensors through one persistent flat arena (one
-    collective per step).  Returns the reduced gradients as VIEWS of the arena (no copy back):
-    valid until the next call with the same shapes."""
+    exchange per step).  Returns the reduced gradients as VIEWS of a persistent buffer (no copy
+    back): valid until the next call with the same shapes.  On NVLink-connected GPUs the arena is
+    symmetric memory and the sum is this library's peer-memory kernel (``PeerArena``); otherwise
+    one NCCL / gloo all-reduce."""
     if not is_distributed() or world_size() == 1:
         return grads
+    if peer_allreduce_enabled() and grads[0].is_cuda:
+        key = (str(grads[0].device), tuple(tuple(g.shape) for g in grads))
+        pa = _peer_arenas.get(key)
+        if pa is None:
+            try:
+                pa = _peer_arenas[key] = PeerArena(grads)
+            except Exception as e:   # pragma: no cover - no P2P / symmetric memory
+                import logging
+                logging.getLogger(__name__).warning(
+                    "symmetric-memory gradient arena unavailable (%s): using NCCL all-reduce", e)
+                _peer_state["enabled"] = False
+                pa = None
+        if pa is not None:
+            return pa.allreduce(grads)
     flat, views = _arena_for(grads)
     torch._foreach_copy_(views, [g.detach() for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)

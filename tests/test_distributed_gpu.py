@@ -60,7 +60,15 @@ def _worker(rank, world, port, q):
         g0, _ = m.get_single_grad(parallel.shard_batch(lr0), parallel.shard_batch(hr0),
                                   m.generator_weights, weight_gen_advers=1e-2, train_gen=True,
                                   train_disc=False, compute_disc=True)
-        g0 = [g.clone().cpu().numpy() for g in parallel.allreduce_sum_grads(g0)]
+        nccl = [g.clone() for g in g0]
+        for t in nccl:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        g0 = [g.clone() for g in parallel.allreduce_sum_grads(g0)]
+        # the NVLink peer-memory reduction (rank-order sum) equals the NCCL all-reduce bit for bit
+        # on two ranks (a + b is commutative)
+        assert all(torch.equal(a, b) for a, b in zip(g0, nccl)), "peer sum != NCCL all-reduce"
+        peer_path = bool(parallel._peer_state["enabled"])
+        g0 = [g.cpu().numpy() for g in g0]
         hist = []
         for lr, hr in _batches():
             d1 = m.run_gradient_descent(lr, hr, m.generator_weights, optimizer=m.optimizer,
@@ -90,7 +98,7 @@ def _worker(rank, world, port, q):
         t = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            q.put(("ok", (w, g0), hist, float(t.item())))
+            q.put(("ok", (w, g0, peer_path), hist, float(t.item())))
     except Exception as e:  # pragma: no cover
         import traceback
         q.put(("error", repr(e) + traceback.format_exc(), None, None))
@@ -112,7 +120,9 @@ def test_two_rank_nccl_training_matches_split_batch_reference(cuda):
     for p in procs:
         p.join(timeout=60)
     assert status == "ok", payload
-    w2, g2 = payload
+    w2, g2, peer_path = payload
+    print("gradient exchange:", "NVLink peer-memory sum kernel (symmetric memory)" if peer_path
+          else "NCCL all-reduce")
 
     # single-process statement of _get_parallel_grad / _sum_parallel_grad: the shards of each
     # batch one after the other, gradients summed, one optimiser step, last shard's details
