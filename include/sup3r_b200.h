@@ -306,6 +306,13 @@ int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int
  * barriers (arenas written / arenas read).  n: floats, a multiple of 4. */
 int s3_peer_sum_f32(const void* const* peer_ptrs, int world, size_t n, float* out,
                     s3_stream stream);
+/* The optimiser step fused into the gradient exchange: for every tensor of the table
+ * g = sum over ranks (rank order) of the gradient arenas at [off, off + n), then the keras Adam
+ * update of s3_adam_step on (p, m, v) -- one launch for the whole network.  segs_dev: DEVICE array
+ * of n_seg records {float* p, m, v; uint64 off, n}; max_n: the largest n; step: 1-based. */
+int s3_peer_sum_adam(const void* const* peer_ptrs, int world, const void* segs_dev, int n_seg,
+                     unsigned long long max_n, float lr, float beta1, float beta2, float eps,
+                     long long step, s3_stream stream);
 
 #ifdef __cplusplus
 }

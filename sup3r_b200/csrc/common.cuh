@@ -281,4 +281,15 @@ __device__ __forceinline__ float finish(const ConvGeom& g, const Epilogue& ep, f
   return v;
 }
 
+// keras Adam update of one element (one definition for the plain and the fused peer-sum kernels so
+// that both round identically): lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is computed on the host
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float lr_t,
+                                            float b1, float b2, float eps) {
+  const float mi = m + (g - m) * (1.f - b1);
+  const float vi = v + (g * g - v) * (1.f - b2);
+  m = mi;
+  v = vi;
+  p -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
 }  // namespace s3

@@ -445,12 +445,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             float b1, float b2, float eps) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-    const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], lr_t, b1, b2, eps);
     m[i] = mi;
     v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
   }
 }
 

@@ -244,7 +244,58 @@ __global__ void peer_sum_kernel(PeerPtrs pp, int world, size_t n4, float4* __res
   }
 }
 
+// The optimiser step fused into the exchange: one launch reads every rank's gradient arena over
+// NVLink (rank-order sum) and applies keras Adam to all weight tensors of the network -- the summed
+// gradient never goes back to HBM and the ~100 per-tensor Adam launches disappear.
+struct AdamSeg {
+  float* p; float* m; float* v;
+  unsigned long long off, n;     // position of this tensor's gradient in the arenas
+};
+
+struct PeerPtrs1 {
+  const float* p[16];
+};
+
+__global__ void peer_sum_adam_kernel(PeerPtrs1 pp, int world, const AdamSeg* __restrict__ segs,
+                                     float lr_t, float b1, float b2, float eps) {
+  const AdamSeg sg = segs[blockIdx.x];     // (x = table entry: up to 2^31 - 1 of them)
+  for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < sg.n;
+       i += (size_t)gridDim.y * blockDim.x) {
+    float g = __ldcg(pp.p[0] + sg.off + i);
+    for (int r = 1; r < world; ++r) g += __ldcg(pp.p[r] + sg.off + i);
+    float pi = sg.p[i], mi = sg.m[i], vi = sg.v[i];
+    adam_update(pi, mi, vi, g, lr_t, b1, b2, eps);
+    sg.m[i] = mi;
+    sg.v[i] = vi;
+    sg.p[i] = pi;
+  }
+}
+
 }  // namespace s3
+
+extern "C" int s3_peer_sum_adam(const void* const* peer_ptrs, int world, const void* segs_dev,
+                                int n_seg, unsigned long long max_n, float lr, float beta1,
+                                float beta2, float eps, long long step, s3_stream stream) {
+  S3_REQUIRE(peer_ptrs && segs_dev && world >= 1 && world <= 16 && n_seg >= 1 && step >= 1,
+             "s3_peer_sum_adam: bad arguments");
+  s3::PeerPtrs1 pp;
+  for (int r = 0; r < world; ++r) {
+    S3_REQUIRE(peer_ptrs[r] != nullptr, "s3_peer_sum_adam: peer pointer %d is null", r);
+    pp.p[r] = static_cast<const float*>(peer_ptrs[r]);
+  }
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) /
+                      (1.0 - pow((double)beta1, (double)step));
+  unsigned bx = (unsigned)((max_n + 255) / 256);
+  unsigned cap = (unsigned)(sm_count() * 16 / (n_seg < 1 ? 1 : n_seg)) + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  if (bx > 65535u) bx = 65535u;
+  dim3 grid((unsigned)n_seg, bx);
+  s3::peer_sum_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      pp, world, static_cast<const s3::AdamSeg*>(segs_dev), (float)lr_t, beta1, beta2, eps);
+  S3_LAUNCH_CHECK("peer_sum_adam");
+  return S3_OK;
+}
 
 extern "C" int s3_peer_sum_f32(const void* const* peer_ptrs, int world, size_t n, float* out,
                                s3_stream stream) {

@@ -445,13 +445,15 @@ class AbstractSingleModel(TensorboardMixIn):
             grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
                                                       device_name=self.default_device,
                                                       **calc_loss_kwargs)
-            grad = parallel.allreduce_sum_grads(grad)
             loss_details = parallel.broadcast_loss_details(loss_details)
+            # SUM of the shard gradients + one optimiser step (fused into one NVLink peer-memory
+            # kernel when the optimiser is this library's Adam)
+            parallel.sum_grads_and_step(grad, training_weights, optimizer)
         else:
             grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
                                                       device_name=self.default_device,
                                                       **calc_loss_kwargs)
-        optimizer.apply_gradients(zip(grad, training_weights))
+            optimizer.apply_gradients(zip(grad, training_weights))
         logger.debug("Finished single gradient descent step in %.4f seconds", time.time() - t0)
         return loss_details
 

@@ -53,6 +53,15 @@ class Adam:
             out.append(_OptVar(f"{self.name}/v/{base}:0", v))
         return out
 
+    def slots_for(self, var):
+        """(m, v) moment tensors of a weight (created on first use)."""
+        slot = self._slots.get(id(var))
+        if slot is None:
+            w = var.value
+            slot = (torch.zeros_like(w), torch.zeros_like(w), var.name)
+            self._slots[id(var)] = slot
+        return slot[0], slot[1]
+
     def apply_gradients(self, grads_and_vars):
         """``grads_and_vars``: iterable of (grad tensor, Variable)."""
         self.iterations += 1

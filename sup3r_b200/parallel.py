@@ -15,6 +15,8 @@ gloo in CPU tests).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -123,6 +125,42 @@ class PeerArena:
             self.out_views.append(self.out[off:off + g.numel()].view(g.shape))
             off += g.numel()
 
+    def sum_and_apply_adam(self, grads, weights, optimizer):
+        """The exchange and the optimiser step in ONE kernel (``s3_peer_sum_adam``): every rank
+        adds all gradient arenas in rank order and applies keras Adam to its own (replicated)
+        weights; the summed gradient never goes back to memory."""
+        import numpy as np
+        from . import _cabi, ops
+        slots = [optimizer.slots_for(var) for var in weights]
+        key = tuple((var.value.data_ptr(), m.data_ptr(), v.data_ptr())
+                    for var, (m, v) in zip(weights, slots))
+        if getattr(self, "_seg_key", None) != key:
+            # one table entry per <= 4096-element piece of a tensor (one CTA each), so that the
+            # big dense / conv kernels spread over the whole GPU
+            rows, off, piece = [], 0, 4096
+            for (wp, mp, vp), g, var in zip(key, grads, weights):
+                if not var.value.is_contiguous() or var.value.dtype != torch.float32:
+                    raise ValueError(f"fused Adam needs contiguous float32 weights ({var.name})")
+                for s0 in range(0, g.numel(), piece):
+                    rows.append((wp + 4 * s0, mp + 4 * s0, vp + 4 * s0, off + s0,
+                                 min(piece, g.numel() - s0)))
+                off += g.numel()
+            rec = np.array(rows, dtype=np.uint64)
+            self._segs = torch.from_numpy(rec.view(np.int64)).to(self.arena.device)
+            self._n_seg, self._max_n = len(rows), piece
+            self._seg_key = key
+        torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
+        optimizer.iterations += 1
+        self.handle.barrier(channel=0)          # every rank's arena is written
+        _cabi.call("s3_peer_sum_adam", self._ptrs, self.world, ops._p(self._segs), self._n_seg,
+                   self._max_n, float(optimizer.learning_rate), float(optimizer.beta_1),
+                   float(optimizer.beta_2), float(optimizer.epsilon), int(optimizer.iterations),
+                   ops._s())
+        ops._count()
+        self.handle.barrier(channel=1)          # every rank has read every arena
+        for var in weights:
+            var.version += 1
+
     def allreduce(self, grads):
         from . import _cabi, ops
         torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
@@ -145,6 +183,38 @@ def peer_allreduce_enabled():
     return _peer_state["enabled"]
 
 
+def _peer_arena_for(grads):
+    if not (peer_allreduce_enabled() and grads[0].is_cuda):
+        return None
+    key = (str(grads[0].device), tuple(tuple(g.shape) for g in grads))
+    pa = _peer_arenas.get(key)
+    if pa is None:
+        try:
+            pa = _peer_arenas[key] = PeerArena(grads)
+        except Exception as e:   # pragma: no cover - no P2P / symmetric memory
+            import logging
+            logging.getLogger(__name__).warning(
+                "symmetric-memory gradient arena unavailable (%s): using NCCL all-reduce", e)
+            _peer_state["enabled"] = False
+            return None
+    return pa
+
+
+def sum_grads_and_step(grads, weights, optimizer):
+    """``_sum_parallel_grad`` + ``optimizer.apply_gradients`` (abstract.py:785-805, 899-912).
+    With NVLink symmetric memory and this library's Adam: one fused kernel per step
+    (``PeerArena.sum_and_apply_adam``); otherwise all-reduce, then the optimiser's own step."""
+    from .optimizers import Adam
+    if is_distributed() and world_size() > 1 and type(optimizer) is Adam \
+            and os.environ.get("SUP3R_B200_FUSED_ADAM", "1") != "0":
+        pa = _peer_arena_for(grads)
+        if pa is not None:
+            pa.sum_and_apply_adam(grads, weights, optimizer)
+            _peer_state["fused_adam_steps"] = _peer_state.get("fused_adam_steps", 0) + 1
+            return
+    optimizer.apply_gradients(zip(allreduce_sum_grads(grads), weights))
+
+
 def allreduce_sum_grads(grads):
     """SUM all-reduce of a list of gradient tensors through one persistent flat arena (one
     exchange per step).  Returns the reduced gradients as VIEWS of a persistent buffer (no copy
@@ -153,20 +223,9 @@ def allreduce_sum_grads(grads):
     one NCCL / gloo all-reduce."""
     if not is_distributed() or world_size() == 1:
         return grads
-    if peer_allreduce_enabled() and grads[0].is_cuda:
-        key = (str(grads[0].device), tuple(tuple(g.shape) for g in grads))
-        pa = _peer_arenas.get(key)
-        if pa is None:
-            try:
-                pa = _peer_arenas[key] = PeerArena(grads)
-            except Exception as e:   # pragma: no cover - no P2P / symmetric memory
-                import logging
-                logging.getLogger(__name__).warning(
-                    "symmetric-memory gradient arena unavailable (%s): using NCCL all-reduce", e)
-                _peer_state["enabled"] = False
-                pa = None
-        if pa is not None:
-            return pa.allreduce(grads)
+    pa = _peer_arena_for(grads)
+    if pa is not None:
+        return pa.allreduce(grads)
     flat, views = _arena_for(grads)
     torch._foreach_copy_(views, [g.detach() for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)

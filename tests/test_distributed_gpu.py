@@ -67,7 +67,6 @@ def _worker(rank, world, port, q):
         # the NVLink peer-memory reduction (rank-order sum) equals the NCCL all-reduce bit for bit
         # on two ranks (a + b is commutative)
         assert all(torch.equal(a, b) for a, b in zip(g0, nccl)), "peer sum != NCCL all-reduce"
-        peer_path = bool(parallel._peer_state["enabled"])
         g0 = [g.cpu().numpy() for g in g0]
         hist = []
         for lr, hr in _batches():
@@ -81,6 +80,10 @@ def _worker(rank, world, port, q):
                          **{"disc_step_" + k: float(v) for k, v in d2.items()}})
         # every rank ends with the same weights and the same loss records
         w = [a for net in (m.generator, m.discriminator) for a in net.get_weights()]
+        # (with symmetric memory the steps above went through the fused sum + Adam kernel)
+        peer_path = (bool(parallel._peer_state["enabled"]),
+                     parallel._peer_state.get("fused_adam_steps", 0))
+        assert not peer_path[0] or peer_path[1] == 2 * N_STEPS, peer_path
         gathered = [None] * world
         dist.all_gather_object(gathered, ([a.tobytes() for a in w], hist))
         assert gathered[0] == gathered[1], "ranks diverged"
@@ -121,8 +124,8 @@ def test_two_rank_nccl_training_matches_split_batch_reference(cuda):
         p.join(timeout=60)
     assert status == "ok", payload
     w2, g2, peer_path = payload
-    print("gradient exchange:", "NVLink peer-memory sum kernel (symmetric memory)" if peer_path
-          else "NCCL all-reduce")
+    print("gradient exchange:", f"NVLink peer-memory kernels (symmetric memory; {peer_path[1]} "
+          "fused sum + Adam steps)" if peer_path[0] else "NCCL all-reduce")
 
     # single-process statement of _get_parallel_grad / _sum_parallel_grad: the shards of each
     # batch one after the other, gradients summed, one optimiser step, last shard's details
