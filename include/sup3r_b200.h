@@ -252,9 +252,12 @@ int s3_dense_bwd(const float* x, const float* w, const float* dy, float* dx, flo
 /* ---- losses and optimiser ------------------------------------------------------------------
  * Content loss (base.py:478-503): kind 0 MeanSquaredError, 1 MeanAbsoluteError over the first
  * `c_use` of `c` channels of gen/true (exo channels sliced off).  loss: device scalar
- * (overwritten).  dgen: NULL or gradient of (weight * loss) w.r.t. gen (zeros on unused ch). */
+ * (overwritten).  dgen: NULL or gradient of (weight * loss) w.r.t. gen (zeros on unused ch).
+ * scratch: S3_LOSS_SCRATCH_FLOATS device floats (block partial sums, added in block order: the
+ * loss is bit-reproducible from run to run). */
+#define S3_LOSS_SCRATCH_FLOATS 1025
 int s3_content_loss(const float* gen, const float* truth, size_t nvox, int c, int c_use, int kind,
-                    float weight, float* loss, float* dgen, s3_stream stream);
+                    float weight, float* loss, float* dgen, float* scratch, s3_stream stream);
 /* Relativistic average discriminator loss (base.py:505-549) for logits (b,) each.
  * loss: device scalar; d_real / d_fake: NULL or gradients scaled by `weight`. */
 int s3_loss_disc(const float* out_real, const float* out_fake, int b, float weight, float* loss,

@@ -82,7 +82,7 @@ SIGNATURES = {
     "s3_channel_affine": (_I, [_P, _P, _SZ, _I, _P, _P, _P]),
     "s3_dense_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "s3_dense_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "s3_content_loss": (_I, [_P, _P, _SZ, _I, _I, _I, _F, _P, _P, _P]),
+    "s3_content_loss": (_I, [_P, _P, _SZ, _I, _I, _I, _F, _P, _P, _P, _P]),
     "s3_loss_disc": (_I, [_P, _P, _I, _F, _P, _P, _P, _P]),
     "s3_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, C.c_int64, _P]),
     "s3_cast_f16": (_I, [_P, _P, _SZ, _P]),

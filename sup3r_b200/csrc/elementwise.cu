@@ -375,7 +375,7 @@ __device__ __forceinline__ float block_sum(float v) {
 __global__ void content_loss_kernel(const float* __restrict__ gen, const float* __restrict__ tru,
                                     size_t total, int c, int c_use, int kind, float weight,
                                     float inv_count, float* __restrict__ loss,
-                                    float* __restrict__ dgen) {
+                                    float* __restrict__ dgen, float* __restrict__ scratch) {
   float acc = 0.f;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -393,8 +393,22 @@ __global__ void content_loss_kernel(const float* __restrict__ gen, const float* 
     }
     if (dgen) dgen[idx] = g;
   }
+  // DETERMINISTIC sum: every block stores its partial, the last block to finish (ticket in
+  // scratch[0]) adds them in block order
   acc = block_sum(acc);
-  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_count);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    scratch[1 + blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s = 0.f;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(scratch + 1 + b);
+  s = block_sum(s);
+  if (threadIdx.x == 0) *loss = s * inv_count;
 }
 
 __device__ __forceinline__ float sce_logits(float x, float z) {
@@ -812,16 +826,21 @@ static int pack_weights_umma(const float* w, int taps, int cin, int cout, void* 
 
 extern "C" int s3_content_loss(const float* gen, const float* truth, size_t nvox, int c, int c_use,
                                int kind, float weight, float* loss, float* dgen,
-                               s3_stream stream) {
-  S3_REQUIRE(gen && truth && loss && c > 0 && c_use > 0 && c_use <= c && (kind == 0 || kind == 1),
+                               float* scratch, s3_stream stream) {
+  S3_REQUIRE(gen && truth && loss && scratch && c > 0 && c_use > 0 && c_use <= c &&
+                 (kind == 0 || kind == 1),
              "s3_content_loss: bad arguments");
   size_t total = nvox * (size_t)c;
-  S3_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream)));
-  if (total == 0) return S3_OK;
+  if (total == 0) {
+    S3_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream)));
+    return S3_OK;
+  }
+  S3_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), as_stream(stream)));   // the ticket
   float inv = 1.f / ((float)nvox * (float)c_use);
-  content_loss_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(gen, truth, total, c, c_use,
-                                                                        kind, weight, inv, loss,
-                                                                        dgen);
+  unsigned blocks = grid_for(total);
+  if (blocks > S3_LOSS_SCRATCH_FLOATS - 1) blocks = S3_LOSS_SCRATCH_FLOATS - 1;
+  content_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(gen, truth, total, c, c_use, kind,
+                                                             weight, inv, loss, dgen, scratch);
   S3_LAUNCH_CHECK("content_loss");
   return S3_OK;
 }

@@ -114,6 +114,8 @@ class AbstractSingleModel(TensorboardMixIn):
         self._train_record = pd.DataFrame()
         self._val_record = pd.DataFrame()
         self._plans = {}
+        from ..train_graph import GraphedSteps
+        self._graphed_steps = GraphedSteps(self)
 
     # ---- device mapping ------------------------------------------------------------------
     def torch_device(self, device_name=None):
@@ -437,23 +439,25 @@ class AbstractSingleModel(TensorboardMixIn):
         if optimizer is None:
             optimizer = self.optimizer
         t0 = time.time()
-        if multi_gpu and parallel.world_size() > 1:
+        multi_gpu = bool(multi_gpu) and parallel.world_size() > 1
+        if multi_gpu:
             low_res = parallel.shard_batch(low_res)
             hi_res_true = parallel.shard_batch(hi_res_true)
             if calc_loss_kwargs.get("mask") is not None:
                 calc_loss_kwargs["mask"] = parallel.shard_batch(calc_loss_kwargs["mask"])
+        # the whole gradient computation replayed as one CUDA graph once the shapes have been
+        # seen a few times (train_graph.py); None -> the eager path below
+        loss_details = self._graphed_steps.run(low_res, hi_res_true, training_weights, optimizer,
+                                               multi_gpu, calc_loss_kwargs)
+        if loss_details is None:
             grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
                                                       device_name=self.default_device,
                                                       **calc_loss_kwargs)
+            # SUM of the shard gradients (multi-GPU) + one optimiser step: one fused kernel with
+            # this library's Adam (over NVLink peer memory when multi_gpu)
+            parallel.sum_grads_and_step(grad, training_weights, optimizer, multi_gpu)
+        if multi_gpu:
             loss_details = parallel.broadcast_loss_details(loss_details)
-            # SUM of the shard gradients + one optimiser step (fused into one NVLink peer-memory
-            # kernel when the optimiser is this library's Adam)
-            parallel.sum_grads_and_step(grad, training_weights, optimizer)
-        else:
-            grad, loss_details = self.get_single_grad(low_res, hi_res_true, training_weights,
-                                                      device_name=self.default_device,
-                                                      **calc_loss_kwargs)
-            optimizer.apply_gradients(zip(grad, training_weights))
         logger.debug("Finished single gradient descent step in %.4f seconds", time.time() - t0)
         return loss_details
 

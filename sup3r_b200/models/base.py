@@ -27,6 +27,8 @@ logger = logging.getLogger(__name__)
 class Sup3rGan(AbstractSingleModel, AbstractInterface):
     """Spatial (4-D) or spatiotemporal (5-D) super-resolution GAN."""
 
+    _graph_safe = True    # gradient step may be captured as a CUDA graph (train_graph.py)
+
     def __init__(self, gen_layers, disc_layers, loss="MeanSquaredError", optimizer=None,
                  learning_rate=1e-4, optimizer_disc=None, learning_rate_disc=None, history=None,
                  meta=None, means=None, stdevs=None, default_device=None, name=None,

@@ -15,6 +15,8 @@ logger = logging.getLogger(__name__)
 class Sup3rGanDC(Sup3rGan):
     """Data-centric model using loss across space / time bins to select training samples."""
 
+    _graph_safe = True    # gradient step may be captured as a CUDA graph (train_graph.py)
+
     def calc_val_loss_gen(self, batch_handler, weight_gen_advers):
         """Total and content loss of every validation bin, shape (n_space_bins, n_time_bins)
         (dc.py:18-62)."""

@@ -557,8 +557,9 @@ def content_loss(gen, truth, c_use, kind, weight=1.0, want_grad=False):
     c = gen.shape[-1]
     loss = torch.empty((), device=gen.device, dtype=torch.float32)
     dgen = torch.empty_like(gen) if want_grad else None
+    scratch = torch.empty(1025, device=gen.device, dtype=torch.float32)   # S3_LOSS_SCRATCH_FLOATS
     _cabi.call("s3_content_loss", _p(gen), _p(truth), gen.numel() // c, c, c_use, kind,
-               float(weight), _p(loss), _p(dgen), _s())
+               float(weight), _p(loss), _p(dgen), _p(scratch), _s())
     _count()
     return loss, dgen
 

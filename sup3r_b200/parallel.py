@@ -99,12 +99,83 @@ _peer_arenas = {}
 _peer_state = {"enabled": None}
 
 
-class PeerArena:
+class GradArena:
+    """Flat fp32 gradient arena + the table ``s3_peer_sum_adam`` walks: one entry per
+    <= 4096-element piece of a weight tensor (weight, first / second moment pointers, position of
+    its gradient in the arena), one CTA each.  The kernel adds the arenas of ``world`` ranks in
+    rank order and applies keras Adam in registers; with one rank (``LocalArena``) it is simply
+    the whole network's optimiser step in one launch."""
+
+    world = 1
+
+    def _layout(self, grads, arena):
+        self.in_views, off = [], 0
+        for g in grads:
+            self.in_views.append(arena[off:off + g.numel()].view(g.shape))
+            off += g.numel()
+
+    def _barrier(self, channel):
+        pass
+
+    def stage(self, grads):
+        """Copy this rank's gradients into the arena (one multi-tensor launch)."""
+        torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
+
+    def sum_and_apply_adam(self, grads, weights, optimizer):
+        """The exchange and the optimiser step in ONE kernel (``s3_peer_sum_adam``): every rank
+        adds all gradient arenas in rank order and applies keras Adam to its own (replicated)
+        weights; the summed gradient never goes back to memory.  ``grads`` None: already staged
+        (the CUDA-graph training step copies them as its last node)."""
+        from . import _cabi, ops
+        slots = [optimizer.slots_for(var) for var in weights]
+        key = tuple((var.value.data_ptr(), m.data_ptr(), v.data_ptr())
+                    for var, (m, v) in zip(weights, slots))
+        if getattr(self, "_seg_key", None) != key:
+            rows, off, piece = [], 0, 4096
+            for (wp, mp, vp), g, var in zip(key, self.in_views, weights):
+                if not var.value.is_contiguous() or var.value.dtype != torch.float32:
+                    raise ValueError(f"fused Adam needs contiguous float32 weights ({var.name})")
+                if var.value.numel() != g.numel():
+                    raise ValueError(f"gradient arena does not match weight {var.name}")
+                for s0 in range(0, g.numel(), piece):
+                    rows.append((wp + 4 * s0, mp + 4 * s0, vp + 4 * s0, off + s0,
+                                 min(piece, g.numel() - s0)))
+                off += g.numel()
+            rec = np.array(rows, dtype=np.uint64)
+            self._segs = torch.from_numpy(rec.view(np.int64)).to(self.arena.device)
+            self._n_seg, self._max_n = len(rows), piece
+            self._seg_key = key
+        if grads is not None:
+            self.stage(grads)
+        optimizer.iterations += 1
+        self._barrier(0)          # every rank's arena is written
+        _cabi.call("s3_peer_sum_adam", self._ptrs, self.world, ops._p(self._segs), self._n_seg,
+                   self._max_n, float(optimizer.learning_rate), float(optimizer.beta_1),
+                   float(optimizer.beta_2), float(optimizer.epsilon), int(optimizer.iterations),
+                   ops._s())
+        ops._count()
+        self._barrier(1)          # every rank has read every arena
+        for var in weights:
+            var.version += 1
+
+
+class LocalArena(GradArena):
+    """Single-GPU arena: the optimiser step of all weight tensors in one launch."""
+
+    def __init__(self, grads):
+        import ctypes as C
+        n = sum(g.numel() for g in grads)
+        self.arena = torch.zeros(max(n, 1), dtype=torch.float32, device=grads[0].device)
+        self._ptrs = (C.c_void_p * 1)(self.arena.data_ptr())
+        self._layout(grads, self.arena)
+
+
+class PeerArena(GradArena):
     """Flat fp32 gradient arena in symmetric (NVLink peer-mapped) memory + a local result buffer.
     ``torch.distributed._symmetric_memory`` only does the plumbing (allocation, exchange of the
     peer mappings, the cross-GPU barrier on its signal pads); the reduction itself is this
-    library's kernel (``s3_peer_sum_f32``): every rank reads all arenas over NVLink and adds them
-    in rank order -- deterministic and bit-identical on all ranks."""
+    library's kernel (``s3_peer_sum_f32`` / ``s3_peer_sum_adam``): every rank reads all arenas
+    over NVLink and adds them in rank order -- deterministic and bit-identical on all ranks."""
 
     def __init__(self, grads):
         import ctypes as C
@@ -119,51 +190,18 @@ class PeerArena:
         ptrs = list(self.handle.buffer_ptrs)
         self._ptrs = (C.c_void_p * self.world)(*ptrs)
         self.out = torch.empty(self.n, device=dev, dtype=torch.float32)
-        self.in_views, self.out_views, off = [], [], 0
+        self._layout(grads, self.arena)
+        self.out_views, off = [], 0
         for g in grads:
-            self.in_views.append(self.arena[off:off + g.numel()].view(g.shape))
             self.out_views.append(self.out[off:off + g.numel()].view(g.shape))
             off += g.numel()
 
-    def sum_and_apply_adam(self, grads, weights, optimizer):
-        """The exchange and the optimiser step in ONE kernel (``s3_peer_sum_adam``): every rank
-        adds all gradient arenas in rank order and applies keras Adam to its own (replicated)
-        weights; the summed gradient never goes back to memory."""
-        import numpy as np
-        from . import _cabi, ops
-        slots = [optimizer.slots_for(var) for var in weights]
-        key = tuple((var.value.data_ptr(), m.data_ptr(), v.data_ptr())
-                    for var, (m, v) in zip(weights, slots))
-        if getattr(self, "_seg_key", None) != key:
-            # one table entry per <= 4096-element piece of a tensor (one CTA each), so that the
-            # big dense / conv kernels spread over the whole GPU
-            rows, off, piece = [], 0, 4096
-            for (wp, mp, vp), g, var in zip(key, grads, weights):
-                if not var.value.is_contiguous() or var.value.dtype != torch.float32:
-                    raise ValueError(f"fused Adam needs contiguous float32 weights ({var.name})")
-                for s0 in range(0, g.numel(), piece):
-                    rows.append((wp + 4 * s0, mp + 4 * s0, vp + 4 * s0, off + s0,
-                                 min(piece, g.numel() - s0)))
-                off += g.numel()
-            rec = np.array(rows, dtype=np.uint64)
-            self._segs = torch.from_numpy(rec.view(np.int64)).to(self.arena.device)
-            self._n_seg, self._max_n = len(rows), piece
-            self._seg_key = key
-        torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
-        optimizer.iterations += 1
-        self.handle.barrier(channel=0)          # every rank's arena is written
-        _cabi.call("s3_peer_sum_adam", self._ptrs, self.world, ops._p(self._segs), self._n_seg,
-                   self._max_n, float(optimizer.learning_rate), float(optimizer.beta_1),
-                   float(optimizer.beta_2), float(optimizer.epsilon), int(optimizer.iterations),
-                   ops._s())
-        ops._count()
-        self.handle.barrier(channel=1)          # every rank has read every arena
-        for var in weights:
-            var.version += 1
+    def _barrier(self, channel):
+        self.handle.barrier(channel=channel)
 
     def allreduce(self, grads):
         from . import _cabi, ops
-        torch._foreach_copy_(self.in_views, [g.detach() for g in grads])
+        self.stage(grads)
         self.handle.barrier(channel=0)          # every rank's arena is written
         _cabi.call("s3_peer_sum_f32", self._ptrs, self.world, self.n,
                    ops._p(self.out), ops._s())
@@ -200,19 +238,41 @@ def _peer_arena_for(grads):
     return pa
 
 
-def sum_grads_and_step(grads, weights, optimizer):
-    """``_sum_parallel_grad`` + ``optimizer.apply_gradients`` (abstract.py:785-805, 899-912).
-    With NVLink symmetric memory and this library's Adam: one fused kernel per step
-    (``PeerArena.sum_and_apply_adam``); otherwise all-reduce, then the optimiser's own step."""
+_local_arenas = {}
+
+
+def step_arena(grads, optimizer, multi_gpu=False):
+    """The arena whose fused kernel can take this optimiser step, or None: this library's Adam on
+    CUDA tensors -- ``PeerArena`` for a multi-GPU step over NVLink symmetric memory,
+    ``LocalArena`` for a single-GPU step.  ``SUP3R_B200_FUSED_ADAM=0`` disables both."""
     from .optimizers import Adam
-    if is_distributed() and world_size() > 1 and type(optimizer) is Adam \
-            and os.environ.get("SUP3R_B200_FUSED_ADAM", "1") != "0":
-        pa = _peer_arena_for(grads)
-        if pa is not None:
-            pa.sum_and_apply_adam(grads, weights, optimizer)
+    if type(optimizer) is not Adam or not grads or not grads[0].is_cuda \
+            or os.environ.get("SUP3R_B200_FUSED_ADAM", "1") == "0":
+        return None
+    if multi_gpu and world_size() > 1:
+        return _peer_arena_for(grads)
+    key = (str(grads[0].device), tuple(tuple(g.shape) for g in grads))
+    la = _local_arenas.get(key)
+    if la is None:
+        la = _local_arenas[key] = LocalArena(grads)
+    return la
+
+
+def sum_grads_and_step(grads, weights, optimizer, multi_gpu=True, arena=None, staged=False):
+    """``_sum_parallel_grad`` + ``optimizer.apply_gradients`` (abstract.py:785-805, 899-912).
+    With this library's Adam: one fused kernel per step (``GradArena.sum_and_apply_adam`` -- over
+    NVLink symmetric memory when ``multi_gpu``); otherwise all-reduce, then the optimiser's own
+    step.  ``staged``: the gradients already sit in ``arena`` (CUDA-graph training step)."""
+    if arena is None:
+        arena = step_arena(grads, optimizer, multi_gpu)
+    if arena is not None:
+        arena.sum_and_apply_adam(None if staged else grads, weights, optimizer)
+        if arena.world > 1:
             _peer_state["fused_adam_steps"] = _peer_state.get("fused_adam_steps", 0) + 1
-            return
-    optimizer.apply_gradients(zip(allreduce_sum_grads(grads), weights))
+        return
+    if multi_gpu and world_size() > 1:
+        grads = allreduce_sum_grads(grads)
+    optimizer.apply_gradients(zip(grads, weights))
 
 
 def allreduce_sum_grads(grads):

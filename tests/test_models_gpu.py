@@ -563,3 +563,51 @@ def test_training_forward_sees_optimizer_updates(cuda):
     assert np.abs(after - before).max() > 1e-3 and np.abs(d_after - d_before).max() > 1e-6
     # and the inference plan (CUDA graph) follows as well
     assert np.allclose(m.generate(lr), fresh.generate(lr), rtol=0, atol=0)
+
+
+def test_graphed_gradient_step_equals_eager_step(cuda, monkeypatch):
+    """The CUDA-graph replay of the gradient step (train_graph.py) runs the very kernels of the
+    eager step: loss records and weights after a GAN schedule of generator / discriminator steps
+    on changing batches are bit-identical to the eager run, the eager forward afterwards sees the
+    graph-updated weights, and a changed loss argument gets its own graph."""
+    gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
+    disc_hl = C.discriminator(3, "same", (16,))
+    lr_shape, hr_shape = (2, 4, 4, 4, 2), (2, 8, 8, 8, 2)
+    rng = np.random.default_rng(17)
+    batches = [(rng.standard_normal(lr_shape).astype(np.float32),
+                rng.standard_normal(hr_shape).astype(np.float32)) for _ in range(7)]
+
+    def run(graph):
+        monkeypatch.setenv("SUP3R_B200_TRAIN_GRAPH", "1" if graph else "0")
+        m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, learning_rate=1e-3)
+        hist = []
+        for i, (lr, hr) in enumerate(batches):
+            w_adv = 1e-2 if i < 5 else 2e-2        # (a new value: new key, eager warm-up again)
+            d1 = m.run_gradient_descent(lr, hr, m.generator_weights, optimizer=m.optimizer,
+                                        weight_gen_advers=w_adv, train_gen=True,
+                                        train_disc=False, compute_disc=True)
+            rec = {k: float(v) for k, v in d1.items()}
+            if i != 3:                              # (the schedule skips a discriminator step)
+                d2 = m.run_gradient_descent(lr, hr, m.discriminator_weights,
+                                            optimizer=m.optimizer_disc, weight_gen_advers=w_adv,
+                                            train_gen=False, train_disc=True)
+                rec.update({"d_" + k: float(v) for k, v in d2.items()})
+            hist.append(rec)
+        with torch.no_grad():
+            out = m._tf_generate(batches[0][0]).cpu().numpy()
+        w = [a for net in (m.generator, m.discriminator) for a in net.get_weights()]
+        opt = {v.name: v.numpy() for v in m.optimizer.variables}
+        return hist, w, out, dict(m._graphed_steps.stats), opt, m
+
+    h0, w0, o0, s0, opt0, _ = run(False)
+    h1, w1, o1, s1, opt1, m1 = run(True)
+    assert s0["replays"] == 0
+    assert s1["captures"] >= 2 and s1["replays"] == 3 + 2, s1   # gen: steps 2,3,4; disc: 2,4
+    assert h0 == h1
+    assert all(np.array_equal(a, b) for a, b in zip(w0, w1))
+    assert np.array_equal(o0, o1)
+    assert opt0.keys() == opt1.keys() and all(np.array_equal(opt0[k], opt1[k]) for k in opt0)
+    # the inference plan follows the graph-updated weights as well
+    fresh = make_model(gen_hl, disc_hl, lr_shape, hr_shape)
+    fresh.generator.set_weights(m1.generator.get_weights())
+    assert np.array_equal(m1.generate(batches[0][0]), fresh.generate(batches[0][0]))

@@ -10,7 +10,7 @@ import torch
 from sup3r_b200.models import Sup3rGan
 from sup3r_b200 import configs as C
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-K = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 feats = [f"f{i}" for i in range(6)]
 Sup3rGan.seed(0)
 m = Sup3rGan(C.spatiotemporal_generator(6, 2, (2, 2, 3)), C.discriminator(3, "same", (1024,)),
@@ -34,6 +34,8 @@ for i in range(K + 1):
                                 train_gen=False, train_disc=True)
     torch.cuda.synchronize()
     times.append(time.perf_counter() - t0)
-print(f"batch {B}: gen + disc gradient step {np.mean(times[1:])*1e3:.1f} ms "
-      f"(first incl. warm-up {times[0]*1e3:.0f} ms); loss_gen {float(d1['loss_gen']):.4f} "
+# (steps 0-1 run eagerly, step 2 captures the CUDA graphs of the two gradient steps)
+print(f"batch {B}: gen + disc gradient step {np.median(times[4:])*1e3:.1f} ms (median of steps 4+; "
+      f"steps 0-3: {' '.join(f'{t*1e3:.0f}' for t in times[:4])} ms; "
+      f"graph {dict(m._graphed_steps.stats)}); loss_gen {float(d1['loss_gen']):.4f} "
       f"loss_disc {float(d2['loss_disc']):.4f}")
