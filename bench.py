@@ -98,7 +98,7 @@ def network_flops(hl, in_shape):
     return flops
 
 
-def train_step_block(dev, peaks, steps=3):
+def train_step_block(dev, peaks, steps=6):
     """BASELINE configs[3]-style training step: generator = gen_2x_12x pattern with 6 in / 6 out
     features, LR (4, 16, 16, 4, 6) -> HR (4, 32, 32, 48, 6), 'same'-padded ST discriminator, Adam
     1e-4, MeanAbsoluteError content loss: one generator gradient step + one discriminator
@@ -126,9 +126,13 @@ def train_step_block(dev, peaks, steps=3):
                                train_gen=True, train_disc=False)
         m.run_gradient_descent(lr_t, hr_t, m.discriminator_weights, weight_gen_advers=1e-3,
                                train_gen=False, train_disc=True)
-    for _ in range(2):
+    t_eager = []
+    for i in range(4):     # untimed: 2 eager steps, the CUDA-graph capture of both steps, 1 replay
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         step()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        t_eager.append((time.perf_counter() - t0) * 1e3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -144,14 +148,19 @@ def train_step_block(dev, peaks, steps=3):
     return {"workload": "Sup3rGan training step (generator step + discriminator step), batch 4, "
                         "LR 16x16x4x6 -> HR 32x32x48x6, gen_2x_12x-pattern generator, same-padded "
                         "ST discriminator (BASELINE configs[3] shapes)",
-            "ms_per_step": ms, "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
+            "ms_per_step": ms, "ms_per_step_eager_launches": t_eager[1],
+            "cuda_graph": dict(m._graphed_steps.stats),
+            "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
             "frac_of_bf16_peak": flops / (ms / 1e3) / 1e12 / peak,
             "algorithmic_flops_per_step": flops,
             "kernels": "generator AND discriminator convolutions: forward + input gradients (fp16c "
                        "operands, 64-channel groups summed through the f32 residual input, stride 2 "
                        "= sampled stride-1 convolution) + weight gradients (fp16, voxels as the K "
                        "dimension of MN-major operands) on tcgen05; dense layers, losses, Adam, "
-                       "layers with extents < 2: fp32 CUDA-core kernels"}
+                       "layers with extents < 2: fp32 CUDA-core kernels.  Each gradient step is "
+                       "replayed as one CUDA graph (sup3r_b200/train_graph.py) + one fused "
+                       "whole-network Adam launch; ms_per_step_eager_launches is the same step "
+                       "issued launch by launch (second step of the run)"}
 
 
 class ClockSampler:

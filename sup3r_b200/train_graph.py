@@ -17,7 +17,8 @@ What a graph bakes in, and how each is kept honest:
 * the power-of-two scales of the fp16c weight packing (they follow max |w| of each kernel):
   checked before every replay with the one host read per step the eager path also does; a
   change re-captures;
-* python scalars of the loss (``weight_gen_advers`` ...) and the schedule flags: part of the key;
+* python scalars of the loss (``weight_gen_advers`` ...) and the schedule flags: part of the key
+  (at most ``MAX_GRAPHS`` graphs stay alive per model, the oldest are dropped);
 * the packed tensor-core weights: every weight version is bumped before a capture, so each graph
   re-packs all the weights it reads at every replay and never depends on another graph's buffers.
 
@@ -39,6 +40,7 @@ import torch
 logger = logging.getLogger(__name__)
 
 WARMUP_CALLS = 2          # eager steps of a key before it is captured (lazy scratch, caches)
+MAX_GRAPHS = 4            # live graphs per model (each owns a memory pool the size of one step)
 _STOCHASTIC = ("noise", "dropout", "random")
 
 
@@ -135,6 +137,17 @@ class GraphedSteps:
         st.details = {k: v for k, v in details.items()}
         return st
 
+    def _evict(self, keep):
+        """Least-recently-captured graphs beyond MAX_GRAPHS are dropped (e.g. the adversarial
+        weight changes every epoch with adaptive updates: each value is its own graph)."""
+        live = [k for k, v in self._steps.items() if v is not False and k != keep]
+        while len(live) + 1 > MAX_GRAPHS:
+            k = live.pop(0)
+            del self._steps[k]
+            self._seen.pop(k, None)
+        if len(self._seen) > 256:
+            self._seen.clear()
+
     def run(self, low_res, hi_res_true, weights, optimizer, multi_gpu, kwargs):
         """One gradient step through a captured graph.  Returns the loss details, or None when
         this call has to take the eager path."""
@@ -144,8 +157,11 @@ class GraphedSteps:
         from .network import to_device_tensor
         m = self.model
         dev = m.torch_device()
+        # (the storage of every weight of both networks is part of the key: a graph reads the
+        #  tensors it was captured on, re-loaded weights live somewhere else)
+        ptrs = tuple(var.value.data_ptr() for net in self._nets() for var in net.weights)
         key = (tuple(id(w) for w in weights), tuple(low_res.shape), tuple(hi_res_true.shape),
-               tuple(sorted(kwargs.items())), bool(multi_gpu), id(optimizer))
+               tuple(sorted(kwargs.items())), bool(multi_gpu), id(optimizer), ptrs)
         st = self._steps.get(key)
         if st is False:
             return None
@@ -172,6 +188,7 @@ class GraphedSteps:
                 return None
             self._steps[key] = st
             self.stats["captures"] += 1
+            self._evict(key)
         else:
             st.lr.copy_(lr)
             st.hr.copy_(hr)

@@ -30,7 +30,8 @@ parallel.broadcast_weights([m.generator, m.discriminator])
 dev = m.torch_device()
 lr_t, hr_t = torch.tensor(lr, device=dev), torch.tensor(hr, device=dev)
 ts = []
-for i in range(K + 2):
+W = 4    # untimed: 2 eager steps, the CUDA-graph capture, 1 replay
+for i in range(K + W):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -42,7 +43,7 @@ for i in range(K + 2):
                                train_gen=False, train_disc=True, multi_gpu=world > 1)
     e1.record()
     torch.cuda.synchronize()
-    if i >= 2:
+    if i >= W:
         ts.append(e0.elapsed_time(e1))
 t = torch.tensor([float(np.mean(ts))], device=dev, dtype=torch.float64)
 if world > 1:
