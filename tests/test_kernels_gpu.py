@@ -590,6 +590,32 @@ def test_fp16c_pack_roundtrip(cuda):
     assert np.abs(a8 - x).max() <= np.abs(x).max() * 2.0 ** -4
 
 
+@pytest.mark.parametrize("halo", [1, 0])
+def test_fp16c_pack_is_exact(cuda, halo):
+    """The (vectorised) operand packing, bit for bit: hi = fp16(x) on the padded extent (reflect /
+    zero halo), correction row = [e4m3((x - hi) 2^11) | e4m3(x)] per 32-channel half."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(8)
+    x = rng_arr(rng, (2, 3, 5, 6, 64), 2.0)
+    xd = dev(x, cuda)
+    hi, corr = ops.pack_act_pad16(xd, split=True, fmt=2, halo=halo)
+    xp = xd.permute(0, 4, 1, 2, 3)
+    xp = (torch.nn.functional.pad(xp, (1,) * 6, mode="reflect") if halo == 1
+          else torch.nn.functional.pad(xp, (1,) * 6))
+    xp = xp.permute(0, 2, 3, 4, 1).contiguous()
+    want_hi = xp.half()
+    assert torch.equal(hi.reshape(want_hi.shape), want_hi)
+    row = corr.view(torch.uint8).reshape(*xp.shape[:-1], 2, 2, 32)
+    lo8 = row[..., 0, :].reshape(xp.shape).view(torch.float8_e4m3fn).float()
+    a8 = row[..., 1, :].reshape(xp.shape).view(torch.float8_e4m3fn).float()
+    assert torch.equal(a8, xp.to(torch.float8_e4m3fn).float())
+    assert torch.equal(lo8, ((xp - want_hi.float()) * 2048.0).to(torch.float8_e4m3fn).float())
+    # a 16-bit pair (bf16 hi + lo) goes through the same kernel
+    bh, bl = ops.pack_act_pad16(xd, split=True, fmt=0, halo=halo)
+    assert torch.equal(bh.reshape(xp.shape), xp.bfloat16())
+    assert torch.equal(bl.reshape(xp.shape), (xp - xp.bfloat16().float()).bfloat16())
+
+
 FP16C_CASES = [
     # n, (z, y, x), variant
     (1, (16, 16, 24), "pad16"),          # hot shape: straight-line two-pass MMA role, V4 epilogue
