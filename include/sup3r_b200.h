@@ -208,6 +208,11 @@ int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], in
  * kernel followed by the adjoint of the reflect pad, s3_pad_bwd). */
 int s3_pack_act_pad16_ex(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
                          void* lo, int fmt, int halo_mode, s3_stream stream);
+/* Same with a zero halo of `halo_width` voxels (1 or 2): width 2 is the operand of the input-
+ * gradient convolution of a reflect-padded layer (the gradient on the padded extent, zero-padded
+ * by one more voxel), without materialising the padded fp32 tensor. */
+int s3_pack_act_pad16_hw(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,
+                         void* lo, int fmt, int halo_mode, int halo_width, s3_stream stream);
 /* inverse (interior only); lo may be NULL.  For tests. */
 int s3_unpack_act_pad16(const void* hi, const void* lo, int ndim, int n, const int32_t dims[3],
                         int c, float* x, int fmt, s3_stream stream);

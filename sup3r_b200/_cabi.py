@@ -67,6 +67,7 @@ SIGNATURES = {
     "s3_pack_weights_umma_c": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P]),
     "s3_pack_act_pad16": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _P]),
     "s3_pack_act_pad16_ex": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _I, _P]),
+    "s3_pack_act_pad16_hw": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _I, _I, _P]),
     "s3_unpack_act_pad16": (_I, [_P, _P, _I, _I, c_i32x3, _I, _P, _I, _P]),
     "s3_pad_fwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),
     "s3_pad_bwd": (_I, [_P, _P, c_i32x5, c_i32x5, c_i32x5, _I, _P]),

@@ -205,13 +205,16 @@ class ConvUmmaFn(torch.autograd.Function):
                 # over the 64-channel blocks of dy.  REFLECT: on the padded extent, then the
                 # adjoint of the reflect pad folds the halo back; ZERO ('same'): directly.
                 ver = ctx.ver
-                gsrc = ops.pad_fwd(dy_p, pads, S3_PAD_ZERO) if reflect else dy_p
-                gn, gdims, _, _ = ops.dims3(gsrc.shape)
+                # (REFLECT: the gradient on the padded extent is dy zero-padded by one voxel; the
+                #  operand packing writes that border itself -- a zero halo two voxels wide)
                 g_parts, g_halo = [], (2 if reflect else 1)
+                gn, gdims, _, _ = ops.dims3(dy_p.shape)
+                if reflect:
+                    gdims = tuple(d + 2 if (nd == 3 or i > 0) else d for i, d in enumerate(gdims))
                 for go in range(gout):
-                    blk = gsrc if gout == 1 else gsrc[..., 64 * go:64 * go + 64].contiguous()
+                    blk = dy_p if gout == 1 else dy_p[..., 64 * go:64 * go + 64].contiguous()
                     g_parts.append(ops.pack_act_pad16(blk, split=True, fmt=ops.S3_FMT_FP16C,
-                                                      halo=S3_PAD_ZERO))
+                                                      halo=S3_PAD_ZERO, halo_width=g_halo))
                 cin_p = (cin + 15) // 16 * 16
                 slices = []
                 for c0 in range(0, cin_p, 256):

@@ -97,13 +97,22 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long rows, int c
   }
 }
 
+// 32 columns x 8 lanes per block: lane l adds blocks l, l + 8, ... in order, the 8 lane sums are
+// added in lane order -- a fixed summation tree, whatever the grid
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nblk, int cols,
                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x >> 5;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * cols + c];
-  out[c] = s;
+  if (c < cols)
+    for (int b = lane; b < nblk; b += 8) s += part[(size_t)b * cols + c];
+  __shared__ float sh[8][33];
+  sh[lane][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lane == 0 && c < cols) {
+    for (int i = 1; i < 8; ++i) s += sh[i][threadIdx.x & 31];
+    out[c] = s;
+  }
 }
 
 // partial-sum scratch of the column sums: grown on demand, one per device (the only allocation
@@ -146,7 +155,7 @@ int launch_colsum(const float* x, long long rows, int cols, float* out, cudaStre
     float* part = colsum_scratch((size_t)bx * cols);
     S3_REQUIRE(part != nullptr, "colsum: cannot allocate %lld x %d partial sums", bx, cols);
     colsum_kernel<<<grid, 256, 0, st>>>(x, rows, cols, part);
-    colsum_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>(part, (int)bx, cols, out);
+    colsum_reduce_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part, (int)bx, cols, out);
   }
   S3_CUDA(cudaGetLastError());
   return S3_OK;

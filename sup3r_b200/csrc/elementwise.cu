@@ -277,8 +277,8 @@ __global__ void channel_affine_kernel(const float* __restrict__ x, float* __rest
 // ------------------------------------------------- 16-bit padded activations / weights
 __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
                                 uint16_t* __restrict__ lo, int pz, int n, int Z, int Y, int X,
-                                int c, int fmt, size_t total, int halo_mode) {
-  const int PZ = Z + 2 * pz, PY = Y + 2, PX = X + 2;
+                                int c, int fmt, size_t total, int halo_mode, int hw) {
+  const int PZ = Z + 2 * hw * pz, PY = Y + 2 * hw, PX = X + 2 * hw;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     size_t t = idx;
@@ -288,9 +288,9 @@ __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restric
     int pzc = (int)(t % PZ);
     int b = (int)(t / PZ);
     bool ok = true;
-    int z = pz ? fold_pad(pzc - 1, Z, halo_mode, &ok) : pzc;
-    int y = fold_pad(py - 1, Y, halo_mode, &ok);
-    int xx = fold_pad(px - 1, X, halo_mode, &ok);
+    int z = pz ? fold_pad(pzc - hw, Z, halo_mode, &ok) : pzc;
+    int y = fold_pad(py - hw, Y, halo_mode, &ok);
+    int xx = fold_pad(px - hw, X, halo_mode, &ok);
     float v = ok ? x[((((size_t)b * Z + z) * Y + y) * X + xx) * c + ch] : 0.f;
     uint16_t h = to16(v, fmt);
     hi[idx] = h;
@@ -311,8 +311,9 @@ __global__ void pack_act_kernel(const float* __restrict__ x, uint16_t* __restric
 // contiguous inside each run).  Element-wise arithmetic identical to pack_act_kernel.
 __global__ void pack_act_vec8_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
                                      uint16_t* __restrict__ lo, int pz, int n, int Z, int Y,
-                                     int X, int c, int fmt, size_t total8, int halo_mode) {
-  const int PZ = Z + 2 * pz, PY = Y + 2, PX = X + 2, c8 = c >> 3;
+                                     int X, int c, int fmt, size_t total8, int halo_mode,
+                                     int hw) {
+  const int PZ = Z + 2 * hw * pz, PY = Y + 2 * hw, PX = X + 2 * hw, c8 = c >> 3;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total8;
        idx += (size_t)gridDim.x * blockDim.x) {
     size_t t = idx;
@@ -323,9 +324,9 @@ __global__ void pack_act_vec8_kernel(const float* __restrict__ x, uint16_t* __re
     int pzc = (int)(t % PZ);
     int b = (int)(t / PZ);
     bool ok = true;
-    int z = pz ? fold_pad(pzc - 1, Z, halo_mode, &ok) : pzc;
-    int y = fold_pad(py - 1, Y, halo_mode, &ok);
-    int xx = fold_pad(px - 1, X, halo_mode, &ok);
+    int z = pz ? fold_pad(pzc - hw, Z, halo_mode, &ok) : pzc;
+    int y = fold_pad(py - hw, Y, halo_mode, &ok);
+    int xx = fold_pad(px - hw, X, halo_mode, &ok);
     float v[8];
     if (ok) {
       const float4* src = reinterpret_cast<const float4*>(
@@ -801,24 +802,32 @@ extern "C" int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t 
 extern "C" int s3_pack_act_pad16_ex(const float* x, int ndim, int n, const int32_t dims[3], int c,
                                     void* hi, void* lo, int fmt, int halo_mode,
                                     s3_stream stream) {
+  return s3_pack_act_pad16_hw(x, ndim, n, dims, c, hi, lo, fmt, halo_mode, 1, stream);
+}
+
+extern "C" int s3_pack_act_pad16_hw(const float* x, int ndim, int n, const int32_t dims[3], int c,
+                                    void* hi, void* lo, int fmt, int halo_mode, int halo_width,
+                                    s3_stream stream) {
   S3_REQUIRE(x && hi && (ndim == 2 || ndim == 3), "s3_pack_act_pad16: bad arguments");
   S3_REQUIRE(halo_mode == S3_PAD_REFLECT || halo_mode == S3_PAD_ZERO,
              "s3_pack_act_pad16: halo_mode must be S3_PAD_REFLECT or S3_PAD_ZERO");
+  S3_REQUIRE(halo_width == 1 || (halo_width == 2 && halo_mode == S3_PAD_ZERO),
+             "s3_pack_act_pad16: halo_width 1, or 2 with a zero halo");
   S3_REQUIRE(fmt != kFmtFp16c || !lo || c == 64, "s3_pack_act_pad16: fp16c rows need c == 64");
-  const int pz = ndim == 3 ? 1 : 0;
+  const int pz = ndim == 3 ? 1 : 0, hw = halo_width;
   S3_REQUIRE(halo_mode == S3_PAD_ZERO || (dims[1] >= 2 && dims[2] >= 2 && (!pz || dims[0] >= 2)),
              "s3_pack_act_pad16: reflect halo needs extents >= 2");
-  size_t total = (size_t)n * (dims[0] + 2 * pz) * (dims[1] + 2) * (dims[2] + 2) * c;
+  size_t total = (size_t)n * (dims[0] + 2 * hw * pz) * (dims[1] + 2 * hw) * (dims[2] + 2 * hw) * c;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) |
                          reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
   if (c % 8 == 0 && aligned)
     pack_act_vec8_kernel<<<grid_for(total / 8), 256, 0, as_stream(stream)>>>(
         x, (uint16_t*)hi, (uint16_t*)lo, pz, n, dims[0], dims[1], dims[2], c, fmt, total / 8,
-        halo_mode);
+        halo_mode, hw);
   else
     pack_act_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
         x, (uint16_t*)hi, (uint16_t*)lo, pz, n, dims[0], dims[1], dims[2], c, fmt, total,
-        halo_mode);
+        halo_mode, hw);
   S3_LAUNCH_CHECK("pack_act");
   return S3_OK;
 }

@@ -312,14 +312,18 @@ def pack_weights_umma(w, split=False, fmt=0, ndim=None, wmax=None):
     return hi, lo
 
 
-def pack_act_pad16(x, split=False, fmt=0, halo=S3_PAD_REFLECT):
+def pack_act_pad16(x, split=False, fmt=0, halo=S3_PAD_REFLECT, halo_width=1):
+    """fp32 channels-last -> 16-bit operand tensor(s) with the halo written.  ``halo_width`` 2
+    (zero halo only): the tensor of the extent + 2 with a one-voxel halo, all zeros outside."""
     x = _f32(x)
     ensure_device(x)
     n, dims, c, ndim = dims3(x.shape)
-    hi = torch.empty(pad16_shape(n, dims, c, ndim), device=x.device, dtype=_dt16(fmt))
+    grow = 2 * (halo_width - 1)
+    pdims = tuple(d + grow if (ndim == 3 or i > 0) else d for i, d in enumerate(dims))
+    hi = torch.empty(pad16_shape(n, pdims, c, ndim), device=x.device, dtype=_dt16(fmt))
     lo = torch.empty_like(hi) if split else None
-    _cabi.call("s3_pack_act_pad16_ex", _p(x), ndim, n, c_i32x3(*dims), c, _p(hi), _p(lo), fmt,
-               halo, _s())
+    _cabi.call("s3_pack_act_pad16_hw", _p(x), ndim, n, c_i32x3(*dims), c, _p(hi), _p(lo), fmt,
+               halo, halo_width, _s())
     _count()
     return hi, lo
 

@@ -542,7 +542,7 @@ class Plan:
     @staticmethod
     def _train_umma_same_ok(st, in_shape):
         """keras ``padding='same'`` 3x3[x3] convolutions (the discriminator) on tcgen05: stride 1,
-        or stride 2 on every dim; cin <= 64 or a multiple of 64, 64 | cout <= 512."""
+        or stride 2 on every dim; cin <= 64 or a multiple of 64; 32 <= cout <= 256 or 64 | cout <= 512."""
         conv = st.conv
         if st.pads is not None or conv.transposed or conv.padding != "same":
             return False
@@ -552,8 +552,9 @@ class Plan:
         if not (all(s == 1 for s in strides) or all(s == 2 for s in strides)):
             return False
         cin = in_shape[-1]
+        filters_ok = 32 <= conv.filters <= 256 or (conv.filters % 64 == 0 and conv.filters <= 512)
         return (conv.nd in (2, 3) and (cin <= 64 or (cin % 64 == 0 and cin <= 512))
-                and conv.filters % 64 == 0 and conv.filters <= 512
+                and filters_ok
                 and all(k == 3 for k in conv.kernel_size) and min(in_shape[1:-1]) >= 2)
 
     def _refresh_weight_maxima(self):

@@ -614,6 +614,13 @@ def test_fp16c_pack_is_exact(cuda, halo):
     bh, bl = ops.pack_act_pad16(xd, split=True, fmt=0, halo=halo)
     assert torch.equal(bh.reshape(xp.shape), xp.bfloat16())
     assert torch.equal(bl.reshape(xp.shape), (xp - xp.bfloat16().float()).bfloat16())
+    if halo == 0:
+        # zero halo two voxels wide == the zero-padded tensor packed with a one-voxel zero halo
+        h2, c2 = ops.pack_act_pad16(xd, split=True, fmt=2, halo=0, halo_width=2)
+        h1, c1 = ops.pack_act_pad16(ops.pad_fwd(xd, [(0, 0)] + [(1, 1)] * 3 + [(0, 0)], 0),
+                                    split=True, fmt=2, halo=0)
+        assert h2.shape == h1.shape and torch.equal(h2, h1)
+        assert torch.equal(c2.view(torch.uint8), c1.view(torch.uint8))
 
 
 FP16C_CASES = [
