@@ -133,3 +133,14 @@ def low_res_loss(x1, x2, s_enhance=1, t_enhance=1, t_method="average",
     if t_enhance > 1 and t_method.casefold() == "subsample":
         x1, x2 = x1[:, :, :, ::t_enhance, :], x2[:, :, :, ::t_enhance, :]
     return {"MeanSquaredError": mse, "MeanAbsoluteError": mae}[tf_loss](x1, x2) + ex
+
+
+def sliced_wasserstein_loss(x1, x2, proj):
+    """loss_metrics.py:754-793 with the (n_projections, H*W*T) projection matrix given (the
+    reference draws it with tf.random.normal and l2-normalises the rows)."""
+    x1, x2 = np.asarray(x1, np.float64), np.asarray(x2, np.float64)
+    b, c = x1.shape[0], x1.shape[-1]
+    p1 = np.asarray(proj, np.float64) @ x1.reshape(b, -1, c)      # (B, P, C)
+    p2 = np.asarray(proj, np.float64) @ x2.reshape(b, -1, c)
+    return float(np.mean((np.sort(p1, axis=1) - np.sort(p2, axis=1)) ** 2))
+

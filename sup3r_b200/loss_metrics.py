@@ -23,10 +23,11 @@ kernels -- so they mirror the reference classes term by term:
 ``SpatialFftLoss``         loss_metrics.py:395-437
 ``SpatiotemporalFftLoss``  loss_metrics.py:440-485
 ``LowResLoss``             loss_metrics.py:488-638
+``SlicedWassersteinLoss``  loss_metrics.py:724-793
 =========================  ==============================================================
 
-Out of scope: ``PerceptualLoss`` (needs a trained discriminator's feature maps),
-``SlicedWassersteinLoss`` (random projections).
+Out of scope: ``PerceptualLoss`` (loss_metrics.py:641-721: feature maps of a VGG16 with ImageNet
+weights, which cannot be obtained here).
 """
 from __future__ import annotations
 
@@ -307,13 +308,41 @@ class LowResLoss(_Base):
         return self._tf_loss(x1, x2) + ex_loss
 
 
+class SlicedWassersteinLoss(_Base):
+    """Sliced Wasserstein distance over random 1-D projections of the flattened space-time
+    axes (loss_metrics.py:724-793): ``proj (P, HWT) @ x (B, HWT, C) -> (B, P, C)``, both sides
+    sorted along axis 1, mean squared difference.  The projections are drawn on the device
+    (unit rows of a standard normal matrix) at every call, as the reference does."""
+
+    def __init__(self, n_projections=1024, **kwargs):
+        super().__init__(**kwargs)
+        self._n_projections = int(n_projections)
+
+    def projections(self, n_points, device):
+        proj = torch.randn((self._n_projections, n_points), device=device, dtype=torch.float32)
+        return proj / proj.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+    def __call__(self, x1, x2):
+        x1, x2 = self._pair(x1, x2)
+        if x1.dim() not in (4, 5) or x2.dim() != x1.dim():
+            raise AssertionError("The SlicedWassersteinLoss is meant to be used on spatial or "
+                                 "spatiotemporal data only. Received tensor(s) that are not 4D "
+                                 "or 5D")
+        b, c = x1.shape[0], x1.shape[-1]
+        x1_flat, x2_flat = x1.reshape(b, -1, c), x2.reshape(b, -1, c)
+        proj = self.projections(x1_flat.shape[1], x1.device)
+        x1_sorted = torch.sort(proj @ x1_flat, dim=1).values
+        x2_sorted = torch.sort(proj @ x2_flat, dim=1).values
+        return torch.mean((x1_sorted - x2_sorted) ** 2)
+
+
 LOSSES = {"MeanSquaredError": MeanSquaredError, "MeanAbsoluteError": MeanAbsoluteError,
           "ExpLoss": ExpLoss, "MmdLoss": MmdLoss, "MaterialDerivativeLoss": MaterialDerivativeLoss,
           "SpatialDerivativeLoss": SpatialDerivativeLoss,
           "TemporalDerivativeLoss": TemporalDerivativeLoss, "CoarseMseLoss": CoarseMseLoss,
           "SpatialExtremesLoss": SpatialExtremesLoss, "TemporalExtremesLoss": TemporalExtremesLoss,
           "SpatialFftLoss": SpatialFftLoss, "SpatiotemporalFftLoss": SpatiotemporalFftLoss,
-          "LowResLoss": LowResLoss}
+          "LowResLoss": LowResLoss, "SlicedWassersteinLoss": SlicedWassersteinLoss}
 
 
 def get_loss_class(name):

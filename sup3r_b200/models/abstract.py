@@ -587,7 +587,14 @@ class AbstractSingleModel(TensorboardMixIn):
         ``hi_res_exo``: {feature: tensor} for the exo layers."""
         x = to_device_tensor(low_res, self.torch_device())
         # (generator convolutions: tcgen05 forward + input gradient unless precision == "fp32")
-        return self.plan_for(self.generator, self.precision).forward_train(x, hi_res_exo or {})
+        plan = self.plan_for(self.generator, self.precision)
+        if not getattr(self, "_gen_on_tape", True):
+            # a step that trains no generator weight (the discriminator step): nothing of the
+            # generator is recorded -- no saved activations, no input gradient of the
+            # discriminator's first layer on the synthetic branch
+            with torch.no_grad():
+                return plan.forward_train(x, hi_res_exo or {})
+        return plan.forward_train(x, hi_res_exo or {})
 
     def _get_hr_exo_and_loss(self, low_res, hi_res_true, **calc_loss_kwargs):
         """Generator forward + loss (abstract.py:1175-1188)."""
@@ -606,9 +613,15 @@ class AbstractSingleModel(TensorboardMixIn):
         gradients are divided by it afterwards: the losses are means over ~1e6 hi-res values, so
         the raw activation gradients are ~1e-6 -- below the normal range of the fp16 operands the
         tensor-core input-gradient kernels use.  Exact for the fp32 kernels (power of two)."""
+        gen_ids = {id(w) for w in self.generator_weights}
+        self._gen_on_tape = any(id(w) in gen_ids for w in training_weights)
+        try:
+            with torch.enable_grad():
+                loss, loss_details, hi_res_gen, _ = self._get_hr_exo_and_loss(
+                    low_res, hi_res_true, **calc_loss_kwargs)
+        finally:
+            self._gen_on_tape = True
         with torch.enable_grad():
-            loss, loss_details, hi_res_gen, _ = self._get_hr_exo_and_loss(
-                low_res, hi_res_true, **calc_loss_kwargs)
             tensors = [w.value for w in training_weights]
             scale = self.grad_loss_scale(hi_res_gen, calc_loss_kwargs.get("train_gen", True))
             if scale != 1.0:

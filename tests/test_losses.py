@@ -119,6 +119,52 @@ def test_device_loss_matches_oracle_and_gradient(cuda, name, kwargs, shape, ref)
     assert abs(got - fd) <= 2e-3 * max(abs(fd), 1e-3) + 1e-6, (got, fd)
 
 
+def test_oracle_sliced_wasserstein_identities():
+    """Properties of the reference formula (loss_metrics.py:754-793): zero for equal inputs,
+    and with unit projections onto single points it is the squared difference of the sorted
+    point values."""
+    x = RNG.standard_normal((2, 3, 3, 2, 2)); y = RNG.standard_normal((2, 3, 3, 2, 2))
+    proj = RNG.standard_normal((16, 18)); proj /= np.linalg.norm(proj, axis=-1, keepdims=True)
+    assert R.sliced_wasserstein_loss(x, x, proj) == 0.0
+    assert R.sliced_wasserstein_loss(x, y, proj) > 0
+    eye = np.eye(18)
+    want = np.mean((np.sort(x.reshape(2, 18, 2), axis=1) - np.sort(y.reshape(2, 18, 2), axis=1)) ** 2)
+    assert np.isclose(R.sliced_wasserstein_loss(x, y, eye), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 5, 4, 3, 2), (3, 6, 5, 2)])
+def test_sliced_wasserstein_loss(cuda, shape, monkeypatch):
+    """Device loss == numpy restatement on the same projection matrix; gradient against float64
+    finite differences; fresh unit-norm projections at every call; zero for equal inputs."""
+    import torch
+    from sup3r_b200 import loss_metrics
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal(shape).astype(np.float32)
+    y = rng.standard_normal(shape).astype(np.float32)
+    fn = loss_metrics.get_loss_class("SlicedWassersteinLoss")(n_projections=48)
+    n_pts = int(np.prod(shape[1:-1]))
+    p_a = fn.projections(n_pts, torch.device(cuda))
+    p_b = fn.projections(n_pts, torch.device(cuda))
+    assert p_a.shape == (48, n_pts) and not torch.equal(p_a, p_b)
+    assert torch.allclose(p_a.norm(dim=-1), torch.ones(48, device=cuda), atol=1e-5)
+    proj = p_a.double().cpu().numpy()
+    monkeypatch.setattr(fn, "projections", lambda n, dev: p_a)
+    xt = torch.tensor(x, device=cuda, requires_grad=True)
+    yt = torch.tensor(y, device=cuda)
+    val = fn(xt, yt)
+    want = R.sliced_wasserstein_loss(x, y, proj)
+    assert val.ndim == 0 and abs(float(val) - want) <= 2e-5 * max(1.0, want)
+    assert float(fn(yt, yt)) == 0.0
+    val.backward()
+    d = rng.standard_normal(shape)
+    eps = 1e-6
+    fd = (R.sliced_wasserstein_loss(x + eps * d, y, proj)
+          - R.sliced_wasserstein_loss(x - eps * d, y, proj)) / (2 * eps)
+    got = float(np.sum(xt.grad.double().cpu().numpy() * d))
+    assert abs(got - fd) <= 2e-3 * max(abs(fd), 1e-3) + 1e-6, (got, fd)
+
+
 @pytest.mark.gpu
 def test_multiterm_loss(cuda):
     # reference tests/utilities/test_loss_metrics.py:292-309

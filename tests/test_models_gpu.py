@@ -611,3 +611,29 @@ def test_graphed_gradient_step_equals_eager_step(cuda, monkeypatch):
     fresh = make_model(gen_hl, disc_hl, lr_shape, hr_shape)
     fresh.generator.set_weights(m1.generator.get_weights())
     assert np.array_equal(m1.generate(batches[0][0]), fresh.generate(batches[0][0]))
+
+
+def test_sliced_wasserstein_training_draws_new_projections_in_graph_replays(cuda):
+    """reference tests/training/test_train_gan.py:250-296 trains with loss={'SlicedWassersteinLoss':
+    {}}, weight_gen_advers=0, generator only.  Here on one fixed batch with learning rate 0: the
+    weights never move, so the recorded loss changes from step to step only through the random
+    projections -- which must stay fresh when the step is replayed as a CUDA graph."""
+    gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
+    disc_hl = C.discriminator(3, "same", (16,))
+    lr_shape, hr_shape = (2, 4, 4, 4, 2), (2, 8, 8, 8, 2)
+    m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, learning_rate=0.0,
+                   loss={"SlicedWassersteinLoss": {"n_projections": 64}})
+    rng = np.random.default_rng(3)
+    lr = rng.standard_normal(lr_shape).astype(np.float32)
+    hr = rng.standard_normal(hr_shape).astype(np.float32)
+    w0 = [a.copy() for a in m.generator.get_weights()]
+    vals = []
+    for _ in range(6):
+        d = m.run_gradient_descent(lr, hr, m.generator_weights, weight_gen_advers=0.0,
+                                   train_gen=True, train_disc=False)
+        vals.append(float(d["loss_gen_content"]))
+    assert m._graphed_steps.stats["replays"] == 4
+    assert all(np.isfinite(v) and v > 0 for v in vals)
+    assert len(set(vals[2:])) == 4, vals            # four replays, four projection draws
+    assert np.std(vals) < 0.5 * np.mean(vals)       # same distance, different slices
+    assert all(np.array_equal(a, b) for a, b in zip(w0, m.generator.get_weights()))
