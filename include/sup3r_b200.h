@@ -307,6 +307,22 @@ int s3_gauss_smooth2d(const float* x, float* tmp, float* y, int n, int s1, int s
  * (the device-resident stand-in for sup3r/preprocessing/samplers/base.py get_next). */
 int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int* origins, int n,
                       int s1, int s2, int t, float* out, s3_stream stream);
+/* Empirical quantile delta mapping of a low-res chunk (sup3r/bias/bias_transforms.py:490-619
+ * _apply_qdm -> rex.utilities.bc_utils.QuantileDeltaMapping, dist "empirical"):
+ *   tau = F_mf(x), x_oh = F_oh^-1(tau), x_mh = F_mh^-1(tau),
+ *   out = relative ? x_oh * (x / x_mh) : x_oh + (x - x_mh)
+ * data / out: (n_sites, n_times) fp32; window[t]: time-window index of time step t; params_*:
+ * (n_sites, n_windows, n_quantiles) fp32 quantile values of the observed-historical, modeled-
+ * historical and modeled-future distributions (pass params_mh as params_mf for no_trend);
+ * quantiles: the n_quantiles levels (device doubles).  delta_denom_zero / delta_denom_min /
+ * delta_range[2] / out_range[2]: HOST pointers or NULL.  Interpolation restates np.interp in
+ * double precision.  n_bad: device counter of non-finite results (the reference raises). */
+int s3_qdm_bc(const float* data, const int* window, const float* params_oh,
+              const float* params_mh, const float* params_mf, const double* quantiles,
+              int n_sites, int n_times, int n_windows, int n_quantiles, int relative,
+              const double* delta_denom_zero, const double* delta_denom_min,
+              const double* delta_range, const double* out_range, float* out,
+              unsigned long long* n_bad, s3_stream stream);
 /* Gradient SUM over NVLink peer memory (sup3r/models/abstract.py:785-805 _sum_parallel_grad):
  * out[i] = peer_ptrs[0][i] + peer_ptrs[1][i] + ... in RANK ORDER (deterministic, identical on
  * every rank).  peer_ptrs: HOST array of `world` device pointers, one per rank, to the ranks' flat

@@ -5,6 +5,14 @@ sup3r/bias/utilities.py:296-332): the linear family of sup3r/bias/bias_transform
 or a dict of arrays (``"{feature}_scalar"``, ``"{feature}_adder"`` on the full low-res grid)
 instead of the reference's h5 files read through rex (a file format that is out of scope here).
 They act on the LOW-RES chunk (a few hundred KB) on the host before it is uploaded.
+
+``local_qdm_bc`` (:622-824) -- empirical quantile delta mapping -- runs on the device
+(``s3_qdm_bc``: three table interpolations per value, HBM-bound).  Its core lives in a
+third-party package the reference imports (``rex.utilities.bc_utils.QuantileDeltaMapping``,
+NREL-rex >= 0.2.91, absent here): the kernel restates the published algorithm (Cannon et al.
+2015, eq. 3-6) and is anchored on the known answers of the reference's own tests
+(tests/bias/test_qdm_bias_correction.py: identity, +-10 offsets, no_trend); PARITY WITH rex IS
+UNPINNED.  Parametric distributions (scipy.stats) and ``local_presrat_bc`` are out of scope.
 """
 from __future__ import annotations
 
@@ -100,17 +108,113 @@ def monthly_local_linear_bc(data, lat_lon, feature_name, bias_fp, months=None,
     return _clip(data * scalar + adder, out_range)
 
 
+def sample_q(n_samples, sampling="linear", log_base=10):
+    """Quantile levels of an empirical CDF table (rex.utilities.bc_utils sample_q_linear /
+    sample_q_log / sample_q_invlog): even spacing, or concentrated near 0 / near 1."""
+    if sampling == "linear":
+        return np.linspace(0, 1, n_samples)
+    log_q = (np.logspace(0, 1, n_samples, base=log_base) - 1) / (log_base - 1)
+    if sampling == "log":
+        return log_q
+    if sampling == "invlog":
+        return 1 - log_q[::-1]
+    raise KeyError(f'sampling option must be linear, log or invlog, got "{sampling}"')
+
+
+def _qdm_params(base_dset, feature_name, bias_fp):
+    src = np.load(bias_fp, allow_pickle=False) if isinstance(bias_fp, str) else bias_fp
+    names = {"base": f"base_{base_dset}_params", "bias": f"bias_{feature_name}_params",
+             "bias_fut": f"bias_fut_{feature_name}_params"}
+    out = {}
+    for k, n in names.items():
+        if n in src:
+            out[k] = np.asarray(src[n], dtype=np.float32)
+        elif k != "bias_fut":
+            raise RuntimeError(f'QDM distribution parameters "{n}" not found in '
+                               f"{bias_fp if isinstance(bias_fp, str) else list(src)}")
+    cfg = {"time_window_center": np.asarray(src["time_window_center"], dtype=np.float64)}
+    for k, default in (("dist", "empirical"), ("sampling", "linear"), ("log_base", 10)):
+        v = src[k] if k in src else default
+        cfg[k] = v.item() if isinstance(v, np.ndarray) else v
+    out["cfg"] = cfg
+    return out
+
+
+def local_qdm_bc(data, lat_lon, base_dset, feature_name, bias_fp, date_range_kwargs=None,
+                 lr_padded_slice=None, threshold=0.1, relative=True, no_trend=False,
+                 delta_denom_min=None, delta_denom_zero=None, delta_range=None, out_range=None,
+                 max_workers=1, day_of_year=None):
+    """Quantile delta mapping of one feature of a low-res chunk (bias_transforms.py:622-824).
+    ``data``: (s1, s2, t); the distribution tables ``base_{base_dset}_params``,
+    ``bias_{feature}_params``, ``bias_fut_{feature}_params`` (s1, s2, n_windows, n_quantiles) and
+    ``time_window_center`` come from ``bias_fp`` (.npz or dict).  Every time step uses the window
+    whose centre is closest to its day of year (``date_range_kwargs`` -> ``pd.date_range``, or
+    ``day_of_year`` directly)."""
+    import torch
+    from . import ops
+    data = np.asarray(data, dtype=np.float32)
+    assert data.ndim == 3, f"data was expected to be a 3D array but got shape {data.shape}"
+    if day_of_year is None:
+        import pandas as pd
+        day_of_year = pd.date_range(**date_range_kwargs).day_of_year
+    day_of_year = np.asarray(day_of_year)
+    assert data.shape[-1] == day_of_year.size, (
+        f"Time should align with data 3rd dimension but got data {data.shape} and time_index "
+        f"length {day_of_year.size}")
+    params = _qdm_params(base_dset, feature_name, bias_fp)
+    cfg = params["cfg"]
+    if cfg["dist"] != "empirical":
+        raise NotImplementedError(f'QDM with dist="{cfg["dist"]}": only empirical CDFs run here')
+    base, bias = params["base"], params["bias"]
+    bias_fut = params.get("bias_fut")
+    if lr_padded_slice is not None:
+        sl = (lr_padded_slice[0], lr_padded_slice[1])
+        base, bias = base[sl], bias[sl]
+        bias_fut = None if bias_fut is None else bias_fut[sl]
+    if no_trend or bias_fut is None:
+        bias_fut = bias             # (rex: params_mf defaults to params_mh)
+    window = np.array([np.argmin(abs(d - cfg["time_window_center"])) for d in day_of_year],
+                      dtype=np.int32)
+    n_q = base.shape[-1]
+    q = sample_q(n_q, cfg["sampling"], cfg["log_base"])
+    if not torch.cuda.is_available():
+        raise RuntimeError("local_qdm_bc runs on the CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shape = data.shape
+    t = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    flat = lambda a: t(a.reshape(-1, *a.shape[2:]))
+    out, bad = ops.qdm_bc(flat(data), t(window, torch.int32), flat(base), flat(bias),
+                          flat(bias_fut), t(q, torch.float64), relative=relative,
+                          delta_denom_zero=delta_denom_zero, delta_denom_min=delta_denom_min,
+                          delta_range=delta_range, out_range=out_range)
+    if int(bad.item()):
+        msg = ("QDM bias correction resulted in NaN / inf values! If this is a relative QDM, you "
+               "may try setting ``delta_denom_min`` or ``delta_denom_zero``")
+        logger.error(msg)
+        raise RuntimeError(msg)
+    return out.cpu().numpy().reshape(shape)
+
+
 METHODS = {"global_linear_bc": global_linear_bc, "local_linear_bc": local_linear_bc,
-           "monthly_local_linear_bc": monthly_local_linear_bc}
+           "monthly_local_linear_bc": monthly_local_linear_bc, "local_qdm_bc": local_qdm_bc}
 
 
-def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padded_slice=None):
+def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padded_slice=None,
+                          time_index=None):
     """Correct the channels of ``data`` (s1, s2, t, f) named in ``bc_kwargs`` in place
-    (bias/utilities.py:296-332).  ``bc_kwargs``: {feature: kwargs of the method}."""
+    (bias/utilities.py:215-332).  ``bc_kwargs``: {feature: kwargs of the method}.  A datetime
+    ``time_index`` of the chunk supplies what the reference passes as ``date_range_kwargs``:
+    the day of year of every step (``local_qdm_bc``) / its month (``monthly_local_linear_bc``)."""
+    from inspect import signature
     if bc_method not in METHODS:
         raise KeyError(f'Could not find bias correction method "{bc_method}"; available: '
-                       f"{sorted(METHODS)} (the quantile-mapping methods are out of scope)")
+                       f"{sorted(METHODS)} (local_presrat_bc is out of scope)")
     fun = METHODS[bc_method]
+    pars = signature(fun).parameters
+    dates = None
+    if time_index is not None and np.issubdtype(np.asarray(time_index).dtype, np.datetime64):
+        import pandas as pd
+        dates = pd.DatetimeIndex(np.asarray(time_index))
     for feat, kw in bc_kwargs.items():
         try:
             i = list(features).index(feat)
@@ -119,7 +223,13 @@ def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padd
                 data[..., i] = fun(data[..., i], **kw)
             else:
                 kw.setdefault("lr_padded_slice", lr_padded_slice)
-                data[..., i] = fun(data[..., i], lat_lon, feat, **kw)
+                kw.setdefault("feature_name", feat)
+                if dates is not None:
+                    if "day_of_year" in pars and "date_range_kwargs" not in kw:
+                        kw.setdefault("day_of_year", np.asarray(dates.day_of_year))
+                    if "months" in pars:
+                        kw.setdefault("months", np.asarray(dates.month))
+                data[..., i] = fun(data[..., i], lat_lon, **kw)
         except Exception as e:
             msg = (f"Could not run bias correction method {bc_method} on feature {feat} with "
                    f"input of shape {data.shape}. Received error: {e}")

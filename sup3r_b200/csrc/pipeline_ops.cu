@@ -146,6 +146,87 @@ __global__ void gather_samples_kernel(const float* __restrict__ data, float* __r
   }
 }
 
+// ---------------------------------------------------------------- quantile delta mapping
+// Empirical QDM (Cannon et al. 2015, eq. 3-6) as the reference applies it to a low-res chunk
+// (sup3r/bias/bias_transforms.py:490-619 -> rex.utilities.bc_utils.QuantileDeltaMapping):
+//   tau = F_mf(x);  x_oh = F_oh^-1(tau);  x_mh = F_mh^-1(tau);
+//   relative: x_oh * (x / x_mh)      absolute: x_oh + (x - x_mh)
+// with every CDF a table of N quantile values per site and time window, evaluated by linear
+// interpolation.  interp() restates numpy's np.interp in double precision without fused
+// multiply-adds (last index with xp[j] <= x; exact hit returns fp[j]; its NaN fall-backs).
+__device__ __forceinline__ double qdm_interp(double x, const float* __restrict__ xp_f,
+                                             const double* __restrict__ xp_d,
+                                             const float* __restrict__ fp_f,
+                                             const double* __restrict__ fp_d, int n) {
+  // exactly one of (xp_f, xp_d) and one of (fp_f, fp_d) is non-null
+  auto XP = [&](int i) { return xp_f ? (double)xp_f[i] : xp_d[i]; };
+  auto FP = [&](int i) { return fp_f ? (double)fp_f[i] : fp_d[i]; };
+  if (isnan(x)) return x;
+  if (x > XP(n - 1)) return FP(n - 1);
+  if (x < XP(0)) return FP(0);
+  int lo = 0, hi = n;                 // first index with xp > x
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if (x >= XP(mid)) lo = mid + 1; else hi = mid;
+  }
+  const int j = lo - 1;
+  if (j < 0) return FP(0);
+  if (j >= n - 1) return FP(n - 1);
+  const double xj = XP(j), fj = FP(j);
+  if (xj == x) return fj;
+  const double xj1 = XP(j + 1), fj1 = FP(j + 1);
+  const double slope = __ddiv_rn(__dsub_rn(fj1, fj), __dsub_rn(xj1, xj));
+  double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xj)), fj);
+  if (isnan(r)) {
+    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xj1)), fj1);
+    if (isnan(r) && fj == fj1) r = fj;
+  }
+  return r;
+}
+
+struct QdmParams {
+  int n_sites, n_times, n_win, n_q, relative, has_zero, has_min, has_range, has_out_range;
+  double denom_zero, denom_min, delta_lo, delta_hi, out_lo, out_hi;
+};
+
+// data / out: (site, time) float32; win: window index of every time step; tables (site, window,
+// quantile) float32; q: the N quantile levels (double).  bad: count of non-finite results.
+__global__ void qdm_kernel(const float* __restrict__ data, const int* __restrict__ win,
+                           const float* __restrict__ oh, const float* __restrict__ mh,
+                           const float* __restrict__ mf, const double* __restrict__ q,
+                           QdmParams p, float* __restrict__ out,
+                           unsigned long long* __restrict__ bad) {
+  const size_t total = (size_t)p.n_sites * p.n_times;
+  unsigned local_bad = 0;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % p.n_times);
+    const size_t site = idx / p.n_times;
+    const size_t row = (site * p.n_win + win[t]) * p.n_q;
+    const double x = (double)data[idx];
+    const double tau = qdm_interp(x, mf + row, nullptr, nullptr, q, p.n_q);
+    const double x_oh = qdm_interp(tau, nullptr, q, oh + row, nullptr, p.n_q);
+    double x_mh = qdm_interp(tau, nullptr, q, mh + row, nullptr, p.n_q);
+    double r;
+    if (p.relative) {
+      if (p.has_zero && x_mh == 0.0) x_mh = p.denom_zero;
+      if (p.has_min && !isnan(x_mh)) x_mh = fmax(x_mh, p.denom_min);   // np.maximum keeps NaN
+      double delta = __ddiv_rn(x, x_mh);
+      if (p.has_range && !isnan(delta)) delta = fmin(fmax(delta, p.delta_lo), p.delta_hi);
+      r = __dmul_rn(x_oh, delta);
+    } else {
+      double delta = __dsub_rn(x, x_mh);
+      if (p.has_range && !isnan(delta)) delta = fmin(fmax(delta, p.delta_lo), p.delta_hi);
+      r = __dadd_rn(x_oh, delta);
+    }
+    float rf = (float)r;
+    if (p.has_out_range && !isnan(rf)) rf = fminf(fmaxf(rf, (float)p.out_lo), (float)p.out_hi);
+    if (!isfinite(rf)) ++local_bad;
+    out[idx] = rf;
+  }
+  if (local_bad) atomicAdd(bad, (unsigned long long)local_bad);
+}
+
 }  // namespace s3
 
 using namespace s3;
@@ -272,6 +353,40 @@ __global__ void peer_sum_adam_kernel(PeerPtrs1 pp, int world, const AdamSeg* __r
 }
 
 }  // namespace s3
+
+extern "C" int s3_qdm_bc(const float* data, const int* window, const float* params_oh,
+                         const float* params_mh, const float* params_mf, const double* quantiles,
+                         int n_sites, int n_times, int n_windows, int n_quantiles, int relative,
+                         const double* delta_denom_zero, const double* delta_denom_min,
+                         const double* delta_range, const double* out_range, float* out,
+                         unsigned long long* n_bad, s3_stream stream) {
+  S3_REQUIRE(data && window && params_oh && params_mh && params_mf && quantiles && out && n_bad,
+             "s3_qdm_bc: null pointer");
+  S3_REQUIRE(n_sites > 0 && n_times > 0 && n_windows > 0 && n_quantiles >= 2,
+             "s3_qdm_bc: needs sites, times, windows > 0 and >= 2 quantiles");
+  s3::QdmParams p{};
+  p.n_sites = n_sites; p.n_times = n_times; p.n_win = n_windows; p.n_q = n_quantiles;
+  p.relative = relative ? 1 : 0;
+  if (delta_denom_zero) { p.has_zero = 1; p.denom_zero = *delta_denom_zero; }
+  if (delta_denom_min) { p.has_min = 1; p.denom_min = *delta_denom_min; }
+  if (delta_range) {
+    p.has_range = 1;
+    p.delta_lo = delta_range[0] < delta_range[1] ? delta_range[0] : delta_range[1];
+    p.delta_hi = delta_range[0] < delta_range[1] ? delta_range[1] : delta_range[0];
+  }
+  if (out_range) {
+    p.has_out_range = 1;
+    p.out_lo = out_range[0] < out_range[1] ? out_range[0] : out_range[1];
+    p.out_hi = out_range[0] < out_range[1] ? out_range[1] : out_range[0];
+  }
+  cudaStream_t st = as_stream(stream);
+  S3_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), st));
+  const size_t total = (size_t)n_sites * n_times;
+  s3::qdm_kernel<<<s3::pgrid(total), 256, 0, st>>>(data, window, params_oh, params_mh, params_mf,
+                                                   quantiles, p, out, n_bad);
+  S3_LAUNCH_CHECK("qdm_bc");
+  return S3_OK;
+}
 
 extern "C" int s3_peer_sum_adam(const void* const* peer_ptrs, int world, const void* segs_dev,
                                 int n_seg, unsigned long long max_n, float lr, float beta1,

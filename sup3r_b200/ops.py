@@ -694,3 +694,32 @@ def gather_samples(data, origins, sample_shape):
                _s())
     _count()
     return out
+
+
+def qdm_bc(data, window, params_oh, params_mh, params_mf, quantiles, relative=True,
+           delta_denom_zero=None, delta_denom_min=None, delta_range=None, out_range=None):
+    """Empirical quantile delta mapping on the device (``s3_qdm_bc``).  data (sites, times) f32,
+    window (times,) int32, params_* (sites, windows, n_q) f32, quantiles (n_q,) f64 -- all device
+    tensors.  Returns (corrected (sites, times) f32, number of non-finite results)."""
+    import ctypes as C
+    ensure_device(data)
+    n_sites, n_times = data.shape
+    n_win, n_q = params_oh.shape[1], params_oh.shape[2]
+    assert params_mh.shape == params_oh.shape == params_mf.shape and window.numel() == n_times
+    assert quantiles.dtype == torch.float64 and quantiles.numel() == n_q
+    assert window.dtype == torch.int32 and data.dtype == torch.float32
+
+    def opt(vals):
+        if vals is None:
+            return None
+        vals = list(vals) if isinstance(vals, (tuple, list)) else [vals]
+        return (C.c_double * len(vals))(*[float(v) for v in vals])
+    out = torch.empty_like(data)
+    bad = torch.zeros(1, device=data.device, dtype=torch.int64)
+    _cabi.call("s3_qdm_bc", _p(data), _p(window), _p(params_oh.contiguous()),
+               _p(params_mh.contiguous()), _p(params_mf.contiguous()), _p(quantiles), n_sites,
+               n_times, n_win, n_q, 1 if relative else 0, opt(delta_denom_zero),
+               opt(delta_denom_min), opt(delta_range), opt(out_range), _p(out), _p(bad), _s())
+    _count()
+    return out, bad
+

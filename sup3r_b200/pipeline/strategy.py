@@ -322,7 +322,8 @@ class ForwardPassStrategy:
             data = bias_correct_features(
                 np.array(data, dtype=np.float32, copy=True), self.features,
                 self.input_handler.lat_lon[lr_pad[0], lr_pad[1]], self.bias_correct_method,
-                self.bias_correct_kwargs, lr_padded_slice=(lr_pad[0], lr_pad[1], ti_pad))
+                self.bias_correct_kwargs, lr_padded_slice=(lr_pad[0], lr_pad[1], ti_pad),
+                time_index=self.input_handler.time_index[ti_pad])
         return data, exo
 
     def chunk_padded_shape(self, chunk_index):
