@@ -316,10 +316,15 @@ int s3_gather_samples(const float* data, int S1, int S2, int T, int F, const int
  * historical and modeled-future distributions (pass params_mh as params_mf for no_trend);
  * quantiles: the n_quantiles levels (device doubles).  delta_denom_zero / delta_denom_min /
  * delta_range[2] / out_range[2]: HOST pointers or NULL.  Interpolation restates np.interp in
- * double precision.  n_bad: device counter of non-finite results (the reference raises). */
+ * double precision.  tau_fut (n_sites, fp32) + k_factor (n_sites, n_windows, DOUBLES: the
+ * reference's k_range clipping promotes them), or both NULL: the PresRat
+ * step of local_presrat_bc (bias_transforms.py:1117-1120): results below tau_fut become 0, the
+ * others are scaled by the window's K factor.  n_bad: 2 device counters {non-finite results,
+ * NaN results} (local_qdm_bc raises on the first, local_presrat_bc on the second). */
 int s3_qdm_bc(const float* data, const int* window, const float* params_oh,
               const float* params_mh, const float* params_mf, const double* quantiles,
-              int n_sites, int n_times, int n_windows, int n_quantiles, int relative,
+              const float* tau_fut, const double* k_factor, int n_sites, int n_times,
+              int n_windows, int n_quantiles, int relative,
               const double* delta_denom_zero, const double* delta_denom_min,
               const double* delta_range, const double* out_range, float* out,
               unsigned long long* n_bad, s3_stream stream);

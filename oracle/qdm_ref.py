@@ -70,29 +70,47 @@ def apply_qdm(subset, base_params, bias_params, bias_fut_params, sampling="linea
 
 
 def local_qdm_bc(data, params, day_of_year, lr_padded_slice=None, relative=True, no_trend=False,
-                 delta_denom_min=None, delta_denom_zero=None, delta_range=None, out_range=None):
+                 delta_denom_min=None, delta_denom_zero=None, delta_range=None, out_range=None,
+                 presrat=False, k_range=None):
     """bias_transforms.py:752-824 on a dict of tables ``base`` / ``bias`` / ``bias_fut``
-    (s1, s2, n_windows, N) + ``cfg`` (time_window_center, sampling, log_base)."""
+    (s1, s2, n_windows, N) + ``cfg`` (time_window_center, sampling, log_base).  ``presrat``:
+    local_presrat_bc, bias_transforms.py:1063-1137 (+ ``bias_tau_fut`` (s1, s2, 1), ``k_factor``
+    (s1, s2, n_windows), ``cfg['zero_rate_threshold']``); unlike the reference, tau_fut and
+    k_factor follow ``lr_padded_slice`` (the reference leaves them on the full grid, which only
+    broadcasts for the full slice)."""
     assert data.ndim == 3
     cfg = params["cfg"]
     base, bias, fut = params["base"], params["bias"], params.get("bias_fut")
+    tau = k_factor = None
+    if presrat:
+        tau, k_factor = np.asarray(params["bias_tau_fut"]), params["k_factor"]
+        delta_denom_min = delta_denom_min or cfg["zero_rate_threshold"]
+        if k_range is not None:
+            k_factor = np.minimum(np.maximum(k_factor, np.min(k_range)), np.max(k_range))
     if lr_padded_slice is not None:
         sl = (lr_padded_slice[0], lr_padded_slice[1])
         base, bias = base[sl], bias[sl]
         fut = None if fut is None else fut[sl]
+        if presrat:
+            tau, k_factor = tau[sl], k_factor[sl]
     out = np.full(data.shape, np.nan, dtype=data.dtype)
     closest = np.array([np.argmin(abs(d - cfg["time_window_center"])) for d in day_of_year])
     for nt in set(closest):
         idx = closest == nt
         mf = None if fut is None else fut[:, :, nt]
-        out[:, :, idx] = apply_qdm(
+        subset = apply_qdm(
             data[:, :, idx], base[:, :, nt], bias[:, :, nt], mf,
             sampling=cfg.get("sampling", "linear"), log_base=cfg.get("log_base", 10),
             relative=relative, no_trend=no_trend or mf is None, delta_denom_min=delta_denom_min,
             delta_denom_zero=delta_denom_zero, delta_range=delta_range)
+        if presrat and not no_trend:
+            subset = np.where(subset < tau, 0, subset * k_factor[:, :, nt:nt + 1])
+        out[:, :, idx] = subset
     if out_range is not None:
         out = np.maximum(out, np.min(out_range))
         out = np.minimum(out, np.max(out_range))
-    if not np.isfinite(out).all():
+    if presrat and np.isnan(out).any():
+        raise RuntimeError("Presrat bias correction resulted in NaN values!")
+    if not presrat and not np.isfinite(out).all():
         raise RuntimeError("QDM bias correction resulted in NaN / inf values!")
     return out

@@ -93,7 +93,7 @@ SIGNATURES = {
     "s3_coarsen": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "s3_gauss_smooth2d": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, C.c_uint32, _P, _I, _P]),
     "s3_gather_samples": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
-    "s3_qdm_bc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "s3_qdm_bc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "s3_peer_sum_f32": (_I, [_P, _I, _SZ, _P, _P]),
     "s3_peer_sum_adam": (_I, [_P, _I, _P, _I, C.c_uint64, _F, _F, _F, _F, C.c_int64, _P]),
 }

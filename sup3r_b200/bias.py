@@ -12,7 +12,9 @@ third-party package the reference imports (``rex.utilities.bc_utils.QuantileDelt
 NREL-rex >= 0.2.91, absent here): the kernel restates the published algorithm (Cannon et al.
 2015, eq. 3-6) and is anchored on the known answers of the reference's own tests
 (tests/bias/test_qdm_bias_correction.py: identity, +-10 offsets, no_trend); PARITY WITH rex IS
-UNPINNED.  Parametric distributions (scipy.stats) and ``local_presrat_bc`` are out of scope.
+UNPINNED.  ``local_presrat_bc`` (:958-1137) adds its zero-rate / K-factor step to the same
+kernel.  Parametric distributions (scipy.stats) and the CALCULATION of the tables / factors
+(sup3r/bias/qdm.py, presrat.py) are out of scope.
 """
 from __future__ import annotations
 
@@ -121,23 +123,87 @@ def sample_q(n_samples, sampling="linear", log_base=10):
     raise KeyError(f'sampling option must be linear, log or invlog, got "{sampling}"')
 
 
-def _qdm_params(base_dset, feature_name, bias_fp):
+def _qdm_params(base_dset, feature_name, bias_fp, presrat=False):
     src = np.load(bias_fp, allow_pickle=False) if isinstance(bias_fp, str) else bias_fp
     names = {"base": f"base_{base_dset}_params", "bias": f"bias_{feature_name}_params",
              "bias_fut": f"bias_fut_{feature_name}_params"}
+    if presrat:     # bias_transforms.py:940-946
+        names.update(bias_tau_fut=f"{feature_name}_tau_fut", k_factor=f"{feature_name}_k_factor")
     out = {}
     for k, n in names.items():
         if n in src:
             out[k] = np.asarray(src[n], dtype=np.float32)
         elif k != "bias_fut":
-            raise RuntimeError(f'QDM distribution parameters "{n}" not found in '
+            raise RuntimeError(f'Bias correction parameters "{n}" not found in '
                                f"{bias_fp if isinstance(bias_fp, str) else list(src)}")
     cfg = {"time_window_center": np.asarray(src["time_window_center"], dtype=np.float64)}
-    for k, default in (("dist", "empirical"), ("sampling", "linear"), ("log_base", 10)):
+    defaults = [("dist", "empirical"), ("sampling", "linear"), ("log_base", 10)]
+    if presrat:
+        defaults.append(("zero_rate_threshold", None))
+    for k, default in defaults:
         v = src[k] if k in src else default
         cfg[k] = v.item() if isinstance(v, np.ndarray) else v
+    if presrat and cfg["zero_rate_threshold"] is None:
+        raise RuntimeError('PresRat parameters need the "zero_rate_threshold" attribute')
     out["cfg"] = cfg
     return out
+
+
+def _run_qdm(data, params, day_of_year, date_range_kwargs, lr_padded_slice, relative, no_trend,
+             delta_denom_min, delta_denom_zero, delta_range, out_range, k_range=None):
+    """Shared driver of ``local_qdm_bc`` / ``local_presrat_bc``: window of every time step, tables
+    of the chunk, one launch of ``s3_qdm_bc``.  Returns (out (s1, s2, t), [n_nonfinite, n_nan])."""
+    import torch
+    from . import ops
+    data = np.asarray(data, dtype=np.float32)
+    assert data.ndim == 3, f"data was expected to be a 3D array but got shape {data.shape}"
+    if day_of_year is None:
+        import pandas as pd
+        day_of_year = pd.date_range(**date_range_kwargs).day_of_year
+    day_of_year = np.asarray(day_of_year)
+    assert data.shape[-1] == day_of_year.size, (
+        f"Time should align with data 3rd dimension but got data {data.shape} and time_index "
+        f"length {day_of_year.size}")
+    cfg = params["cfg"]
+    if cfg["dist"] != "empirical":
+        raise NotImplementedError(f'QDM with dist="{cfg["dist"]}": only empirical CDFs run here')
+    base, bias = params["base"], params["bias"]
+    bias_fut = params.get("bias_fut")
+    tau, k_factor = params.get("bias_tau_fut"), params.get("k_factor")
+    if k_factor is not None and k_range is not None:
+        k_factor = np.minimum(np.maximum(k_factor, np.min(k_range)), np.max(k_range))
+    if lr_padded_slice is not None:
+        sl = (lr_padded_slice[0], lr_padded_slice[1])
+        base, bias = base[sl], bias[sl]
+        bias_fut = None if bias_fut is None else bias_fut[sl]
+        # (the reference leaves tau_fut / k_factor unsliced -- bias_transforms.py:1085-1090 --
+        #  which only broadcasts when the slice is the whole grid; here they follow the chunk)
+        tau = None if tau is None else tau[sl]
+        k_factor = None if k_factor is None else k_factor[sl]
+    if no_trend or bias_fut is None:
+        bias_fut = bias             # (rex: params_mf defaults to params_mh)
+    if no_trend:
+        tau = k_factor = None       # QDM only (bias_transforms.py:1114-1116)
+    window = np.array([np.argmin(abs(d - cfg["time_window_center"])) for d in day_of_year],
+                      dtype=np.int32)
+    q = sample_q(base.shape[-1], cfg["sampling"], cfg["log_base"])
+    if not torch.cuda.is_available():
+        raise RuntimeError("quantile delta mapping runs on the CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shape = data.shape
+
+    def t(a, dt=torch.float32):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+
+    def flat(a, dt=torch.float32):
+        return None if a is None else t(a.reshape(-1, *a.shape[2:]), dt)
+    out, bad = ops.qdm_bc(flat(data), t(window, torch.int32), flat(base), flat(bias),
+                          flat(bias_fut), t(q, torch.float64), relative=relative,
+                          delta_denom_zero=delta_denom_zero, delta_denom_min=delta_denom_min,
+                          delta_range=delta_range, out_range=out_range,
+                          tau_fut=None if tau is None else flat(tau).reshape(-1),
+                          k_factor=flat(k_factor, torch.float64))
+    return out.cpu().numpy().reshape(shape), bad.tolist()
 
 
 def local_qdm_bc(data, lat_lon, base_dset, feature_name, bias_fp, date_range_kwargs=None,
@@ -150,53 +216,42 @@ def local_qdm_bc(data, lat_lon, base_dset, feature_name, bias_fp, date_range_kwa
     ``time_window_center`` come from ``bias_fp`` (.npz or dict).  Every time step uses the window
     whose centre is closest to its day of year (``date_range_kwargs`` -> ``pd.date_range``, or
     ``day_of_year`` directly)."""
-    import torch
-    from . import ops
-    data = np.asarray(data, dtype=np.float32)
-    assert data.ndim == 3, f"data was expected to be a 3D array but got shape {data.shape}"
-    if day_of_year is None:
-        import pandas as pd
-        day_of_year = pd.date_range(**date_range_kwargs).day_of_year
-    day_of_year = np.asarray(day_of_year)
-    assert data.shape[-1] == day_of_year.size, (
-        f"Time should align with data 3rd dimension but got data {data.shape} and time_index "
-        f"length {day_of_year.size}")
     params = _qdm_params(base_dset, feature_name, bias_fp)
-    cfg = params["cfg"]
-    if cfg["dist"] != "empirical":
-        raise NotImplementedError(f'QDM with dist="{cfg["dist"]}": only empirical CDFs run here')
-    base, bias = params["base"], params["bias"]
-    bias_fut = params.get("bias_fut")
-    if lr_padded_slice is not None:
-        sl = (lr_padded_slice[0], lr_padded_slice[1])
-        base, bias = base[sl], bias[sl]
-        bias_fut = None if bias_fut is None else bias_fut[sl]
-    if no_trend or bias_fut is None:
-        bias_fut = bias             # (rex: params_mf defaults to params_mh)
-    window = np.array([np.argmin(abs(d - cfg["time_window_center"])) for d in day_of_year],
-                      dtype=np.int32)
-    n_q = base.shape[-1]
-    q = sample_q(n_q, cfg["sampling"], cfg["log_base"])
-    if not torch.cuda.is_available():
-        raise RuntimeError("local_qdm_bc runs on the CUDA device (there is no CPU fallback)")
-    dev = torch.device("cuda", torch.cuda.current_device())
-    shape = data.shape
-    t = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
-    flat = lambda a: t(a.reshape(-1, *a.shape[2:]))
-    out, bad = ops.qdm_bc(flat(data), t(window, torch.int32), flat(base), flat(bias),
-                          flat(bias_fut), t(q, torch.float64), relative=relative,
-                          delta_denom_zero=delta_denom_zero, delta_denom_min=delta_denom_min,
-                          delta_range=delta_range, out_range=out_range)
-    if int(bad.item()):
+    out, bad = _run_qdm(data, params, day_of_year, date_range_kwargs, lr_padded_slice, relative,
+                        no_trend, delta_denom_min, delta_denom_zero, delta_range, out_range)
+    if bad[0]:
         msg = ("QDM bias correction resulted in NaN / inf values! If this is a relative QDM, you "
                "may try setting ``delta_denom_min`` or ``delta_denom_zero``")
         logger.error(msg)
         raise RuntimeError(msg)
-    return out.cpu().numpy().reshape(shape)
+    return out
+
+
+def local_presrat_bc(data, lat_lon, base_dset, feature_name, bias_fp, date_range_kwargs=None,
+                     lr_padded_slice=None, threshold=0.1, relative=True, no_trend=False,
+                     delta_denom_min=None, delta_denom_zero=None, delta_range=None,
+                     k_range=None, out_range=None, max_workers=1, day_of_year=None):
+    """PresRat (Pierce et al. 2015) of one feature of a low-res chunk
+    (bias_transforms.py:958-1137): QDM with ``delta_denom_min`` defaulting to the file's
+    ``zero_rate_threshold``, then results below ``{feature}_tau_fut`` become dry (0) and the
+    others are scaled by the window's ``{feature}_k_factor`` (optionally clipped to ``k_range``)
+    -- both steps inside the same kernel.  Raises on NaN results only (the reference's check)."""
+    params = _qdm_params(base_dset, feature_name, bias_fp, presrat=True)
+    delta_denom_min = delta_denom_min or params["cfg"]["zero_rate_threshold"]
+    out, bad = _run_qdm(data, params, day_of_year, date_range_kwargs, lr_padded_slice, relative,
+                        no_trend, delta_denom_min, delta_denom_zero, delta_range, out_range,
+                        k_range=k_range)
+    if bad[1]:
+        msg = ("Presrat bias correction resulted in NaN values! If this is a relative QDM, you "
+               "may try setting ``delta_denom_min`` or ``delta_denom_zero``")
+        logger.error(msg)
+        raise RuntimeError(msg)
+    return out
 
 
 METHODS = {"global_linear_bc": global_linear_bc, "local_linear_bc": local_linear_bc,
-           "monthly_local_linear_bc": monthly_local_linear_bc, "local_qdm_bc": local_qdm_bc}
+           "monthly_local_linear_bc": monthly_local_linear_bc, "local_qdm_bc": local_qdm_bc,
+           "local_presrat_bc": local_presrat_bc}
 
 
 def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padded_slice=None,
@@ -208,7 +263,7 @@ def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padd
     from inspect import signature
     if bc_method not in METHODS:
         raise KeyError(f'Could not find bias correction method "{bc_method}"; available: '
-                       f"{sorted(METHODS)} (local_presrat_bc is out of scope)")
+                       f"{sorted(METHODS)}")
     fun = METHODS[bc_method]
     pars = signature(fun).parameters
     dates = None

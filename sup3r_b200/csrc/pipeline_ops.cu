@@ -194,15 +194,17 @@ struct QdmParams {
 __global__ void qdm_kernel(const float* __restrict__ data, const int* __restrict__ win,
                            const float* __restrict__ oh, const float* __restrict__ mh,
                            const float* __restrict__ mf, const double* __restrict__ q,
+                           const float* __restrict__ tau_fut, const double* __restrict__ k_factor,
                            QdmParams p, float* __restrict__ out,
                            unsigned long long* __restrict__ bad) {
   const size_t total = (size_t)p.n_sites * p.n_times;
-  unsigned local_bad = 0;
+  unsigned local_bad = 0, local_nan = 0;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int t = (int)(idx % p.n_times);
     const size_t site = idx / p.n_times;
-    const size_t row = (site * p.n_win + win[t]) * p.n_q;
+    const int w = win[t];
+    const size_t row = (site * p.n_win + w) * p.n_q;
     const double x = (double)data[idx];
     const double tau = qdm_interp(x, mf + row, nullptr, nullptr, q, p.n_q);
     const double x_oh = qdm_interp(tau, nullptr, q, oh + row, nullptr, p.n_q);
@@ -219,12 +221,17 @@ __global__ void qdm_kernel(const float* __restrict__ data, const int* __restrict
       if (p.has_range && !isnan(delta)) delta = fmin(fmax(delta, p.delta_lo), p.delta_hi);
       r = __dadd_rn(x_oh, delta);
     }
+    // PresRat (bias_transforms.py:1117-1120): dry days below the future zero-rate threshold,
+    // wet days scaled by the window's K factor
+    if (tau_fut) r = r < (double)tau_fut[site] ? 0.0 : __dmul_rn(r, k_factor[site * p.n_win + w]);
     float rf = (float)r;
     if (p.has_out_range && !isnan(rf)) rf = fminf(fmaxf(rf, (float)p.out_lo), (float)p.out_hi);
     if (!isfinite(rf)) ++local_bad;
+    if (isnan(rf)) ++local_nan;
     out[idx] = rf;
   }
   if (local_bad) atomicAdd(bad, (unsigned long long)local_bad);
+  if (local_nan) atomicAdd(bad + 1, (unsigned long long)local_nan);
 }
 
 }  // namespace s3
@@ -356,7 +363,8 @@ __global__ void peer_sum_adam_kernel(PeerPtrs1 pp, int world, const AdamSeg* __r
 
 extern "C" int s3_qdm_bc(const float* data, const int* window, const float* params_oh,
                          const float* params_mh, const float* params_mf, const double* quantiles,
-                         int n_sites, int n_times, int n_windows, int n_quantiles, int relative,
+                         const float* tau_fut, const double* k_factor, int n_sites, int n_times,
+                         int n_windows, int n_quantiles, int relative,
                          const double* delta_denom_zero, const double* delta_denom_min,
                          const double* delta_range, const double* out_range, float* out,
                          unsigned long long* n_bad, s3_stream stream) {
@@ -364,6 +372,8 @@ extern "C" int s3_qdm_bc(const float* data, const int* window, const float* para
              "s3_qdm_bc: null pointer");
   S3_REQUIRE(n_sites > 0 && n_times > 0 && n_windows > 0 && n_quantiles >= 2,
              "s3_qdm_bc: needs sites, times, windows > 0 and >= 2 quantiles");
+  S3_REQUIRE((tau_fut == nullptr) == (k_factor == nullptr),
+             "s3_qdm_bc: tau_fut and k_factor go together (PresRat) or are both NULL (QDM)");
   s3::QdmParams p{};
   p.n_sites = n_sites; p.n_times = n_times; p.n_win = n_windows; p.n_q = n_quantiles;
   p.relative = relative ? 1 : 0;
@@ -380,10 +390,10 @@ extern "C" int s3_qdm_bc(const float* data, const int* window, const float* para
     p.out_hi = out_range[0] < out_range[1] ? out_range[1] : out_range[0];
   }
   cudaStream_t st = as_stream(stream);
-  S3_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), st));
+  S3_CUDA(cudaMemsetAsync(n_bad, 0, 2 * sizeof(unsigned long long), st));
   const size_t total = (size_t)n_sites * n_times;
   s3::qdm_kernel<<<s3::pgrid(total), 256, 0, st>>>(data, window, params_oh, params_mh, params_mf,
-                                                   quantiles, p, out, n_bad);
+                                                   quantiles, tau_fut, k_factor, p, out, n_bad);
   S3_LAUNCH_CHECK("qdm_bc");
   return S3_OK;
 }

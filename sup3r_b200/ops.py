@@ -697,10 +697,12 @@ def gather_samples(data, origins, sample_shape):
 
 
 def qdm_bc(data, window, params_oh, params_mh, params_mf, quantiles, relative=True,
-           delta_denom_zero=None, delta_denom_min=None, delta_range=None, out_range=None):
+           delta_denom_zero=None, delta_denom_min=None, delta_range=None, out_range=None,
+           tau_fut=None, k_factor=None):
     """Empirical quantile delta mapping on the device (``s3_qdm_bc``).  data (sites, times) f32,
-    window (times,) int32, params_* (sites, windows, n_q) f32, quantiles (n_q,) f64 -- all device
-    tensors.  Returns (corrected (sites, times) f32, number of non-finite results)."""
+    window (times,) int32, params_* (sites, windows, n_q) f32, quantiles (n_q,) f64, optional
+    PresRat tau_fut (sites,) f32 / k_factor (sites, windows) f64 -- all device tensors.  Returns
+    (corrected (sites, times) f32, device counters [non-finite results, NaN results])."""
     import ctypes as C
     ensure_device(data)
     n_sites, n_times = data.shape
@@ -715,9 +717,14 @@ def qdm_bc(data, window, params_oh, params_mh, params_mf, quantiles, relative=Tr
         vals = list(vals) if isinstance(vals, (tuple, list)) else [vals]
         return (C.c_double * len(vals))(*[float(v) for v in vals])
     out = torch.empty_like(data)
-    bad = torch.zeros(1, device=data.device, dtype=torch.int64)
+    bad = torch.zeros(2, device=data.device, dtype=torch.int64)
+    if tau_fut is not None:
+        assert tau_fut.numel() == n_sites and tuple(k_factor.shape) == (n_sites, n_win)
+        assert k_factor.dtype == torch.float64 and tau_fut.dtype == torch.float32
+        tau_fut, k_factor = tau_fut.contiguous(), k_factor.contiguous()
     _cabi.call("s3_qdm_bc", _p(data), _p(window), _p(params_oh.contiguous()),
-               _p(params_mh.contiguous()), _p(params_mf.contiguous()), _p(quantiles), n_sites,
+               _p(params_mh.contiguous()), _p(params_mf.contiguous()), _p(quantiles),
+               _p(tau_fut), _p(k_factor), n_sites,
                n_times, n_win, n_q, 1 if relative else 0, opt(delta_denom_zero),
                opt(delta_denom_min), opt(delta_range), opt(out_range), _p(out), _p(bad), _s())
     _count()

@@ -177,7 +177,7 @@ def test_bias_transforms_match_reference(tmp_path):
         bias.bias_correct_features(np.zeros((6, 5, 8, 1), np.float32), ["v"], None,
                                    "local_linear_bc", {"v": {"bias_fp": fp}})
     with pytest.raises(KeyError):
-        bias.bias_correct_features(np.zeros((6, 5, 8, 1), np.float32), ["u"], None, "local_presrat_bc",
+        bias.bias_correct_features(np.zeros((6, 5, 8, 1), np.float32), ["u"], None, "no_such_bc",
                                    {"u": {}})
 
 

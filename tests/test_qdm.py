@@ -89,14 +89,80 @@ def test_oracle_quantile_sampling():
 
 def test_host_side_rejects_what_does_not_run_here():
     from sup3r_b200 import bias
-    assert "local_qdm_bc" in bias.METHODS
+    assert "local_qdm_bc" in bias.METHODS and "local_presrat_bc" in bias.METHODS
     assert np.array_equal(bias.sample_q(11, "invlog", 7), R.sample_q(11, "invlog", 7))
     with pytest.raises(KeyError):
         bias.bias_correct_features(np.zeros((2, 2, 2, 1), np.float32), ["u"], None,
-                                   "local_presrat_bc", {"u": {}})
+                                   "no_such_bc", {"u": {}})
+
+
+def make_presrat(p, thr=0.5):
+    s1, s2, n_win = p["base"].shape[:3]
+    p = dict(p)
+    p["bias_tau_fut"] = RNG.uniform(5, 60, (s1, s2, 1)).astype(np.float32)
+    p["k_factor"] = RNG.uniform(0.7, 1.4, (s1, s2, n_win)).astype(np.float32)
+    p["cfg"] = dict(p["cfg"], zero_rate_threshold=thr)
+    return p
+
+
+def test_oracle_presrat_identities():
+    """tests/bias/test_presrat_bias_correction.py:633-736: identical CDFs + zero tau + K = 1 ->
+    no change; zero tau -> no wet value turned dry; PresRat has at least as many values below
+    tau as QDM; and PresRat == where(QDM < tau, 0, QDM * K) with the threshold as denominator
+    floor (bias_transforms.py:1076, 1117-1120)."""
+    p = make_presrat(make_params())
+    data, doy = make_data(p)
+    pr = R.local_qdm_bc(data, p, doy, presrat=True)
+    qd = R.local_qdm_bc(data, p, doy, delta_denom_min=0.5)
+    k = p["k_factor"][:, :, [int(np.argmin(abs(d - p["cfg"]["time_window_center"]))) for d in doy]]
+    clear = np.abs(qd - p["bias_tau_fut"]) > 1e-3     # (qd is the fp32-rounded QDM result)
+    want = np.where(qd < p["bias_tau_fut"], 0, qd.astype(np.float64) * k)
+    assert np.allclose(pr[clear], want[clear], rtol=1e-6, atol=0)
+    assert (pr < p["bias_tau_fut"]).sum() >= (qd < p["bias_tau_fut"]).sum() > 0
+    nz = dict(p, bias_tau_fut=p["bias_tau_fut"] * 0)
+    out = R.local_qdm_bc(data, nz, doy, presrat=True)
+    assert not ((data > 0) & (out == 0)).any() and not np.allclose(out, data)
+    same = dict(nz, base=p["bias_fut"], bias=p["bias_fut"], k_factor=p["k_factor"] * 0 + 1,
+                cfg=dict(p["cfg"], zero_rate_threshold=0))
+    out = R.local_qdm_bc(data, same, doy, presrat=True)
+    inside = (data >= p["bias_fut"].min(axis=(2, 3))[..., None]) & \
+        (data <= p["bias_fut"].max(axis=(2, 3))[..., None]) & (np.abs(data) > 1e-3)
+    assert np.allclose(out[inside], data[inside], rtol=1e-5)
+    # no_trend: QDM only (bias_transforms.py:1114-1116)
+    assert np.array_equal(R.local_qdm_bc(data, p, doy, presrat=True, no_trend=True),
+                          R.local_qdm_bc(data, p, doy, no_trend=True, delta_denom_min=0.5))
 
 
 # ---------------------------------------------------------------------------- CUDA kernel (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [dict(), dict(relative=False, k_range=(0.9, 1.1)),
+                                  dict(no_trend=True), dict(out_range=(0.0, 400.0),
+                                                            delta_range=(0.2, 3.0))],
+                         ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()) or "default")
+def test_cuda_presrat_equals_oracle_bit_for_bit(cuda, case):
+    from sup3r_b200 import bias
+    p = make_presrat(make_params())
+    data, doy = make_data(p, n_t=45)
+    src = {"base_ghi_params": p["base"], "bias_rsds_params": p["bias"],
+           "bias_fut_rsds_params": p["bias_fut"], "rsds_tau_fut": p["bias_tau_fut"],
+           "rsds_k_factor": p["k_factor"], **p["cfg"]}
+    sl = (slice(0, 3), slice(1, 4))
+    for lrps in (None, sl):
+        d = data if lrps is None else data[sl]
+        want = R.local_qdm_bc(d, p, doy, lr_padded_slice=lrps, presrat=True, **case)
+        got = bias.local_presrat_bc(d, None, "ghi", "rsds", src, day_of_year=doy,
+                                    lr_padded_slice=lrps, **case)
+        assert np.array_equal(got, want), np.abs(got - want).max()
+        assert (got == 0).any() or case.get("no_trend")
+    bad = data.copy()
+    bad[0, 0, 0] = np.nan
+    with pytest.raises(RuntimeError, match="NaN values"):
+        bias.local_presrat_bc(bad, None, "ghi", "rsds", src, day_of_year=doy)
+    with pytest.raises(RuntimeError, match="zero_rate_threshold"):
+        bias.local_presrat_bc(data, None, "ghi", "rsds",
+                              {k: v for k, v in src.items() if k != "zero_rate_threshold"},
+                              day_of_year=doy)
+
 CASES = [
     dict(relative=True),
     dict(relative=False),
