@@ -48,3 +48,15 @@ span = evs[-1].time_range.end - evs[0].time_range.start
 print(f"training step batch {B}: {len(evs)} kernels, device sum {tot / 1e3:.1f} ms, span {span / 1e3:.1f} ms")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
     print(f"{k:90s} n={v[0]:4d} {v[1] / 1e3:8.2f} ms {100 * v[1] / tot:5.1f}%")
+# the longest individual launches (which layer shapes carry the step)
+print("longest launches:")
+for e in sorted(evs, key=lambda e: -e.device_time)[:28]:
+    print(f"  {e.device_time:8.1f} us  {e.name[:70]}")
+# histogram of the ring kernel's launch durations
+ring = sorted(e.device_time for e in evs if "zring" in e.name)
+if ring:
+    import numpy as _np
+    r = _np.array(ring)
+    print(f"ring kernel: n={len(r)} median {_np.median(r):.1f} us, <15us: {(r < 15).sum()}, "
+          f"15-50us: {((r >= 15) & (r < 50)).sum()}, >=50us: {(r >= 50).sum()} "
+          f"(sum {r[r >= 50].sum() / 1e3:.2f} ms)")
