@@ -637,3 +637,38 @@ def test_sliced_wasserstein_training_draws_new_projections_in_graph_replays(cuda
     assert len(set(vals[2:])) == 4, vals            # four replays, four projection draws
     assert np.std(vals) < 0.5 * np.mean(vals)       # same distance, different slices
     assert all(np.array_equal(a, b) for a, b in zip(w0, m.generator.get_weights()))
+
+
+def test_failed_graph_capture_falls_back_to_the_eager_step(cuda, monkeypatch):
+    """A capture that raises (e.g. a host synchronisation inside a user-supplied loss) leaves the
+    model on the eager path for that configuration, with every packed-weight cache invalidated:
+    the run equals the one with graphs switched off."""
+    from sup3r_b200.train_graph import GraphedSteps
+    gen_hl = C.spatiotemporal_generator(2, 2, (2,), n_blocks=1)
+    disc_hl = C.discriminator(3, "same", (16,))
+    lr_shape, hr_shape = (2, 4, 4, 4, 2), (2, 8, 8, 8, 2)
+    rng = np.random.default_rng(23)
+    batches = [(rng.standard_normal(lr_shape).astype(np.float32),
+                rng.standard_normal(hr_shape).astype(np.float32)) for _ in range(5)]
+
+    def run():
+        m = make_model(gen_hl, disc_hl, lr_shape, hr_shape, learning_rate=1e-3)
+        hist = [{k: float(v) for k, v in m.run_gradient_descent(
+            lr, hr, m.generator_weights, weight_gen_advers=1e-2, train_gen=True,
+            train_disc=False, compute_disc=True).items()} for lr, hr in batches]
+        return hist, m.generator.get_weights(), m
+
+    monkeypatch.setenv("SUP3R_B200_TRAIN_GRAPH", "0")
+    h0, w0, _ = run()
+    monkeypatch.setenv("SUP3R_B200_TRAIN_GRAPH", "1")
+    calls = []
+
+    def broken(self, *a, **k):
+        calls.append(1)
+        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+            raise RuntimeError("host synchronisation while capturing")
+    monkeypatch.setattr(GraphedSteps, "_capture", broken)
+    h1, w1, m1 = run()
+    assert len(calls) == 1 and m1._graphed_steps.stats["replays"] == 0
+    assert list(m1._graphed_steps._steps.values()) == [False]
+    assert h0 == h1 and all(np.array_equal(a, b) for a, b in zip(w0, w1))
