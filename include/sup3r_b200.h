@@ -198,6 +198,16 @@ int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi
  * then called with s3_umma_tuning.acc_scale = 1 / scale). */
 int s3_pack_weights_umma_c(const float* w, int taps, int cin, int cout, void* w_hi, void* w_corr,
                            float scale, int layout, s3_stream stream);
+/* The same packing of a VIEW of the keras kernel w (taps, src_cin, src_cout), so that the
+ * training step never materialises sliced / padded / flipped copies of its weights:
+ *   adjoint == 0: rows ci0 .. ci0+63 (input channels), columns co0 .. co0+cout-1;
+ *   adjoint == 1: the operand of the input-gradient convolution (tape.gradient w.r.t. the
+ *                 layer input, abstract.py:1230-1238): taps flipped, row r = output channel
+ *                 ci0 + r of w, column c = input channel co0 + c of w.
+ * Elements outside w are zero. */
+int s3_pack_weights_umma_view(const float* w, int taps, int src_cin, int src_cout, int ci0,
+                              int co0, int adjoint, int cout, void* w_hi, void* w_corr,
+                              float scale, int layout, s3_stream stream);
 /* f32 (n, z, y, x, c) -> 16-bit (n, z+2*pz, y+2, x+2, c), pz = (ndim == 3), reflect halo.
  * fmt S3_FMT_FP16C (c == 64): lo receives the e4m3 correction rows (same byte geometry). */
 int s3_pack_act_pad16(const float* x, int ndim, int n, const int32_t dims[3], int c, void* hi,

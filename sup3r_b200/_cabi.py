@@ -65,6 +65,7 @@ SIGNATURES = {
     "s3_umma_weight_layout": (_I, [_I, _I, _I]),
     "s3_pack_weights_umma": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "s3_pack_weights_umma_c": (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _P]),
+    "s3_pack_weights_umma_view": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P]),
     "s3_pack_act_pad16": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _P]),
     "s3_pack_act_pad16_ex": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _I, _P]),
     "s3_pack_act_pad16_hw": (_I, [_P, _I, _I, c_i32x3, _I, _P, _P, _I, _I, _I, _P]),

@@ -92,19 +92,19 @@ class ConvUmmaFn(torch.autograd.Function):
     (sup3r/models/abstract.py:1131-1173, 1230-1238; base.py:283-313)."""
 
     @staticmethod
-    def _pack_w(cache, key, ver, make, nd):
+    def _pack_w(cache, key, ver, w, ci0, co0, cout, adjoint, nd):
+        """Packed fp16c operand of a 64-row view of ``w`` (see ``ops.pack_weights_umma_view``:
+        slices, zero padding, the flip / transpose of the input-gradient kernel all happen inside
+        the packing kernel), cached per weight version."""
         hit = cache.get(key)
         if hit is None or hit[0] != ver:
+            # cache["wmax"]: max |w| of the whole kernel for this weight version (set by
+            # Plan.forward_train for all layers with ONE host read per step); every view shares
+            # it (its own maximum can only be smaller)
+            wmax = cache.get("wmax")
             with torch.no_grad():
-                wk = make()
-                if wk.shape[-2] < 64:     # zero rows for the padded input channels
-                    wk = torch.nn.functional.pad(wk, (0, 0, 0, 64 - wk.shape[-2]))
-                # cache["wmax"]: max |w| of the whole kernel for this weight version (set by
-                # Plan.forward_train for all layers with ONE host read per step); slices and
-                # flipped views share it (their own maximum can only be smaller)
-                wmax = cache.get("wmax")
-                hit = (ver, *ops.pack_weights_umma(
-                    wk.contiguous(), ndim=nd, fmt=ops.S3_FMT_FP16C,
+                hit = (ver, *ops.pack_weights_umma_view(
+                    w.detach(), ci0, co0, cout, adjoint=adjoint, ndim=nd,
                     wmax=wmax[1] if (wmax is not None and wmax[0] == ver[0]) else None))
             cache[key] = hit
         return hit[1:]
@@ -150,10 +150,8 @@ class ConvUmmaFn(torch.autograd.Function):
             c1 = min(cout, c0 + 256)
             y = None
             for gi in range(gin):
-                w_hi, w_c, acc = ConvUmmaFn._pack_w(
-                    cache, ("fwd", gi, c0), ver,
-                    lambda: w.detach()[..., 64 * gi:64 * gi + 64, c0:c1] if gin > 1
-                    else w.detach()[..., c0:c1], nd)
+                w_hi, w_c, acc = ConvUmmaFn._pack_w(cache, ("fwd", gi, c0), ver, w, 64 * gi, c0,
+                                                    c1 - c0, False, nd)
                 sp = ConvUmmaFn._kernel_spec(spec, nd, cout=c1 - c0)
                 if not fuse_act:
                     sp = dataclasses.replace(sp, act=S3_ACT_NONE, alpha=0.0)
@@ -221,15 +219,10 @@ class ConvUmmaFn(torch.autograd.Function):
                     c1 = min(cin_p, c0 + 256)
                     dxp = None
                     for go in range(gout):
-                        def make(go=go, c0=c0, c1=c1):
-                            wt = w.detach()[..., 64 * go:64 * go + 64]
-                            if wt.shape[-1] < 64:
-                                wt = torch.nn.functional.pad(wt, (0, 64 - wt.shape[-1]))
-                            wt = wt.flip(dims=tuple(range(nd))).transpose(-1, -2)
-                            if cin_p != cin:
-                                wt = torch.nn.functional.pad(wt, (0, cin_p - cin))
-                            return wt[..., c0:c1]
-                        w_hi, w_c, acc = ConvUmmaFn._pack_w(cache, ("dgrad", go, c0), ver, make, nd)
+                        # (flipped taps, rows = output channels of block go, columns = input
+                        #  channels c0 .. c1 of w: a view packed without copies)
+                        w_hi, w_c, acc = ConvUmmaFn._pack_w(cache, ("dgrad", go, c0), ver, w,
+                                                            64 * go, c0, c1 - c0, True, nd)
                         sp = ConvUmmaFn._kernel_spec(lin, nd, cout=c1 - c0)
                         dxp, _, _ = ops.conv_fwd_umma(g_parts[go][0], g_parts[go][1], w_hi, w_c,
                                                       None, sp, gn, gdims, residual=dxp,

@@ -393,9 +393,16 @@ __global__ void unpack_act_kernel(const uint16_t* __restrict__ hi, const uint16_
   }
 }
 
+// A view of a keras kernel (taps, src_cin, src_cout): rows ci0.. / columns co0.. (zero outside the
+// tensor), or -- adjoint -- the spatially flipped kernel with input and output channels swapped
+// (the operand of the input-gradient convolution), without materialising either.
+struct WView {
+  int src_cin, src_cout, ci0, co0, adjoint;
+};
+
 __global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi,
                               uint16_t* __restrict__ lo, int taps, int cin, int cout, int npad,
-                              int fmt, int layout, size_t total, float scale) {
+                              int fmt, int layout, size_t total, float scale, WView v) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     size_t t = idx;
@@ -406,16 +413,25 @@ __global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict_
       const int dz = tap % 3, dydx = tap / 3;
       tap = dz * 9 + dydx;
     }
-    float v = (co < cout ? w[((size_t)tap * cin + ci) * cout + co] : 0.f) * scale;
-    uint16_t h = to16(v, fmt);
+    float val = 0.f;
+    if (co < cout) {
+      // source element: plain (tap, ci0 + ci, co0 + co); adjoint (taps-1-tap, co0 + co, ci0 + ci)
+      const int st = v.adjoint ? taps - 1 - tap : tap;
+      const int sci = v.adjoint ? v.co0 + co : v.ci0 + ci;
+      const int sco = v.adjoint ? v.ci0 + ci : v.co0 + co;
+      if (sci < v.src_cin && sco < v.src_cout)
+        val = w[((size_t)st * v.src_cin + sci) * v.src_cout + sco];
+    }
+    val *= scale;
+    uint16_t h = to16(val, fmt);
     hi[idx] = h;
     if (lo) {
       if (fmt == kFmtFp16c) {   // corr row (cin == 64): [e4m3(w S 2^-11) | e4m3(w S - hi)] per half
         uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (idx - ci) * 2;
-        row[corr_byte(0, ci)] = (uint8_t)e4m3x2(v * kCorrInv, 0.f);
-        row[corr_byte(1, ci)] = (uint8_t)e4m3x2(v - from16(h, fmt), 0.f);
+        row[corr_byte(0, ci)] = (uint8_t)e4m3x2(val * kCorrInv, 0.f);
+        row[corr_byte(1, ci)] = (uint8_t)e4m3x2(val - from16(h, fmt), 0.f);
       } else {
-        lo[idx] = to16(v - from16(h, fmt), fmt);
+        lo[idx] = to16(val - from16(h, fmt), fmt);
       }
     }
   }
@@ -872,34 +888,51 @@ extern "C" int s3_cast_f16(const float* x, void* y, size_t n, s3_stream stream) 
 
 extern "C" int s3_umma_npad(int cout) { return (cout + 15) / 16 * 16; }
 
+namespace s3 { struct WView; }
 static int pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
-                             int fmt, int layout, float scale, s3_stream stream);
+                             int fmt, int layout, float scale, s3_stream stream,
+                             const WView* view);
 
 extern "C" int s3_pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi,
                                     void* w_lo, int fmt, int layout, s3_stream stream) {
   S3_REQUIRE(fmt != kFmtFp16c, "s3_pack_weights_umma: fp16c weights carry a scale, use "
              "s3_pack_weights_umma_c");
-  return pack_weights_umma(w, taps, cin, cout, w_hi, w_lo, fmt, layout, 1.f, stream);
+  return pack_weights_umma(w, taps, cin, cout, w_hi, w_lo, fmt, layout, 1.f, stream, nullptr);
 }
 
 extern "C" int s3_pack_weights_umma_c(const float* w, int taps, int cin, int cout, void* w_hi,
                                       void* w_corr, float scale, int layout, s3_stream stream) {
   S3_REQUIRE(w_corr && scale > 0.f, "s3_pack_weights_umma_c: needs w_corr and a positive scale");
-  return pack_weights_umma(w, taps, cin, cout, w_hi, w_corr, kFmtFp16c, layout, scale, stream);
+  return pack_weights_umma(w, taps, cin, cout, w_hi, w_corr, kFmtFp16c, layout, scale, stream,
+                           nullptr);
 }
 
 static int pack_weights_umma(const float* w, int taps, int cin, int cout, void* w_hi, void* w_lo,
-                             int fmt, int layout, float scale, s3_stream stream) {
+                             int fmt, int layout, float scale, s3_stream stream,
+                             const WView* view) {
   S3_REQUIRE(layout == 0 || (layout == 1 && taps == 27),
              "s3_pack_weights_umma: layout 1 (zcat) needs 27 taps");
   S3_REQUIRE(w && w_hi && taps > 0 && cin == 64 && cout > 0 && cout <= 256,
              "s3_pack_weights_umma: needs cin == 64 and cout <= 256 (got %d, %d)", cin, cout);
   const int npad = s3_umma_npad(cout);
   size_t total = (size_t)taps * npad * cin;
+  WView v{cin, cout, 0, 0, 0};
+  if (view) v = *view;
   pack_w_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
-      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, layout, total, scale);
+      w, (uint16_t*)w_hi, (uint16_t*)w_lo, taps, cin, cout, npad, fmt, layout, total, scale, v);
   S3_LAUNCH_CHECK("pack_w");
   return S3_OK;
+}
+
+extern "C" int s3_pack_weights_umma_view(const float* w, int taps, int src_cin, int src_cout,
+                                         int ci0, int co0, int adjoint, int cout, void* w_hi,
+                                         void* w_corr, float scale, int layout,
+                                         s3_stream stream) {
+  S3_REQUIRE(w_corr && scale > 0.f, "s3_pack_weights_umma_view: needs w_corr and a scale > 0");
+  S3_REQUIRE(src_cin > 0 && src_cout > 0 && ci0 >= 0 && co0 >= 0,
+             "s3_pack_weights_umma_view: bad view");
+  WView v{src_cin, src_cout, ci0, co0, adjoint ? 1 : 0};
+  return pack_weights_umma(w, taps, 64, cout, w_hi, w_corr, kFmtFp16c, layout, scale, stream, &v);
 }
 
 extern "C" int s3_content_loss(const float* gen, const float* truth, size_t nvox, int c, int c_use,

@@ -312,6 +312,32 @@ def pack_weights_umma(w, split=False, fmt=0, ndim=None, wmax=None):
     return hi, lo
 
 
+def pack_weights_umma_view(w, ci0, co0, cout, adjoint=False, ndim=None, wmax=None):
+    """fp16c packing of a view of the keras kernel ``w (*k, cin, cout_w)`` without copies
+    (``s3_pack_weights_umma_view``): 64 rows from input channel ``ci0`` and ``cout`` columns from
+    output channel ``co0`` -- or, ``adjoint``, the flipped kernel with the channel roles swapped
+    (rows = output channels from ``ci0``, columns = input channels from ``co0``), the operand of
+    the input-gradient convolution.  Zero outside ``w``.  -> (hi, corr, acc_scale)."""
+    import math
+    w = _f32(w)
+    ensure_device(w)
+    src_cin, src_cout = w.shape[-2], w.shape[-1]
+    taps = w.numel() // (src_cin * src_cout)
+    if ndim is None:
+        ndim = 3 if taps == 27 else 2
+    npad = umma_npad(cout)
+    layout = _cabi.load().s3_umma_weight_layout(ndim, cout, 0)
+    wmax = float(w.abs().max()) if wmax is None else float(wmax)
+    scale = 2.0 ** math.floor(math.log2(16383.0 / wmax)) if wmax > 0 else 1.0
+    scale = min(max(scale, 2.0 ** -24), 2.0 ** 24)
+    hi = torch.empty((taps, npad, 64), device=w.device, dtype=torch.float16)
+    corr = torch.empty_like(hi)
+    _cabi.call("s3_pack_weights_umma_view", _p(w), taps, src_cin, src_cout, int(ci0), int(co0),
+               1 if adjoint else 0, int(cout), _p(hi), _p(corr), float(scale), layout, _s())
+    _count()
+    return hi, corr, 1.0 / scale
+
+
 def pack_act_pad16(x, split=False, fmt=0, halo=S3_PAD_REFLECT, halo_width=1):
     """fp32 channels-last -> 16-bit operand tensor(s) with the halo written.  ``halo_width`` 2
     (zero halo only): the tensor of the extent + 2 with a one-voxel halo, all zeros outside."""

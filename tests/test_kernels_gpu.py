@@ -623,6 +623,46 @@ def test_fp16c_pack_is_exact(cuda, halo):
         assert torch.equal(c2.view(torch.uint8), c1.view(torch.uint8))
 
 
+@pytest.mark.parametrize("nd,cin,cout", [(3, 6, 32), (3, 64, 64), (3, 128, 96), (2, 64, 200),
+                                         (3, 32, 6)])
+def test_weight_view_packing_equals_packing_of_copies(cuda, nd, cin, cout):
+    """s3_pack_weights_umma_view == s3_pack_weights_umma_c of the sliced / zero-padded (forward)
+    or flipped + transposed (input gradient) copies it replaces, bit for bit."""
+    from sup3r_b200 import ops
+    rng = np.random.default_rng(12)
+    w = dev(rng_arr(rng, (3,) * nd + (cin, cout), 0.3), cuda)
+    wmax = float(w.abs().max())
+    pad = torch.nn.functional.pad
+    # forward views: 64 input channels from ci0, up to 256 output channels from co0
+    for ci0 in range(0, cin, 64):
+        for co0 in range(0, cout, 256):
+            n_co = min(256, cout - co0)
+            ref = w[..., ci0:ci0 + 64, co0:co0 + n_co]
+            if ref.shape[-2] < 64:
+                ref = pad(ref, (0, 0, 0, 64 - ref.shape[-2]))
+            want = ops.pack_weights_umma(ref.contiguous(), ndim=nd, fmt=ops.S3_FMT_FP16C, wmax=wmax)
+            got = ops.pack_weights_umma_view(w, ci0, co0, n_co, ndim=nd, wmax=wmax)
+            assert torch.equal(got[0], want[0]) and got[2] == want[2]
+            assert torch.equal(got[1].view(torch.uint8), want[1].view(torch.uint8))
+    # adjoint views: rows = 64 output channels from 64 go, columns = input channels (padded to 16)
+    cin_p = (cin + 15) // 16 * 16
+    for go in range((cout + 63) // 64):
+        wt = w[..., 64 * go:64 * go + 64]
+        if wt.shape[-1] < 64:
+            wt = pad(wt, (0, 64 - wt.shape[-1]))
+        wt = wt.flip(dims=tuple(range(nd))).transpose(-1, -2)
+        if cin_p != cin:
+            wt = pad(wt, (0, cin_p - cin))
+        for c0 in range(0, cin_p, 256):
+            c1 = min(cin_p, c0 + 256)
+            want = ops.pack_weights_umma(wt[..., c0:c1].contiguous(), ndim=nd,
+                                         fmt=ops.S3_FMT_FP16C, wmax=wmax)
+            got = ops.pack_weights_umma_view(w, 64 * go, c0, c1 - c0, adjoint=True, ndim=nd,
+                                             wmax=wmax)
+            assert torch.equal(got[0], want[0]) and got[2] == want[2]
+            assert torch.equal(got[1].view(torch.uint8), want[1].view(torch.uint8))
+
+
 FP16C_CASES = [
     # n, (z, y, x), variant
     (1, (16, 16, 24), "pad16"),          # hot shape: straight-line two-pass MMA role, V4 epilogue
