@@ -126,13 +126,24 @@ def train_step_block(dev, peaks, steps=6):
                                train_gen=True, train_disc=False)
         m.run_gradient_descent(lr_t, hr_t, m.discriminator_weights, weight_gen_advers=1e-3,
                                train_gen=False, train_disc=True)
-    t_eager = []
-    for i in range(4):     # untimed: 2 eager steps, the CUDA-graph capture of both steps, 1 replay
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    # the same step issued launch by launch (graphs off): 3 warm-up steps, 3 timed
+    prev = os.environ.get("SUP3R_B200_TRAIN_GRAPH")
+    os.environ["SUP3R_B200_TRAIN_GRAPH"] = "0"
+    for _ in range(3):
         step()
-        torch.cuda.synchronize()
-        t_eager.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ms_eager = (time.perf_counter() - t0) * 1e3 / 3
+    if prev is None:
+        os.environ.pop("SUP3R_B200_TRAIN_GRAPH")
+    else:
+        os.environ["SUP3R_B200_TRAIN_GRAPH"] = prev
+    for _ in range(4):     # untimed: 2 eager steps, the CUDA-graph capture of both steps, 1 replay
+        step()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -148,7 +159,7 @@ def train_step_block(dev, peaks, steps=6):
     return {"workload": "Sup3rGan training step (generator step + discriminator step), batch 4, "
                         "LR 16x16x4x6 -> HR 32x32x48x6, gen_2x_12x-pattern generator, same-padded "
                         "ST discriminator (BASELINE configs[3] shapes)",
-            "ms_per_step": ms, "ms_per_step_eager_launches": t_eager[1],
+            "ms_per_step": ms, "ms_per_step_eager_launches": ms_eager,
             "cuda_graph": dict(m._graphed_steps.stats),
             "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
             "frac_of_bf16_peak": flops / (ms / 1e3) / 1e12 / peak,
@@ -160,7 +171,7 @@ def train_step_block(dev, peaks, steps=6):
                        "layers with extents < 2: fp32 CUDA-core kernels.  Each gradient step is "
                        "replayed as one CUDA graph (sup3r_b200/train_graph.py) + one fused "
                        "whole-network Adam launch; ms_per_step_eager_launches is the same step "
-                       "issued launch by launch (second step of the run)"}
+                       "issued launch by launch (graphs off, wall clock, after warm-up)"}
 
 
 class ClockSampler:
