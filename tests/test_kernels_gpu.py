@@ -242,6 +242,13 @@ def test_pad_fwd_bwd(cuda, mode):
     lhs = float((ref.astype(np.float64) * dy).sum())
     rhs = float((x.astype(np.float64) * dx).sum())
     assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), 1.0)
+    # 4 | channels takes the float4 kernel: same sums as the scalar kernel, channel by channel
+    dy8 = rng_arr(rng, ref.shape[:-1] + (8,))
+    got = ops.pad_bwd(dev(dy8, cuda), x.shape[:-1] + (8,), pads, code)
+    for ch in (0, 3, 7):        # (a 1-channel tensor goes through the scalar kernel)
+        one = ops.pad_bwd(dev(np.ascontiguousarray(dy8[..., ch:ch + 1]), cuda),
+                          x.shape[:-1] + (1,), pads, code)
+        assert torch.equal(got[..., ch:ch + 1], one)
 
 
 def test_crop_act_add_concat_affine(cuda):
