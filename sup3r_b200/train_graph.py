@@ -44,6 +44,14 @@ MAX_GRAPHS = 4            # live graphs per model (each owns a memory pool the s
 _STOCHASTIC = ("noise", "dropout", "random")
 
 
+def _shape(x):
+    s = getattr(x, "shape", None)
+    if s is None:
+        import numpy as np
+        s = np.shape(x)
+    return tuple(int(d) for d in s)
+
+
 class _Step:
     __slots__ = ("graph", "lr", "hr", "grads", "details", "scales", "arena", "replays")
 
@@ -160,8 +168,8 @@ class GraphedSteps:
         # (the storage of every weight of both networks is part of the key: a graph reads the
         #  tensors it was captured on, re-loaded weights live somewhere else)
         ptrs = tuple(var.value.data_ptr() for net in self._nets() for var in net.weights)
-        key = (tuple(id(w) for w in weights), tuple(low_res.shape), tuple(hi_res_true.shape),
-               tuple(sorted(kwargs.items())), bool(multi_gpu), id(optimizer), ptrs)
+        key = (tuple(id(w) for w in weights), _shape(low_res), _shape(hi_res_true),
+               tuple(sorted(kwargs.items())), bool(multi_gpu), id(optimizer), ptrs, m.precision)
         st = self._steps.get(key)
         if st is False:
             return None
