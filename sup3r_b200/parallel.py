@@ -107,6 +107,24 @@ class GradArena:
     the whole network's optimiser step in one launch."""
 
     world = 1
+    PIECE = 4096      # elements per table entry (one CTA each)
+
+    def segment_table(self, ptrs, weights):
+        """(n_pieces, 5) uint64 records {weight, m, v pointers of the piece, its offset in the
+        arena, its length}: every weight tensor cut into pieces of <= PIECE elements so that the
+        big dense / conv kernels spread over the whole GPU.  ``ptrs``: (weight, m, v) data
+        pointers per tensor."""
+        rows, off = [], 0
+        for (wp, mp, vp), g, var in zip(ptrs, self.in_views, weights):
+            if not var.value.is_contiguous() or var.value.dtype != torch.float32:
+                raise ValueError(f"fused Adam needs contiguous float32 weights ({var.name})")
+            if var.value.numel() != g.numel():
+                raise ValueError(f"gradient arena does not match weight {var.name}")
+            for s0 in range(0, g.numel(), self.PIECE):
+                rows.append((wp + 4 * s0, mp + 4 * s0, vp + 4 * s0, off + s0,
+                             min(self.PIECE, g.numel() - s0)))
+            off += g.numel()
+        return np.array(rows, dtype=np.uint64).reshape(-1, 5)
 
     def _layout(self, grads, arena):
         self.in_views, off = [], 0
@@ -131,19 +149,9 @@ class GradArena:
         key = tuple((var.value.data_ptr(), m.data_ptr(), v.data_ptr())
                     for var, (m, v) in zip(weights, slots))
         if getattr(self, "_seg_key", None) != key:
-            rows, off, piece = [], 0, 4096
-            for (wp, mp, vp), g, var in zip(key, self.in_views, weights):
-                if not var.value.is_contiguous() or var.value.dtype != torch.float32:
-                    raise ValueError(f"fused Adam needs contiguous float32 weights ({var.name})")
-                if var.value.numel() != g.numel():
-                    raise ValueError(f"gradient arena does not match weight {var.name}")
-                for s0 in range(0, g.numel(), piece):
-                    rows.append((wp + 4 * s0, mp + 4 * s0, vp + 4 * s0, off + s0,
-                                 min(piece, g.numel() - s0)))
-                off += g.numel()
-            rec = np.array(rows, dtype=np.uint64)
+            rec = self.segment_table(key, weights)
             self._segs = torch.from_numpy(rec.view(np.int64)).to(self.arena.device)
-            self._n_seg, self._max_n = len(rows), piece
+            self._n_seg, self._max_n = len(rec), self.PIECE
             self._seg_key = key
         if grads is not None:
             self.stage(grads)
