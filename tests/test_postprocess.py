@@ -208,3 +208,35 @@ def test_forward_pass_bias_correction_hook(cuda, tmp_path):
     assert sorted(got) == sorted(want) == [0, 1, 2, 3]
     for k in got:
         assert np.array_equal(got[k], want[k])
+
+
+def test_bias_hook_derives_months_from_a_datetime_time_index(tmp_path):
+    """bias/utilities.py:263-265: the hook passes the chunk's time index to the transform
+    (``date_range_kwargs`` in the reference); here a datetime index supplies the calendar month
+    of every step to ``monthly_local_linear_bc`` unless the kwargs already name it."""
+    import pandas as pd
+    from sup3r_b200 import bias
+    rng = np.random.default_rng(0)
+    scalar = rng.uniform(0.5, 1.5, (4, 3, 12)).astype(np.float32)
+    adder = rng.uniform(-1, 1, (4, 3, 12)).astype(np.float32)
+    fp = str(tmp_path / "bc.npz")
+    np.savez(fp, u_scalar=scalar, u_adder=adder)
+    data = rng.standard_normal((4, 3, 6, 2)).astype(np.float32)
+    ti = pd.date_range("2020-11-15", periods=6, freq="20D")
+    months = np.asarray(ti.month)
+    assert len(set(months)) > 2
+    kw = {"u": {"bias_fp": fp, "temporal_avg": False}}
+    out = bias.bias_correct_features(data.copy(), ["u", "v"], None, "monthly_local_linear_bc", kw,
+                                     time_index=ti.values)
+    want = bias.monthly_local_linear_bc(data[..., 0], None, "u", fp, months=months,
+                                        temporal_avg=False)
+    assert np.array_equal(out[..., 0], want) and np.array_equal(out[..., 1], data[..., 1])
+    assert np.allclose(want, data[..., 0] * scalar[..., months - 1] + adder[..., months - 1])
+    # explicit months win over the time index; an integer time index supplies nothing
+    kw2 = {"u": {"bias_fp": fp, "temporal_avg": False, "months": [1] * 6}}
+    out2 = bias.bias_correct_features(data.copy(), ["u", "v"], None, "monthly_local_linear_bc",
+                                      kw2, time_index=ti.values)
+    assert np.allclose(out2[..., 0], data[..., 0] * scalar[..., :1] + adder[..., :1])
+    with pytest.raises(RuntimeError):
+        bias.bias_correct_features(data.copy(), ["u", "v"], None, "monthly_local_linear_bc", kw,
+                                   time_index=np.arange(6))
