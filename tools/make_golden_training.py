@@ -1,0 +1,172 @@
+"""Golden records of the GAN training schedule and history bookkeeping (SURVEY 8(a) rows a13,
+a14) from the REAL reference methods: the source text of ``update_loss_details``, ``early_stop``
+(sup3r/models/abstract.py), ``get_weight_update_fraction``, ``update_adversarial_weights``,
+``_train_batch``, ``_post_batch`` and ``_train_epoch`` (sup3r/models/base.py) is exec'd from
+/root/reference and bound to a stand-in object whose ``run_gradient_descent`` returns scripted
+loss values (the modules themselves import tensorflow / phygnn, which are not installed).
+
+    python tools/make_golden_training.py   ->  tests/golden/training_schedule.json
+"""
+import json
+import os
+import textwrap
+import time
+from unittest.mock import MagicMock
+
+import numpy as np
+import pandas as pd
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden", "training_schedule.json")
+
+
+def grab_method(src, name, ns):
+    """exec one method of a class body (found by its 4-space indentation)."""
+    a = src.index(f"    def {name}(")
+    deco = src.rfind("\n", 0, a - 1)
+    if src[deco:a].strip() == "@staticmethod":
+        pass
+    b = a
+    while True:
+        b = src.find("\n    ", b + 1)
+        nxt = src[b + 5:b + 9]
+        if b < 0 or (src[b + 5] != " " and src[b + 5] != "\n" and src[b + 5] != ")"):
+            break
+    body = textwrap.dedent(src[a:b if b > 0 else len(src)])
+    exec(compile(body, name, "exec"), ns)
+    return ns[name]
+
+
+# the scripted losses: what run_gradient_descent reports for call number n
+def scripted_losses(n, train_gen, train_disc, compute_disc):
+    out = {}
+    if train_gen:
+        out["loss_gen"] = 1.0 / (1 + 0.1 * n)
+        out["loss_gen_content"] = 0.9 / (1 + 0.1 * n)
+        out["loss_gen_advers"] = 0.7 + 0.01 * n
+    if train_disc or compute_disc:
+        out["loss_disc"] = 0.72 - 0.045 * (n % 11) + 0.02 * (n // 11)
+    return out
+
+
+SCENARIOS = [
+    # (train_gen, train_disc, disc_loss_bounds, n_batches) per epoch
+    [(True, True, (0.45, 0.6), 6), (True, True, (0.45, 0.6), 6), (True, True, (0.3, 0.5), 5)],
+    [(True, False, (0.45, 0.6), 4), (False, True, (0.45, 0.6), 4), (True, True, (0.6, 0.7), 7)],
+]
+
+
+class Batch:
+    def __init__(self, i):
+        self.low_res, self.high_res = ("lr", i), ("hr", i)
+
+
+class Handler:
+    shapes = ((2, 4, 4, 4, 2), (2, 8, 8, 8, 2))
+    lr_shape, hr_shape = (4, 4, 4, 2), (8, 8, 8, 2)
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter([Batch(i) for i in range(self.n)])
+
+
+def run_scenario(obj, scenario):
+    """Drive ``obj._train_epoch`` through the scenario; returns the golden record."""
+    rec = {"calls": [], "epochs": []}
+    counter = [0]
+
+    def run_gradient_descent(low_res, hi_res, weights, weight_gen_advers=None, optimizer=None,
+                             train_gen=True, train_disc=False, compute_disc=False,
+                             multi_gpu=False):
+        counter[0] += 1
+        rec["calls"].append([weights, optimizer, bool(train_gen), bool(train_disc),
+                             bool(compute_disc), low_res[1]])
+        return scripted_losses(counter[0], train_gen, train_disc, compute_disc)
+    obj.run_gradient_descent = run_gradient_descent
+    for train_gen, train_disc, bounds, n in scenario:
+        details = obj._train_epoch(Handler(n), 1e-3, train_gen, train_disc, bounds)
+        rec["epochs"].append({k: float(v) for k, v in details.items()})
+    tr = obj._train_record
+    rec["record_columns"] = list(tr.columns)
+    rec["record_index"] = [int(i) for i in tr.index]
+    rec["record"] = [[None if pd.isna(v) else float(v) for v in row] for row in tr.values]
+    return rec
+
+
+def make_reference_object():
+    asrc = open(os.path.join(REF, "sup3r/models/abstract.py")).read()
+    bsrc = open(os.path.join(REF, "sup3r/models/base.py")).read()
+    ns = {"np": np, "pd": pd, "time": time, "logger": MagicMock(), "warn": lambda *a, **k: None,
+          "tf": MagicMock(), "numpy_if_tensor": lambda v: v}
+
+    class Ref:
+        pass
+    for name in ("update_loss_details", "early_stop"):
+        setattr(Ref, name, staticmethod(grab_method(asrc, name, ns)))
+    setattr(Ref, "get_weight_update_fraction",
+            staticmethod(grab_method(bsrc, "get_weight_update_fraction", ns)))
+    for name in ("update_adversarial_weights", "_train_batch", "_post_batch", "_train_epoch"):
+        setattr(Ref, name, grab_method(bsrc, name, ns))
+    return Ref
+
+
+def prime(obj):
+    obj._train_record = pd.DataFrame()
+    obj._tb_writer = None
+    obj._write_tb_profile = False
+    obj.total_batches = 0
+    obj.generator_weights, obj.discriminator_weights = "gen_weights", "disc_weights"
+    obj.timer = lambda f, log=False, **k: f
+    obj.init_weights = lambda *a, **k: None
+    obj.profile_to_tensorboard = lambda *a, **k: None
+    return obj
+
+
+def main():
+    Ref = make_reference_object()
+    out = {"scenarios": []}
+    for sc in SCENARIOS:
+        obj = prime(Ref())
+        obj.optimizer, obj.optimizer_disc = "opt_gen", "opt_disc"
+        out["scenarios"].append(run_scenario(obj, sc))
+    # history bookkeeping
+    rec = pd.DataFrame()
+    rows = []
+    for i in range(7):
+        new = {"loss_gen": 1.0 - 0.1 * i, "disc_train_frac": float(i % 2),
+               "train_extra": 3.0 * i}
+        if i % 3 == 0:
+            new["loss_disc"] = 0.5 + 0.01 * i
+        rec = Ref.update_loss_details(rec, new, 4, prefix="train_")
+        rows.append({"columns": list(rec.columns), "index": [int(j) for j in rec.index],
+                     "values": [[None if pd.isna(v) else float(v) for v in r]
+                                for r in rec.values]})
+    out["update_loss_details"] = rows
+    hist = pd.DataFrame({"val_loss_gen": [1.0, 0.8, 0.7, 0.699, 0.6985, 0.6981, 0.698, 0.6979,
+                                          0.6979]})
+    out["early_stop"] = [[n, thr, m, bool(Ref.early_stop(hist.iloc[:n], "val_loss_gen", thr, m))]
+                         for n in (3, 6, 7, 8, 9) for thr in (0.005, 0.0005) for m in (3, 5)]
+    out["early_stop_none"] = bool(Ref.early_stop(None, "val_loss_gen"))
+    out["weight_update_fraction"] = [
+        [v, b, f, float(Ref.get_weight_update_fraction({"disc_train_frac": v}, "disc_train_frac",
+                                                       update_bounds=b, update_frac=f))]
+        for v in (0.2, 0.5, 0.93, 0.97, [0.1, 0.99], (0.99, 0.2))
+        for b in ((0.5, 0.95), (0.9, 0.99)) for f in (0.0, 0.05)]
+    obj = prime(Ref())
+    out["adversarial_weights"] = [
+        [frac, td, v, float(obj.update_adversarial_weights({"disc_train_frac": v}, frac,
+                                                           (0.9, 0.99), 1e-3, td))]
+        for frac in (0.0, 0.1) for td in (True, False) for v in (0.5, 0.95, 1.0)]
+    with open(OUT, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()
