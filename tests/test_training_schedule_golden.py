@@ -88,3 +88,23 @@ def test_golden_file_is_reproducible_from_the_reference_when_present():
     obj = T.prime(Ref())
     obj.optimizer, obj.optimizer_disc = "opt_gen", "opt_disc"
     assert T.run_scenario(obj, T.SCENARIOS[0]) == G["scenarios"][0]
+
+
+def test_normalisation_matches_reference(monkeypatch):
+    """a15: ``set_norm_stats / norm_input / un_norm_output`` (abstract.py:133-275) on float32
+    host arrays -- stored statistics (float32, replaced by new ones, ignored when None), the
+    zero-stdev warning, KeyError on a missing feature and the arrays themselves, bit for bit."""
+    from sup3r_b200.models import Sup3rGan, abstract
+    log = []
+    monkeypatch.setattr(abstract, "warn", lambda m, *a, **k: log.append(str(m)))
+
+    class Scripted(Sup3rGan):
+        def __init__(self):
+            self._means = self._stdevs = None
+            self._meta = dict(T.NORM_META)
+    rec, arrs = T.norm_scenario(Scripted(), log)
+    want = G["norm"]
+    assert json.loads(json.dumps(rec)) == want
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "norm.npz"))
+    for k, a in arrs.items():
+        assert a.dtype == gold[k].dtype and np.array_equal(a, gold[k]), k

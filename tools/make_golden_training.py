@@ -128,6 +128,61 @@ def prime(obj):
     return obj
 
 
+# ---------------------------------------------------------------- normalisation (row a15)
+NORM_META = {"lr_features": ["u_10m", "v_10m", "topography"],
+             "hr_out_features": ["v_10m", "u_10m"], "hr_exo_features": []}
+NORM_STATS = ({"u_10m": 1.5, "v_10m": -0.25, "topography": 812.0, "unused": 3.0},
+              {"u_10m": 4.0, "v_10m": 0.0, "topography": 330.5, "unused": 1.0})
+
+
+def norm_scenario(obj, warn_log):
+    """set_norm_stats / norm_input / un_norm_output on float32 arrays; -> (record, arrays)."""
+    rng = np.random.default_rng(8)
+    low = rng.standard_normal((2, 3, 4, 5, 3)).astype(np.float32) * 7
+    out = rng.standard_normal((2, 6, 8, 5, 2)).astype(np.float32)
+    rec, arrs = {}, {}
+    arrs["norm_none"] = np.asarray(obj.norm_input(low))          # no stats yet: unchanged
+    obj.set_norm_stats({"u_10m": 9.0, "v_10m": 9.0, "topography": 9.0},
+                       {"u_10m": 9.0, "v_10m": 9.0, "topography": 9.0})
+    obj.set_norm_stats(*NORM_STATS)                               # new stats REPLACE the old ones
+    rec["means"] = {k: [float(v), type(v).__name__] for k, v in obj._means.items()}
+    rec["stdevs"] = {k: [float(v), type(v).__name__] for k, v in obj._stdevs.items()}
+    n0 = len(warn_log)
+    arrs["norm"] = np.asarray(obj.norm_input(low))
+    rec["zero_std_warnings"] = len(warn_log) - n0
+    arrs["unnorm"] = np.asarray(obj.un_norm_output(out))
+    rec["dtypes"] = [str(arrs["norm"].dtype), str(arrs["unnorm"].dtype)]
+    obj.set_norm_stats(None, NORM_STATS[1])                       # ignored
+    rec["means_after_none"] = {k: float(v) for k, v in obj._means.items()}
+    obj._means = {"u_10m": np.float32(1)}
+    for name, fn in (("norm_missing", lambda: obj.norm_input(low)),
+                     ("unnorm_missing", lambda: obj.un_norm_output(out))):
+        try:
+            fn()
+            rec[name] = "ok"
+        except Exception as e:      # noqa: BLE001
+            rec[name] = type(e).__name__
+    return rec, arrs
+
+
+def make_reference_norm_object(warn_log):
+    import pprint
+    from types import SimpleNamespace
+    asrc = open(os.path.join(REF, "sup3r/models/abstract.py")).read()
+    ns = {"np": np, "logger": MagicMock(), "pprint": pprint,
+          "warn": lambda m, *a, **k: warn_log.append(str(m)),
+          "tf": SimpleNamespace(Tensor=type("Tensor", (), {}))}
+
+    class RefNorm:
+        _means = _stdevs = None
+        lr_features = NORM_META["lr_features"]
+        hr_out_features = NORM_META["hr_out_features"]
+        hr_exo_features = NORM_META["hr_exo_features"]
+    for name in ("set_norm_stats", "norm_input", "un_norm_output"):
+        setattr(RefNorm, name, grab_method(asrc, name, ns))
+    return RefNorm()
+
+
 def main():
     Ref = make_reference_object()
     out = {"scenarios": []}
@@ -163,6 +218,10 @@ def main():
         [frac, td, v, float(obj.update_adversarial_weights({"disc_train_frac": v}, frac,
                                                            (0.9, 0.99), 1e-3, td))]
         for frac in (0.0, 0.1) for td in (True, False) for v in (0.5, 0.95, 1.0)]
+    warn_log = []
+    rec, arrs = norm_scenario(make_reference_norm_object(warn_log), warn_log)
+    out["norm"] = rec
+    np.savez_compressed(OUT.replace("training_schedule.json", "norm.npz"), **arrs)
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
