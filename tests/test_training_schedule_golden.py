@@ -108,3 +108,16 @@ def test_normalisation_matches_reference(monkeypatch):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "norm.npz"))
     for k, a in arrs.items():
         assert a.dtype == gold[k].dtype and np.array_equal(a, gold[k]), k
+
+
+def test_finish_epoch_matches_reference():
+    """a14: ``finish_epoch`` (abstract.py:698-783) -- history rows incl. the ``extras`` columns,
+    checkpoint triggers (every ``checkpoint_int`` epochs and the last epoch, ``{epoch}`` in the
+    directory name), early stop and its extra checkpoint."""
+    got = T.finish_epoch_scenario(make_model())
+    want = G["finish_epoch"]
+    assert got.keys() == want.keys()
+    for k in want:
+        if k != "values":
+            assert got[k] == want[k], k
+    _same_table(got["values"], want["values"])

@@ -128,6 +128,54 @@ def prime(obj):
     return obj
 
 
+# ---------------------------------------------------------------- finish_epoch (row a14)
+def finish_epoch_scenario(obj):
+    """History rows, checkpoint triggers and early stop over 9 epochs; -> record."""
+    saves = []
+    obj.save = lambda out_dir: saves.append(out_dir)
+    obj._history = pd.DataFrame(columns=["elapsed_time"])
+    obj._history.index.name = "epoch"
+    epochs = list(range(3, 12))
+    vals = [1.0, 0.8, 0.7, 0.699, 0.6985, 0.6981, 0.698, 0.6979, 0.6979]
+    stops = []
+    for e, v in zip(epochs, vals):
+        details = {"train_loss_gen": v * 1.1, "val_loss_gen": v, "train_loss_disc": 0.5 + 0.01 * e}
+        extras = {"weight_gen_advers": 1e-3 * e, "OptmGen/learning_rate": np.float32(1e-4),
+                  "flag": True} if e % 2 else None
+        stops.append(bool(obj.finish_epoch(e, epochs, time.time(), details, 4, "ckpt_{epoch}",
+                                           "val_loss_gen", 0.002, 3, extras=extras)))
+    h = obj._history
+    rec = {"saves": saves, "stops": stops, "columns": list(h.columns),
+           "index": [int(i) for i in h.index], "index_name": h.index.name,
+           "elapsed_positive": bool((h["elapsed_time"] >= 0).all()),
+           "values": [[None if pd.isna(v) else float(v) for v in row]
+                      for row in h.drop(columns=["elapsed_time"]).values]}
+    try:
+        obj.finish_epoch(12, [12], time.time(), {"val_loss_gen": 0.5}, None, "no_key", None,
+                         0.002, 3)
+        rec["bad_out_dir"] = "ok"
+    except Exception as e:      # noqa: BLE001
+        rec["bad_out_dir"] = type(e).__name__
+    return rec
+
+
+def make_reference_finish_object():
+    asrc = open(os.path.join(REF, "sup3r/models/abstract.py")).read()
+    from types import SimpleNamespace
+    ns = {"np": np, "pd": pd, "time": time, "logger": MagicMock(),
+          "tf": SimpleNamespace(Tensor=type("Tensor", (), {}))}
+    usrc = open(os.path.join(REF, "sup3r/utilities/utilities.py")).read()
+    a = usrc.index("def safe_cast(")
+    exec(compile(usrc[a:usrc.index("\ndef ", a + 5)], "safe_cast", "exec"), ns)
+
+    class RefFinish:
+        pass
+    for name in ("early_stop", "log_loss_details"):
+        setattr(RefFinish, name, staticmethod(grab_method(asrc, name, ns)))
+    RefFinish.finish_epoch = grab_method(asrc, "finish_epoch", ns)
+    return RefFinish()
+
+
 # ---------------------------------------------------------------- normalisation (row a15)
 NORM_META = {"lr_features": ["u_10m", "v_10m", "topography"],
              "hr_out_features": ["v_10m", "u_10m"], "hr_exo_features": []}
@@ -218,6 +266,7 @@ def main():
         [frac, td, v, float(obj.update_adversarial_weights({"disc_train_frac": v}, frac,
                                                            (0.9, 0.99), 1e-3, td))]
         for frac in (0.0, 0.1) for td in (True, False) for v in (0.5, 0.95, 1.0)]
+    out["finish_epoch"] = finish_epoch_scenario(make_reference_finish_object())
     warn_log = []
     rec, arrs = norm_scenario(make_reference_norm_object(warn_log), warn_log)
     out["norm"] = rec
