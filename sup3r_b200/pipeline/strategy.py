@@ -100,25 +100,84 @@ class ForwardPassChunk:
         self.shape = self.input_data.shape
 
 
-def _hr_lat_lon(lr_lat_lon, s_enhance):
-    """Bilinear refinement of the low-res lat / lon grid to the high-res grid."""
-    if s_enhance == 1:
-        return lr_lat_lon
-    n1, n2 = lr_lat_lon.shape[:2]
-    y = (np.arange(n1 * s_enhance) + 0.5) / s_enhance - 0.5
-    x = (np.arange(n2 * s_enhance) + 0.5) / s_enhance - 0.5
-    out = np.empty((n1 * s_enhance, n2 * s_enhance, 2), dtype=np.float32)
-    for k in range(2):
-        rows = np.stack([np.interp(x, np.arange(n2), lr_lat_lon[i, :, k]) if n2 > 1
-                         else np.full(len(x), lr_lat_lon[i, 0, k]) for i in range(n1)])
-        if n1 > 1:
-            # linear extrapolation at the borders, interpolation inside
-            yi = np.clip(np.floor(y).astype(int), 0, n1 - 2)
-            w = (y - yi)[:, None]
-            out[..., k] = rows[yi] * (1 - w) + rows[yi + 1] * w
-        else:
-            out[..., k] = rows[0][None]
-    return out
+def _extend_grid(lat_lon):
+    """The low-res grid with one extra row / column on every side, continued with the spacing of
+    the outermost cells (writers/base.py:347-421): new columns keep their row's latitude and
+    step the longitude, new rows keep their column's longitude and step the latitude, corners
+    take the latitude of their row neighbour and the longitude of their column neighbour."""
+    n1, n2 = lat_lon.shape[:2]
+    g = np.zeros((n1 + 2, n2 + 2, 2))
+    g[1:-1, 1:-1] = lat_lon
+    lat, lon = g[..., 0], g[..., 1]
+    d_left, d_right = lon[:, 2] - lon[:, 1], lon[:, -2] - lon[:, -3]
+    d_top, d_bottom = lat[1, :] - lat[2, :], lat[-3, :] - lat[-2, :]
+    lon[:, 0], lat[:, 0] = lon[:, 1] - d_left, lat[:, 1]
+    lon[:, -1], lat[:, -1] = lon[:, -2] + d_right, lat[:, -2]
+    lat[0, :], lon[0, :] = lat[1, :] + d_top, lon[1, :]
+    lat[-1, :], lon[-1, :] = lat[-2, :] - d_bottom, lon[-2, :]
+    for r, rn in ((0, 1), (-1, -2)):
+        for c, cn in ((0, 1), (-1, -2)):
+            lat[r, c], lon[r, c] = lat[r, cn], lon[rn, c]
+    return g
+
+
+def _hr_lat_lon(lr_lat_lon, s_enhance=None, shape=None):
+    """High-res (lat, lon) grid of the full output domain, the reference's
+    ``OutputHandler.get_lat_lon`` (writers/base.py:434-508): longitudes wrapped to [-180, 180)
+    (shifted to [0, 360) when a row crosses the date line), the grid extended by one cell
+    (``_extend_grid``), both grids laid on cell centres of the same (0, 10) square and the
+    coordinates interpolated linearly over its triangulation (``scipy.interpolate.griddata``, as
+    the reference does -- host-side metadata, not a kernel), longitudes wrapped back.  float64
+    (S1, S2, 2)."""
+    from scipy.interpolate import griddata
+    ll = np.array(lr_lat_lon, dtype=np.asarray(lr_lat_lon).dtype, copy=True)
+    n1, n2 = ll.shape[:2]
+    if shape is None:
+        shape = (n1 * s_enhance, n2 * s_enhance)
+    assert n1 > 1 and n2 > 1, "low res lat/lon must have at least 2 rows and 2 columns"
+    ll[..., 1] = (ll[..., 1] + 180) % 360 - 180
+    if any(ll[i, -1, 1] < ll[i, 0, 1] for i in range(n1)):
+        ll[..., 1] = (ll[..., 1] + 360) % 360
+    g = _extend_grid(ll)
+
+    def centres(n):
+        return np.arange(0, 10, 10 / n) + 5 / n
+    y, x = centres(n1), centres(n2)
+    y = np.concatenate([[y[0] - 10 / n1], y, [y[-1] + 10 / n1]])
+    x = np.concatenate([[x[0] - 10 / n2], x, [x[-1] + 10 / n2]])
+    xx, yy = np.meshgrid(x, y, copy=False)
+    old = np.array([yy.flatten(), xx.flatten()], dtype=np.float32).T
+    xx, yy = np.meshgrid(centres(shape[1]), centres(shape[0]), copy=False)
+    new = np.array([yy.flatten(), xx.flatten()], dtype=np.float32).T
+    lons = griddata(old, g[..., 1].flatten(), new)
+    lats = griddata(old, g[..., 0].flatten(), new)
+    lons = (lons + 180) % 360 - 180
+    return np.dstack((lats.reshape(shape), lons.reshape(shape)))
+
+
+def _hr_times(lr_times, n_hr):
+    """High-res time axis of a chunk, the reference's ``OutputHandler.get_times``
+    (writers/base.py:510-549): the smallest low-res step divided by the enhancement, continued
+    one low-res step past the last time; 29 February dropped when the low-res index has none.
+    Datetime input -> ``pd.DatetimeIndex``; a plain numeric index (the in-memory handler's
+    default) -> evenly spaced floats."""
+    lr = np.asarray(lr_times)
+    t_enhance = int(n_hr / len(lr))
+    if not np.issubdtype(lr.dtype, np.datetime64):
+        step = float(np.min(np.diff(lr))) if len(lr) > 1 else 1.0
+        return float(lr[0]) + np.arange(n_hr) * (step / t_enhance)
+    import pandas as pd
+    ti = pd.DatetimeIndex(lr)
+    secs = min(set(np.diff(ti)) if len(ti) > 1 else [np.timedelta64(1, "D")]) \
+        / np.timedelta64(1, "s")
+    offset = pd.tseries.offsets.DateOffset(seconds=secs)
+    freq = pd.tseries.offsets.DateOffset(seconds=int(offset.seconds / t_enhance))
+    times = pd.date_range(ti[0], ti[-1] + offset, freq=freq)[:-1]
+    if not any((ti.month == 2) & (ti.day == 29)):
+        times = times[~((times.month == 2) & (times.day == 29))]
+    assert len(times) == n_hr, (
+        f"High res times length {len(times)} does not match expected shape {n_hr}")
+    return times
 
 
 @dataclass
@@ -348,12 +407,7 @@ class ForwardPassStrategy:
         lr_times = self.input_handler.time_index[ti_slice]
         data, exo = self.timer(self.prep_chunk_data, log=True, call_id=chunk_index)(
             chunk_index=chunk_index)
-        n_hr_t = self.t_enhance * len(lr_times)
-        if len(lr_times) > 1:
-            hr_times = np.interp(np.arange(n_hr_t) / self.t_enhance, np.arange(len(lr_times)),
-                                 np.asarray(lr_times, dtype=np.float64))
-        else:
-            hr_times = np.repeat(np.asarray(lr_times, dtype=np.float64), n_hr_t)
+        hr_times = _hr_times(lr_times, self.t_enhance * len(lr_times))
         return ForwardPassChunk(
             input_data=data, exo_data=exo, lr_pad_slice=self.lr_pad_slices[s_idx],
             hr_crop_slice=self.fwp_slicer.hr_crop_slices[t_idx][s_idx],
