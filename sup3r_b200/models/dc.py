@@ -18,40 +18,36 @@ class Sup3rGanDC(Sup3rGan):
     _graph_safe = True    # gradient step may be captured as a CUDA graph (train_graph.py)
 
     def calc_val_loss_gen(self, batch_handler, weight_gen_advers):
-        """Total and content loss of every validation bin, shape (n_space_bins, n_time_bins)
-        (dc.py:18-62)."""
-        shape = (batch_handler.n_space_bins, batch_handler.n_time_bins)
-        total_losses = np.zeros(shape, dtype=np.float32)
-        content_losses = np.zeros(shape, dtype=np.float32)
+        """Total and content loss of every validation bin, two ``(n_space_bins, n_time_bins)``
+        float32 arrays; validation batch ``i`` belongs to bin ``divmod(i, n_time_bins)``
+        (dc.py:18-62).  Forward only: nothing is taped."""
+        n_t = batch_handler.n_time_bins
+        per_bin = np.zeros((2, batch_handler.n_space_bins, n_t), dtype=np.float32)
+        n_val = len(batch_handler.val_data)
         for i, batch in enumerate(batch_handler.val_data):
-            logger.info("Calculating validation loss for batch %d / %d...", i,
-                        len(batch_handler.val_data))
+            logger.info("Calculating validation loss for batch %d / %d...", i, n_val)
             with torch.no_grad():
-                loss, loss_details, _, _ = self._get_hr_exo_and_loss(
+                loss, details, _, _ = self._get_hr_exo_and_loss(
                     low_res=batch.low_res, hi_res_true=batch.high_res,
                     weight_gen_advers=weight_gen_advers)
-            row, col = i // batch_handler.n_time_bins, i % batch_handler.n_time_bins
-            total_losses[row, col] = float(loss)
-            content_losses[row, col] = float(loss_details["loss_gen_content"])
-        return total_losses, content_losses
+            per_bin[(slice(None), *divmod(i, n_t))] = (float(loss),
+                                                       float(details["loss_gen_content"]))
+        return per_bin[0], per_bin[1]
 
     def calc_val_loss(self, batch_handler, weight_gen_advers):
-        """Update the batch handler's spatial / temporal sampling weights from the per-bin
-        validation losses (dc.py:64-116)."""
+        """End-of-epoch validation for the data-centric sampler (dc.py:64-116): the mean loss of
+        every time bin / space bin, normalised to sum 1, becomes the sampler's new temporal /
+        spatial weight (bins the generator does badly on are drawn more often)."""
         logger.debug("Starting end-of-epoch validation loss calculation...")
-        loss_details = {}
-        total_losses, content_losses = self.calc_val_loss_gen(batch_handler, weight_gen_advers)
-        t_weights = total_losses.mean(axis=0)
-        t_weights /= t_weights.sum()
-        s_weights = total_losses.mean(axis=1)
-        s_weights /= s_weights.sum()
-        logger.debug("Previous spatial weights: %s", batch_handler.spatial_weights)
-        logger.debug("Previous temporal weights: %s", batch_handler.temporal_weights)
-        batch_handler.update_weights(spatial_weights=s_weights, temporal_weights=t_weights)
-        logger.debug("New spatiotemporal weights (space, time):\n%s",
-                     total_losses / total_losses.sum())
-        logger.debug("New spatial weights: %s", s_weights)
-        logger.debug("New temporal weights: %s", t_weights)
-        loss_details["mean_val_loss_gen"] = round(float(np.mean(total_losses)), 3)
-        loss_details["mean_val_loss_gen_content"] = round(float(np.mean(content_losses)), 3)
-        return loss_details
+        total, content = self.calc_val_loss_gen(batch_handler, weight_gen_advers)
+
+        def share(v):
+            return v / v.sum()
+        new = {"spatial_weights": share(total.mean(axis=1)),
+               "temporal_weights": share(total.mean(axis=0))}
+        logger.debug("Sampler weights (space, time) before: %s, %s; after: %s, %s; per bin:\n%s",
+                     batch_handler.spatial_weights, batch_handler.temporal_weights,
+                     new["spatial_weights"], new["temporal_weights"], share(total))
+        batch_handler.update_weights(**new)
+        return {"mean_val_loss_gen": round(np.mean(total), 3),
+                "mean_val_loss_gen_content": round(np.mean(content), 3)}

@@ -121,3 +121,18 @@ def test_finish_epoch_matches_reference():
         if k != "values":
             assert got[k] == want[k], k
     _same_table(got["values"], want["values"])
+
+
+def test_data_centric_validation_matches_reference():
+    """8(f)1 ``Sup3rGanDC`` (dc.py:18-116): per-bin validation losses, the sampler weights handed
+    to ``batch_handler.update_weights`` and the reported means (value AND type), bit for bit."""
+    from sup3r_b200.models import Sup3rGanDC
+
+    class Scripted(Sup3rGanDC):
+        def __init__(self):
+            pass
+    rec, arrs = T.dc_scenario(Scripted())
+    assert json.loads(json.dumps(rec)) == G["dc"]
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "norm.npz"))
+    for k, a in arrs.items():
+        assert a.dtype == gold[k].dtype and np.array_equal(a, gold[k]), k

@@ -176,6 +176,44 @@ def make_reference_finish_object():
     return RefFinish()
 
 
+# ---------------------------------------------------------------- Sup3rGanDC (8(f)1)
+class DCHandler:
+    n_space_bins, n_time_bins = 3, 4
+    spatial_weights, temporal_weights = [1 / 3] * 3, [0.25] * 4
+
+    def __init__(self):
+        self.val_data = [Batch(i) for i in range(12)]
+        self.updates = []
+
+    def update_weights(self, spatial_weights, temporal_weights):
+        self.updates.append([np.asarray(spatial_weights), np.asarray(temporal_weights)])
+
+
+def dc_scenario(obj):
+    """Per-bin validation losses -> sampler weights (sup3r/models/dc.py:18-116)."""
+    def scripted(low_res, hi_res_true, weight_gen_advers):
+        i = low_res[1]
+        loss = 0.3 + 0.07 * ((i * 5) % 12) + 1e-3 * weight_gen_advers
+        return loss, {"loss_gen_content": 0.9 * loss, "loss_gen": loss}, None, None
+    obj._get_hr_exo_and_loss = scripted
+    bh = DCHandler()
+    total, content = obj.calc_val_loss_gen(bh, 0.5)
+    details = obj.calc_val_loss(bh, 0.5)
+    rec = {"details": {k: [float(v), type(v).__name__] for k, v in details.items()},
+           "n_updates": len(bh.updates),
+           "weight_dtypes": [str(a.dtype) for a in bh.updates[0]]}
+    arrs = {"dc_total": np.asarray(total), "dc_content": np.asarray(content),
+            "dc_spatial_weights": bh.updates[0][0], "dc_temporal_weights": bh.updates[0][1]}
+    return rec, arrs
+
+
+def make_reference_dc_object():
+    src = open(os.path.join(REF, "sup3r/models/dc.py")).read()
+    ns = {"np": np, "logger": MagicMock(), "Sup3rGan": object}
+    exec(compile(src[src.index("class Sup3rGanDC"):], "dc.py", "exec"), ns)
+    return ns["Sup3rGanDC"]()
+
+
 # ---------------------------------------------------------------- normalisation (row a15)
 NORM_META = {"lr_features": ["u_10m", "v_10m", "topography"],
              "hr_out_features": ["v_10m", "u_10m"], "hr_exo_features": []}
@@ -270,6 +308,8 @@ def main():
     warn_log = []
     rec, arrs = norm_scenario(make_reference_norm_object(warn_log), warn_log)
     out["norm"] = rec
+    out["dc"], dc_arrs = dc_scenario(make_reference_dc_object())
+    arrs.update(dc_arrs)
     np.savez_compressed(OUT.replace("training_schedule.json", "norm.npz"), **arrs)
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
