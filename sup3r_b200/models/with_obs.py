@@ -132,7 +132,8 @@ class Sup3rGanWithObs(Sup3rGan):
                 torch.as_tensor(np.asarray(hi_res_true, np.float32), device=hi_res_gen.device)
             mask = hi_res_exo["mask"]
             loss_obs, loss_non_obs = self._get_loss_obs_comparison(hi_true, hi_res_gen, mask)
-            obs_frac = float((~mask).sum()) / float(mask.numel())
+            # (float32 division, like the reference's tf.cast(..., tf.float32) operands)
+            obs_frac = float(np.float32(int((~mask).sum())) / np.float32(mask.numel()))
             loss_update = {"loss_obs": loss_obs, "loss_non_obs": loss_non_obs,
                            "obs_frac": obs_frac}
             if self.loss_obs_weight and obs_frac > 0:
