@@ -136,3 +136,17 @@ def test_data_centric_validation_matches_reference():
     gold = np.load(os.path.join(ROOT, "tests", "golden", "norm.npz"))
     for k, a in arrs.items():
         assert a.dtype == gold[k].dtype and np.array_equal(a, gold[k]), k
+
+
+def test_persistence_helpers_match_reference(tmp_path):
+    """a12 / a16: ``save_params`` (the bytes of model_params.json: key order, indent, casting of
+    numpy / tuple / arbitrary values), ``load_saved_params`` (history path, version record
+    dropped, float32 statistics), ``get_optimizer_config`` / ``get_optimizer_state``,
+    ``check_batch_handler_attrs``."""
+    from sup3r_b200.models import Sup3rGan
+    got = T.persistence_scenario(type("Scripted", (Sup3rGan,), {}), str(tmp_path))
+    want = G["persistence"]
+    assert got.keys() == want.keys()
+    assert got["params_json"] == want["params_json"]
+    for k in want:
+        assert json.loads(json.dumps(got[k])) == want[k], k

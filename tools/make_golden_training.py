@@ -176,6 +176,89 @@ def make_reference_finish_object():
     return RefFinish()
 
 
+# ---------------------------------------------------------------- persistence (rows a12, a16)
+class StubVar:
+    def __init__(self, name, arr):
+        self.name, self._arr = name, np.asarray(arr)
+
+    def numpy(self):
+        return self._arr
+
+
+class StubOptimizer:
+    variables = [StubVar("Adam/iteration:0", 7), StubVar("Adam/m/conv/kernel:0", [[-1.0, 3.0]]),
+                 StubVar("Adam/v/conv/kernel:0", [0.5, 0.25, 0.0])]
+
+    def get_config(self):
+        return {"name": "Adam", "learning_rate": np.float32(1e-4), "beta_1": np.float64(0.9),
+                "steps": np.int64(3), "amsgrad": False, "epsilon": 1e-7}
+
+
+class StubHandler:
+    smoothing = 0.5
+    lr_features = ["u", "v"]
+    hr_out_features = ["u"]
+    unrelated = 1
+
+
+PARAMS = {"name": "gan", "loss": {"MeanAbsoluteError": {}}, "learning_rate": np.float32(1e-4),
+          "means": {"u": np.float32(1.5), "v": 2}, "stdevs": {"u": 0.5, "v": np.float64(3)},
+          "meta": {"s_enhance": np.int64(3), "lr_features": ("u", "v"), "arr": np.arange(3),
+                   "class": "Sup3rGan", "obj": complex(1, 2)},
+          "version_record": {"sup3r": "0.2"}, "default_device": "/gpu:0"}
+
+
+def persistence_scenario(cls, td):
+    """save_params / load_saved_params / optimiser config + state / batch handler attributes."""
+    rec = {}
+    obj = cls.__new__(cls)
+    type(obj).model_params = property(lambda self: PARAMS)
+    out_dir = os.path.join(td, "model", "sub")
+    obj.save_params(out_dir)
+    rec["files"] = sorted(os.listdir(out_dir))
+    rec["params_json"] = open(os.path.join(out_dir, "model_params.json")).read()
+    for with_history in (False, True):
+        if with_history:
+            open(os.path.join(out_dir, "history.csv"), "w").write("epoch,x\n0,1\n")
+        p = cls.load_saved_params(out_dir, verbose=with_history)
+        rec[f"loaded_{int(with_history)}"] = {
+            "keys": sorted(p), "history": None if p["history"] is None
+            else os.path.relpath(p["history"], td),
+            "means": {k: [float(v), type(v).__name__] for k, v in p["means"].items()},
+            "stdevs": {k: [float(v), type(v).__name__] for k, v in p["stdevs"].items()},
+            "meta": p["meta"]}
+    conf = cls.get_optimizer_config(StubOptimizer())
+    rec["optimizer_config"] = {k: [v, type(v).__name__] for k, v in conf.items()}
+    state = cls.get_optimizer_state(StubOptimizer())
+    rec["optimizer_state"] = {k: [float(v), type(v).__name__] for k, v in state.items()}
+    rec["handler_attrs"] = cls.check_batch_handler_attrs(StubHandler())
+    return rec
+
+
+def make_reference_persistence_class():
+    import locale
+    import pprint
+    from types import SimpleNamespace
+    asrc = open(os.path.join(REF, "sup3r/models/abstract.py")).read()
+    bsrc = open(os.path.join(REF, "sup3r/models/base.py")).read()
+    isrc = open(os.path.join(REF, "sup3r/models/interface.py")).read()
+    usrc = open(os.path.join(REF, "sup3r/utilities/utilities.py")).read()
+    ns = {"np": np, "os": os, "json": json, "locale": locale, "pprint": pprint,
+          "logger": MagicMock(), "tf": SimpleNamespace(Tensor=type("Tensor", (), {}))}
+    a = usrc.index("def safe_cast(")
+    exec(compile(usrc[a:usrc.index("\ndef ", a + 5)], "safe_cast", "exec"), ns)
+
+    class RefPersist:
+        pass
+    for name in ("load_saved_params", "get_optimizer_config"):
+        setattr(RefPersist, name, staticmethod(grab_method(asrc, name, ns)))
+    RefPersist.get_optimizer_state = classmethod(grab_method(asrc, "get_optimizer_state", ns))
+    RefPersist.check_batch_handler_attrs = staticmethod(
+        grab_method(bsrc, "check_batch_handler_attrs", ns))
+    RefPersist.save_params = grab_method(isrc, "save_params", ns)
+    return RefPersist
+
+
 # ---------------------------------------------------------------- Sup3rGanDC (8(f)1)
 class DCHandler:
     n_space_bins, n_time_bins = 3, 4
@@ -305,6 +388,9 @@ def main():
                                                            (0.9, 0.99), 1e-3, td))]
         for frac in (0.0, 0.1) for td in (True, False) for v in (0.5, 0.95, 1.0)]
     out["finish_epoch"] = finish_epoch_scenario(make_reference_finish_object())
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out["persistence"] = persistence_scenario(make_reference_persistence_class(), td)
     warn_log = []
     rec, arrs = norm_scenario(make_reference_norm_object(warn_log), warn_log)
     out["norm"] = rec
