@@ -18,10 +18,7 @@ def get_model(model_class, kwargs):
                "Make sure you typed in the model class name correctly.")
         logger.error(msg)
         raise KeyError(msg)
-    kwargs = dict(kwargs)
-    if "model_dirs" in kwargs:
-        return cls.load(**kwargs, verbose=True)
-    return cls.load(**kwargs, verbose=True)
+    return cls.load(**dict(kwargs), verbose=True)
 
 
 def get_chunk_slices(arr_size, chunk_size, index_slice=slice(None)):
