@@ -4,7 +4,12 @@ incremental-restart logic of SURVEY §5(d)) from the REAL reference methods: ``n
 and ``chunk_masked`` (sup3r/pipeline/strategy.py:363-383, 438-472, 663-700) are exec'd from
 their source text onto a stand-in object.
 
-    python tools/make_golden_strategy.py   ->  tests/golden/strategy.json
+Second record: ``get_time_slices`` (with the reference's ``_parse_time_slice``),
+``_get_fwp_chunk_shape`` and ``_init_features`` (strategy.py:306-333, 356-362, 385-391) over
+time slices given as slice / list / tuple / None, with and without a temporal pad, default
+(``None``) chunk-shape entries, exo features from ``exo_handler_kwargs``.
+
+    python tools/make_golden_strategy.py   ->  tests/golden/strategy.json, strategy_slices.json
 """
 import json
 import os
@@ -97,10 +102,66 @@ def scenario(Strategy):
     return rec
 
 
+OUT_SLICES = os.path.join(ROOT, "tests", "golden", "strategy_slices.json")
+TIME_SLICES = [None, slice(None), slice(0, 20), slice(5, 40, 2), [3, 30], (10, None), [None, 25],
+               slice(4, None, 3), [0, 12, 1]]
+CHUNK_SHAPES = [(4, 4, 10), (None, 6, None), (8, None, 5), (None, None, None)]
+
+
+def load_reference_slices():
+    src = open(os.path.join(REF, "sup3r/pipeline/strategy.py")).read()
+    usrc = open(os.path.join(REF, "sup3r/preprocessing/utilities.py")).read()
+    a = usrc.index("def _parse_time_slice")
+    ns = {"np": np, "logger": MagicMock()}
+    exec(compile(usrc[a:usrc.index("\ndef ", a + 1)], "utilities.py", "exec"), ns)
+    body = {}
+    for n in ("get_time_slices", "_get_fwp_chunk_shape", "_init_features"):
+        exec(compile(grab_body(src, n), n, "exec"), ns)
+        body[n] = ns[n]
+    return type("RefStrategy", (), body)
+
+
+def _sl(s):
+    return [s.start, s.stop, s.step]
+
+
+def slices_scenario(Strategy):
+    rec = {"time_slices": [], "chunk_shapes": [], "features": []}
+    for ts in TIME_SLICES:
+        for pad in (0, 3):
+            st = Strategy.__new__(Strategy)
+            st.input_handler_kwargs = {} if ts is None else {"time_slice": ts}
+            st.temporal_pad = pad
+            unpadded, padded = st.get_time_slices()
+            # (what the pair selects from a 60-step source, the statement that matters)
+            src_steps = np.arange(60)[padded]
+            rec["time_slices"].append({"unpadded": _sl(unpadded), "padded": _sl(padded),
+                                       "source_steps": [int(v) for v in src_steps],
+                                       "kept_steps": [int(v) for v in src_steps[unpadded]]})
+    for shape in CHUNK_SHAPES:
+        for tslice in (slice(None), slice(2, -2)):
+            st = Strategy.__new__(Strategy)
+            st.fwp_chunk_shape = shape
+            st.time_slice = tslice
+            st.input_handler = SimpleNamespace(grid_shape=(20, 30), time_index=np.arange(48))
+            rec["chunk_shapes"].append([int(v) for v in st._get_fwp_chunk_shape()])
+    model = SimpleNamespace(lr_features=["u_10m", "v_10m", "topography", "sza"])
+    for exo_kwargs in (None, {}, {"topography": {"a": 1}}, {"sza": {}, "topography": {}}):
+        st = Strategy.__new__(Strategy)
+        st.exo_handler_kwargs = exo_kwargs
+        st.exo_data = None
+        feats, exo = st._init_features(model)
+        rec["features"].append([list(feats), list(exo), st.exo_handler_kwargs])
+    return rec
+
+
 def main():
     rec = scenario(load_reference())
     json.dump(rec, open(OUT, "w"), indent=1)
     print("wrote", OUT)
+    srec = slices_scenario(load_reference_slices())
+    json.dump(srec, open(OUT_SLICES, "w"), indent=1)
+    print("wrote", OUT_SLICES)
     for r in rec:
         print(r["node_chunks"], r["node_finished"])
 
