@@ -169,9 +169,11 @@ class ForwardPass:
         (forward_pass.py:427-449).  Returns {chunk_index: output} for in-memory runs."""
         out = {}
         if not strategy.node_finished(node_index):
-            if strategy.pass_workers == 1:
+            if strategy.pass_workers == 1 and not strategy.postprocess:
                 out = cls._run_serial(strategy, node_index)
             else:
+                # (device-side post-processing lives in the streamed driver, whatever the
+                #  number of pass workers)
                 out = cls._run_batched(strategy, node_index, batch_size=strategy.pass_workers)
             logger.debug("Timing report:\n%s", pprint.pformat(strategy.timer.log, indent=2))
         return out

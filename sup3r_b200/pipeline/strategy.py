@@ -215,11 +215,16 @@ class ForwardPassStrategy:
     output_dtype: str = "float32"   # "float16": results are cast on the device and leave as fp16
     # apply the writer-side transforms (sup3r/writers/base.py:297-346: u/v -> ws/wd when
     # ``invert_uv``, physical limits with ``nn_fill`` or clipping) on the device before a chunk
-    # leaves the GPU (pipeline/postprocess.py)
-    postprocess: bool = False
+    # leaves the GPU (pipeline/postprocess.py).  None: on for ``.nc`` chunk files -- what the
+    # reference's writers always do (writers/nc.py:19-100 -> ``_transform_output``) -- and off for
+    # in-memory results and ``.npy`` files, which hold the raw generator output like the
+    # reference's ``run_chunk`` return value
+    postprocess: Optional[bool] = None
 
     def __post_init__(self):
         self.bias_correct_kwargs = self.bias_correct_kwargs or {}
+        if self.postprocess is None:
+            self.postprocess = bool(self.out_pattern) and str(self.out_pattern).endswith(".nc")
         if self.bias_correct_kwargs:
             from ..bias import METHODS
             if self.bias_correct_method not in METHODS:

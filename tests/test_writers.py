@@ -88,3 +88,38 @@ def test_forward_pass_writes_nc_chunks_and_collects(cuda, tmp_path):
         s_idx, t_idx = sl.get_chunk_indices(idx)
         hs = sl.s_hr_slices[s_idx]
         assert np.array_equal(ws[:, hs[0], hs[1]], np.transpose(chunk[..., 0], (2, 0, 1)))
+
+
+def test_writer_transform_default_and_dispatch(monkeypatch, tmp_path):
+    """``postprocess=None`` resolves to the reference's behaviour: chunk files in the reference's
+    format (.nc) get the writer-side transforms (writers/nc.py -> ``_transform_output``),
+    in-memory results and .npy files stay raw; runs that post-process go through the streamed
+    driver for any number of pass workers."""
+    from sup3r_b200 import configs as C
+    from sup3r_b200.models import Sup3rGan
+    from sup3r_b200.pipeline import ArrayInputHandler, ForwardPass, ForwardPassStrategy
+    m = Sup3rGan(C.spatiotemporal_generator(2, 2, (2,), n_blocks=1, filters=16),
+                 C.discriminator(3, "same", (8,)), default_device="/cpu:0",
+                 meta={"lr_features": ["u_100m", "v_100m"], "hr_out_features": ["u_100m", "v_100m"],
+                       "s_enhance": 2, "t_enhance": 2})
+    data = np.zeros((8, 8, 6, 2), np.float32)
+    mk = lambda **kw: ForwardPassStrategy(
+        model=m, input_handler=ArrayInputHandler(data, ["u_100m", "v_100m"]),
+        fwp_chunk_shape=(4, 4, 6), **kw)
+    assert mk().postprocess is False
+    assert mk(out_pattern=str(tmp_path / "a_{file_id}.npy")).postprocess is False
+    assert mk(out_pattern=str(tmp_path / "a_{file_id}.nc")).postprocess is True
+    assert mk(out_pattern=str(tmp_path / "a_{file_id}.nc"), postprocess=False).postprocess is False
+    assert mk(postprocess=True).postprocess is True
+    calls = []
+    monkeypatch.setattr(ForwardPass, "_run_serial",
+                        classmethod(lambda cls, s, n: calls.append("serial") or {}))
+    monkeypatch.setattr(ForwardPass, "_run_streamed",
+                        classmethod(lambda cls, s, n, fwp=None: calls.append("streamed") or {}))
+    monkeypatch.setattr(ForwardPass, "__init__", lambda self, strategy, node_index=0: setattr(
+        self, "model", strategy.model))
+    ForwardPass.run(mk(), 0)
+    ForwardPass.run(mk(postprocess=True), 0)
+    ForwardPass.run(mk(postprocess=True, pass_workers=4), 0)
+    ForwardPass.run(mk(out_pattern=str(tmp_path / "b_{file_id}.nc")), 0)
+    assert calls == ["serial", "streamed", "streamed", "streamed"]
