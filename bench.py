@@ -274,13 +274,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 12))       # bounded sample: about 10 - 20 s of host work
     warm = 1 if args.warmup > 0 else 0
     vox, times, cores = cpu_reference(steps, warm)
     ms = 1e3 * float(np.mean(times))
     value = vox / (ms / 1e3)
-    sample = (f"{steps} timed pass(es) of 1 LR chunk {LR_CHUNK} through the torch-CPU port of the "
-              "literal reference op order (pad3 -> conv -> crop2 per layer, oneDNN, fp32)")
+    sample = (f"{steps} timed pass(es) ({sum(times):.1f} s) of 1 LR chunk {LR_CHUNK} through the "
+              "torch-CPU port of the literal reference op order (pad3 -> conv -> crop2 per layer, "
+              "oneDNN, fp32)")
     line = {"metric": METRIC, "value": value, "unit": "LR voxels/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -588,12 +589,14 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         # the CPU port runs the GPU arm's weights on its first chunk: its timing is the
         # cpu_baseline, its fp32 output the parity oracle (checker only, never the product path)
-        vox, times, cores, y_ref = cpu_reference(1, 1, weights=model.generator.get_weights(),
+        n_cpu = 8                         # about 10 s of host work on the box's 16 cores
+        vox, times, cores, y_ref = cpu_reference(n_cpu, 1, weights=model.generator.get_weights(),
                                                  x=x_host.numpy(), want_output=True)
         cpu = {"value": vox / float(np.mean(times)), "unit": "LR voxels/s", "cores": cores,
                "kind": "port",
-               "sample": "1 timed pass (after 1 warm-up) of 1 LR chunk 16x16x24x4 through the "
-                         "torch-CPU port of the literal reference op order (fp32, oneDNN)"}
+               "sample": f"{n_cpu} timed passes (after 1 warm-up, {sum(times):.1f} s) of 1 LR "
+                         "chunk 16x16x24x4 through the torch-CPU port of the literal reference "
+                         "op order (fp32, oneDNN)"}
         y_ref = y_ref.astype(np.float64)
         sc, rms = np.abs(y_ref).max(), np.sqrt(np.mean(y_ref ** 2))
         parity = {"oracle": "oracle/torch_ref.py (fp32 CPU port of the literal reference layer "
