@@ -30,7 +30,30 @@ for (_, use), name in sorted(zip(rows, names), key=lambda t: -int(t[0][1].get("R
                  f"{use.get('STACK')} |")
     spill += int(use.get("LOCAL", 0)) > 0 or int(use.get("STACK", 0)) > 0
 lines += ["", f"{len(rows)} kernels; {spill} with a local-memory stack frame (register-pressure "
-          "spills or locally indexed arrays; the tcgen05 kernels' frames belong to the epilogue "
-          "warps, whose `setmaxnreg` budget is 96 - 104 registers)."]
+          "spills or locally indexed arrays)."]
+# where the hot kernel's frame is touched: local loads / stores between consecutive tcgen05.mma
+sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+for tag, label in (("zring_kernelILi4ELi6E", "conv_umma_zring_kernel<4, 6>"),):
+    inside, gaps, with_local, local, n_local = False, 0, 0, 0, 0
+    seen = False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            inside = tag in line
+            seen = False
+            continue
+        if not inside:
+            continue
+        if re.search(r"UTC[HQ]MMA", line):
+            if seen:
+                gaps += 1
+                with_local += local > 0
+            seen, local = True, 0
+        elif re.search(r"\b(LDL|STL)\b", line):
+            local += 1
+            n_local += 1
+    lines += ["", f"`{label}` (the body convolution): {n_local} static LDL / STL instructions; "
+              f"{with_local} of the {gaps} gaps between consecutive `tcgen05.mma` instructions of "
+              "the issuing thread contain one (the rest of the frame traffic is in the producer / "
+              "epilogue code)."]
 open(OUT, "w").write("\n".join(lines) + "\n")
 print("wrote", OUT, len(rows), "kernels,", spill, "with a stack frame")
