@@ -3,9 +3,12 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/ as the checker of sup3r_b200.loss_metrics, never by
 the product.  Each function cites the reference lines it follows; keras MeanSquaredError /
 MeanAbsoluteError reduce to the global mean for the equally-shaped tensors used here.
-Pinned by the reference's own known-answer identities (tests/utilities/test_loss_metrics.py:
-174-309): np.gradient equality of the material derivative, LowResLoss == MSE without
-coarsening, LowResLoss on pre-coarsened fields, extremes dominated by single spikes.
+PINNED: ``tests/golden/losses.json`` holds the values of the REAL reference classes
+(``tools/make_golden_losses.py`` execs sup3r/utilities/loss_metrics.py with a numpy-backed ``tf``
+stub); ``tests/test_losses_golden.py`` holds this file to them at 1e-12.  Also checked against
+the reference's own known-answer identities (tests/utilities/test_loss_metrics.py:174-309):
+np.gradient equality of the material derivative, LowResLoss == MSE without coarsening,
+LowResLoss on pre-coarsened fields, extremes dominated by single spikes.
 """
 import numpy as np
 
