@@ -50,8 +50,10 @@ class ExoData(dict):
         return ExoData(out)
 
     @staticmethod
-    def _bounded(steps, lo, hi=None):
-        return [s for s in steps if lo <= s["model"] and (hi is None or s["model"] < hi)]
+    def _get_bounded_steps(steps, min_step, max_step=None):
+        """Steps whose model index lies in [min_step, max_step) (exo.py:132-142)."""
+        return [s for s in steps
+                if min_step <= s["model"] and (max_step is None or s["model"] < max_step)]
 
     def split(self, split_steps):
         """Split into consecutive ExoData objects at the given model-step indices; the step
@@ -63,7 +65,7 @@ class ExoData(dict):
         for feature, entry in self.items():
             for i, lo in enumerate(split_steps):
                 hi = split_steps[i + 1] if i + 1 < len(split_steps) else None
-                chosen = self._bounded(entry["steps"], lo, hi)
+                chosen = self._get_bounded_steps(entry["steps"], lo, hi)
                 for s in chosen:
                     s.update({"model": s["model"] - lo})
                 if chosen:
@@ -81,7 +83,8 @@ class ExoData(dict):
         return steps[kinds.index(combine_type)]["data"]
 
     @staticmethod
-    def _enhanced_slices(lr_slices, step):
+    def _get_enhanced_slices(lr_slices, step):
+        """Low-res slices scaled by the step's enhancement factors (exo.py:226-238)."""
         factors = [step["s_enhance"], step["s_enhance"], step["t_enhance"]]
         return [slice(s.start * f, s.stop * f) for f, s in zip(factors, lr_slices)]
 
@@ -91,7 +94,7 @@ class ExoData(dict):
         chunk = {f: {"steps": []} for f in self}
         for feature in self:
             for step in self[feature]["steps"]:
-                sl = self._enhanced_slices(lr_slices, step)
+                sl = self._get_enhanced_slices(lr_slices, step)
                 new = {}
                 for k, v in step.items():
                     new[k] = v[tuple(sl)[: len(v.shape) - 1]] if k == "data" else v

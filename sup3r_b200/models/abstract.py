@@ -461,7 +461,41 @@ class AbstractSingleModel(TensorboardMixIn):
         logger.debug("Finished single gradient descent step in %.4f seconds", time.time() - t0)
         return loss_details
 
+    def _get_parallel_grad(self, low_res, hi_res_true, training_weights, **calc_loss_kwargs):
+        """``(total_grad, loss_details)`` of a multi-GPU step (abstract.py:807-841) in a
+        one-process-per-GPU world: the batch (and a ``mask`` keyword) is split along axis 0 into
+        world_size equal shards, this rank differentiates shard ``rank`` (the reference's
+        ``/gpu:<rank>`` thread), the shard gradients are SUMMED over the ranks and the loss
+        details of the last shard reach every rank (``_sum_parallel_grad``)."""
+        from .. import parallel
+        kw = dict(calc_loss_kwargs)
+        if kw.get("mask") is not None:
+            kw["mask"] = parallel.shard_batch(kw["mask"])
+        grad, loss_details = self.get_single_grad(
+            parallel.shard_batch(low_res), parallel.shard_batch(hi_res_true), training_weights,
+            device_name=self.default_device, **kw)
+        return parallel.allreduce_sum_grads(grad), parallel.broadcast_loss_details(loss_details)
+
+    def _sum_parallel_grad(self, futures, start_time):
+        """SUM of the ``(grad, loss_details)`` results of ``futures`` (objects with
+        ``.result()``), loss details of the last one (abstract.py:785-805).  The product's
+        multi-GPU step sums over ranks instead (``_get_parallel_grad``); kept for callers that
+        hold per-shard results in one process."""
+        total_grad = loss_details = None
+        for future in futures:
+            grad, loss_details = future.result()
+            total_grad = list(grad) if total_grad is None else \
+                [t + g for t, g in zip(total_grad, grad)]
+        logger.info("Finished %d gradient descent steps in %.4f seconds", len(futures),
+                    time.time() - start_time)
+        return total_grad, loss_details
+
     # ---- exo layers --------------------------------------------------------------------------
+    def _run_exo_layer(self, layer, input_array, hi_res_exo):
+        """Run an exo / observation layer on a device tensor with the ``{feature: tensor}``
+        dictionary of ``_tf_generate`` (abstract.py:1107-1129)."""
+        return _run_exo_layer(layer, input_array, hi_res_exo)
+
     def _reshape_norm_exo(self, hi_res, hi_res_exo, exo_name, norm_in=True):
         """Normalise a hi-res exo array and tile it to the rank of ``hi_res``
         (abstract.py:916-979)."""

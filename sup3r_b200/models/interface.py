@@ -21,6 +21,21 @@ logger = logging.getLogger(__name__)
 class AbstractInterface:
     """Interface shared by single and multi-step models."""
 
+    # ---- abstract in the reference (interface.py:32-57, 358-361): every model class defines them
+    @classmethod
+    def load(cls, model_dir, verbose=True):
+        """Load the model from a previously saved-to output directory."""
+        raise NotImplementedError(f"{cls.__name__} must define load()")
+
+    def generate(self, low_res, norm_in=True, un_norm_out=True, exogenous_data=None):
+        """High-res data from low-res input: the public generate function."""
+        raise NotImplementedError(f"{type(self).__name__} must define generate()")
+
+    @property
+    def meta(self):
+        """Meta data dictionary that defines how the model was created."""
+        raise NotImplementedError(f"{type(self).__name__} must define meta")
+
     @staticmethod
     def seed(s=0):
         """Seed weight initialisation for reproducible results (interface.py:59-69)."""

@@ -22,12 +22,16 @@ import numpy as np
 from ..utilities import Timer
 from .strategy import ForwardPassChunk, ForwardPassStrategy
 from .utilities import get_model
+from .writers import OutputHandlerNC
 
 logger = logging.getLogger(__name__)
 
 
 class ForwardPass:
     """Forward-pass driver for one node (= one GPU rank)."""
+
+    # chunk file writers by file type (forward_pass.py:49-52; the h5 writer is out of scope)
+    OUTPUT_HANDLER_CLASS = {"nc": OutputHandlerNC}
 
     def __init__(self, strategy, node_index=0):
         self.timer = Timer()
@@ -204,6 +208,12 @@ class ForwardPass:
                 outputs[chunk_index] = data
         logger.info("Finished forward passes on %d chunks in %s", len(chunks), dt.now() - start)
         return outputs
+
+    @classmethod
+    def _run_parallel(cls, strategy, node_index):
+        """The reference's name for the multi-worker path (forward_pass.py:503-580: a pool of
+        ``pass_workers`` processes); here the workers are the batch entries of one GPU."""
+        return cls._run_batched(strategy, node_index, batch_size=strategy.pass_workers)
 
     @classmethod
     def _run_batched(cls, strategy, node_index, batch_size=8):

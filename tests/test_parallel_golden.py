@@ -72,6 +72,12 @@ def _run_case(name, rank):
     assert sorted(details) == sorted(want["details"])
     for k, v in want["details"].items():
         assert float(details[k]) == pytest.approx(v, rel=2e-6), (name, k)
+    if sharded:
+        # the reference's private entry point (abstract.py:807-841) gives the same sums
+        total, det = obj._get_parallel_grad(lr, hr, weights, **kw)
+        for g, w in zip(total, want["applied"]):
+            np.testing.assert_allclose(g.numpy(), np.array(w), rtol=2e-6, err_msg=name)
+        assert float(det["first"]) == pytest.approx(want["details"]["first"], rel=2e-6)
 
 
 def _worker(rank, world, port, q):
