@@ -48,3 +48,30 @@ def test_enhancement_check():
         with pytest.raises(RuntimeError):
             model.set_model_params(input_resolution={"spatial": "12km", "temporal": "60min"},
                                    s_enhance=7, t_enhance=3)
+
+
+def test_training_session_runs_train_in_a_thread_and_stops_the_handler_on_failure():
+    """sup3r/models/utilities.py:30-74."""
+    import threading
+    from sup3r_b200.models.utilities import (SUP3R_EXO_LAYERS, SUP3R_LAYERS, SUP3R_OBS_LAYERS,
+                                             TrainingSession, get_optimizer_class)
+    assert set(SUP3R_LAYERS) == set(SUP3R_EXO_LAYERS) | set(SUP3R_OBS_LAYERS)
+    assert get_optimizer_class({"name": "Adam"}).__name__ == "Adam"
+    seen = {}
+
+    class Handler:
+        stopped = 0
+
+        def stop(self):
+            Handler.stopped += 1
+
+    class Model:
+        def train(self, batch_handler, **kw):
+            seen.update(handler=batch_handler, kw=kw, thread=threading.current_thread())
+    bh = Handler()
+    TrainingSession(bh, Model(), n_epoch=3, input_resolution={"spatial": "4km"}).run()
+    assert seen["handler"] is bh and seen["kw"]["n_epoch"] == 3
+    assert seen["thread"] is not threading.main_thread() and Handler.stopped == 0
+    with pytest.raises(SystemExit):          # no n_epoch: the session cannot start
+        TrainingSession(bh, Model()).run()
+    assert Handler.stopped == 1
