@@ -76,12 +76,29 @@ def local_linear_bc(data, lat_lon, feature_name, bias_fp, lr_padded_slice=None, 
     return _clip(data * scalar + adder, out_range)
 
 
-def monthly_local_linear_bc(data, lat_lon, feature_name, bias_fp, months=None,
+def make_time_index_from_kws(date_range_kwargs):
+    """``pd.date_range(**date_range_kwargs)``; the extra key ``drop_leap`` removes every
+    29 February (sup3r/preprocessing/utilities.py:222-244; the caller's dict is left alone)."""
+    import pandas as pd
+    kw = dict(date_range_kwargs)
+    drop_leap = kw.pop("drop_leap", False)
+    time_index = pd.date_range(**kw)
+    if drop_leap:
+        time_index = time_index[~((time_index.month == 2) & (time_index.day == 29))]
+    return time_index
+
+
+def monthly_local_linear_bc(data, lat_lon, feature_name, bias_fp, date_range_kwargs=None,
                             lr_padded_slice=None, temporal_avg=True, out_range=None, smoothing=0,
-                            scalar_range=None, adder_range=None, threshold=0.1):
+                            scalar_range=None, adder_range=None, threshold=0.1, months=None):
     """Site-by-site linear correction with one factor pair per calendar month
-    (bias_transforms.py:351-487).  ``months``: 1-based month of every time step of ``data`` (the
-    reference derives it from ``date_range_kwargs``)."""
+    (bias_transforms.py:351-487).  The month of every time step of ``data`` comes from
+    ``date_range_kwargs`` (-> ``pd.date_range``, like the reference) or, when the forward-pass
+    hook knows the chunk's time index, from ``months`` (1-based)."""
+    if months is None:
+        assert date_range_kwargs is not None, (
+            "monthly_local_linear_bc needs date_range_kwargs (or the months of the time steps)")
+        months = make_time_index_from_kws(date_range_kwargs).month.values
     scalar, adder = _factors(feature_name, bias_fp)
     assert scalar.ndim == 3, "Monthly bias correct needs 3D scalars"
     assert adder.ndim == 3, "Monthly bias correct needs 3D adders"
@@ -158,8 +175,7 @@ def _run_qdm(data, params, day_of_year, date_range_kwargs, lr_padded_slice, rela
     data = np.asarray(data, dtype=np.float32)
     assert data.ndim == 3, f"data was expected to be a 3D array but got shape {data.shape}"
     if day_of_year is None:
-        import pandas as pd
-        day_of_year = pd.date_range(**date_range_kwargs).day_of_year
+        day_of_year = make_time_index_from_kws(date_range_kwargs).day_of_year
     day_of_year = np.asarray(day_of_year)
     assert data.shape[-1] == day_of_year.size, (
         f"Time should align with data 3rd dimension but got data {data.shape} and time_index "
@@ -282,7 +298,7 @@ def bias_correct_features(data, features, lat_lon, bc_method, bc_kwargs, lr_padd
                 if dates is not None:
                     if "day_of_year" in pars and "date_range_kwargs" not in kw:
                         kw.setdefault("day_of_year", np.asarray(dates.day_of_year))
-                    if "months" in pars:
+                    if "months" in pars and "date_range_kwargs" not in kw:
                         kw.setdefault("months", np.asarray(dates.month))
                 data[..., i] = fun(data[..., i], lat_lon, **kw)
         except Exception as e:

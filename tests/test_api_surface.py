@@ -45,7 +45,32 @@ def _classes():
             "SingleExoDataStep": E.SingleExoDataStep, "ExoData": E.ExoData}
 
 
-@pytest.mark.parametrize("cname", sorted(G))
+FUNCTION_HOMES = {"sup3r/bias/bias_transforms.py": "sup3r_b200.bias",
+                  "sup3r/utilities/utilities.py": "sup3r_b200.utilities",
+                  "sup3r/pipeline/utilities.py": "sup3r_b200.pipeline.utilities",
+                  "sup3r/models/utilities.py": "sup3r_b200.models.utilities",
+                  "sup3r/preprocessing/utilities.py": "sup3r_b200.bias"}
+
+
+def test_function_signatures_match_reference():
+    import importlib
+    problems = []
+    for name, d in G["__functions__"].items():
+        fn = getattr(importlib.import_module(FUNCTION_HOMES[d["file"]]), name)
+        params = list(inspect.signature(fn).parameters.values())
+        ref_names = [p for p, _ in d["params"]]
+        if [p.name for p in params[:len(ref_names)]] != ref_names:
+            problems.append(f"{name}: {ref_names} in the reference, {[p.name for p in params]}")
+            continue
+        for (pn, pdef), p in zip(d["params"], params):
+            if pdef is not None and pdef != "slice(None)" and repr(p.default) != pdef:
+                problems.append(f"{name}({pn}): default {pdef} in the reference, {p.default!r}")
+        problems += [f"{name}({p.name}): extra REQUIRED parameter"
+                     for p in params[len(ref_names):] if p.default is inspect.Parameter.empty]
+    assert not problems, "\n  ".join(problems)
+
+
+@pytest.mark.parametrize("cname", sorted(k for k in G if not k.startswith("__")))
 def test_class_surface_matches_reference(cname):
     cls = _classes()[cname]
     fields = {f.name: f for f in dataclasses.fields(cls)} if dataclasses.is_dataclass(cls) else {}

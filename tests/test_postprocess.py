@@ -240,3 +240,33 @@ def test_bias_hook_derives_months_from_a_datetime_time_index(tmp_path):
     with pytest.raises(RuntimeError):
         bias.bias_correct_features(data.copy(), ["u", "v"], None, "monthly_local_linear_bc", kw,
                                    time_index=np.arange(6))
+
+
+def test_monthly_bias_correction_with_the_reference_call_signature(tmp_path):
+    """bias_transforms.py:351-487: ``date_range_kwargs`` is the fifth positional argument; the
+    time index is ``pd.date_range(**kwargs)`` minus 29 February when ``drop_leap`` is set
+    (preprocessing/utilities.py:222-244)."""
+    import pandas as pd
+    from sup3r_b200 import bias
+    rng = np.random.default_rng(1)
+    scalar = rng.uniform(0.5, 1.5, (4, 3, 12)).astype(np.float32)
+    adder = rng.uniform(-1, 1, (4, 3, 12)).astype(np.float32)
+    fp = str(tmp_path / "bc.npz")
+    np.savez(fp, u_scalar=scalar, u_adder=adder)
+    drk = {"start": "2020-02-27", "end": "2020-03-04", "freq": "D", "drop_leap": True}
+    ti = bias.make_time_index_from_kws(drk)
+    assert drk["drop_leap"] is True                      # the caller's dict is not consumed
+    assert len(ti) == 6 and not ((ti.month == 2) & (ti.day == 29)).any()
+    assert len(bias.make_time_index_from_kws({k: v for k, v in drk.items()
+                                              if k != "drop_leap"})) == 7
+    data = rng.standard_normal((4, 3, 6)).astype(np.float32)
+    out = bias.monthly_local_linear_bc(data, None, "u", fp, drk, None, False)
+    m = np.asarray(ti.month) - 1
+    assert np.allclose(out, data * scalar[..., m] + adder[..., m])
+    kw = {"u": {"bias_fp": fp, "temporal_avg": False, "date_range_kwargs": drk}}
+    hooked = bias.bias_correct_features(
+        np.stack([data, data], -1), ["u", "v"], None, "monthly_local_linear_bc", kw,
+        time_index=pd.date_range("2021-07-01", periods=6).values)   # kwargs win over the index
+    assert np.array_equal(hooked[..., 0], out)
+    with pytest.raises(AssertionError):
+        bias.monthly_local_linear_bc(data, None, "u", fp)

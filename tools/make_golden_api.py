@@ -29,6 +29,19 @@ CLASSES = {
 }
 
 
+# reference file -> module-level functions mirrored here
+FUNCTIONS = {
+    "sup3r/bias/bias_transforms.py": ["global_linear_bc", "local_linear_bc",
+                                      "monthly_local_linear_bc", "local_qdm_bc",
+                                      "local_presrat_bc"],
+    "sup3r/utilities/utilities.py": ["camel_to_underscore", "safe_cast", "temporal_coarsening",
+                                     "spatial_coarsening"],
+    "sup3r/pipeline/utilities.py": ["get_model", "get_chunk_slices"],
+    "sup3r/models/utilities.py": ["get_optimizer_class"],
+    "sup3r/preprocessing/utilities.py": ["make_time_index_from_kws"],
+}
+
+
 def _default(node):
     try:
         return repr(ast.literal_eval(node))
@@ -74,8 +87,15 @@ def main():
                             "kind": "field",
                             "default": None if item.value is None else _default(item.value)}
                 rec[node.name] = {"file": path, "members": members}
+    funcs = {}
+    for path, names in FUNCTIONS.items():
+        tree = ast.parse(open(os.path.join(REF, path)).read())
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                funcs[node.name] = dict(describe(node), file=path)
+    rec["__functions__"] = funcs
     json.dump(rec, open(OUT, "w"), indent=1, sort_keys=True)
-    print("wrote", OUT, {k: len(v["members"]) for k, v in rec.items()})
+    print("wrote", OUT, {k: len(v.get("members", v)) for k, v in rec.items()})
 
 
 if __name__ == "__main__":
