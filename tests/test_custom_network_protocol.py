@@ -81,3 +81,36 @@ def test_bad_configs_raise():
         CustomNetwork(hidden_layers=[{"class": "NoSuchLayer"}], device="cpu")
     with pytest.raises(TypeError):
         CustomNetwork(hidden_layers=["Conv2D"], device="cpu")
+
+
+def test_optimizer_protocol():
+    """What sup3r.models consumes from a keras optimiser (abstract.py:321-350, 543-587, base.py:
+    326-348, tests/training/test_train_gan.py:370-386): ``get_config`` with ``name`` and
+    ``learning_rate``, ``from_config``, ``variables`` with ``.name`` / ``.numpy()``,
+    ``learning_rate`` comparable to a float, class lookup by config (``ValueError`` otherwise)."""
+    import torch
+    from sup3r_b200.models.abstract import AbstractSingleModel
+    from sup3r_b200.network import Variable
+    from sup3r_b200.optimizers import Adam, get_optimizer_class
+    opt = AbstractSingleModel.init_optimizer(None, 1e-4)
+    assert isinstance(opt, Adam) and opt.learning_rate == 1e-4
+    conf = opt.get_config()
+    assert conf["name"] == "Adam" and conf["learning_rate"] == 1e-4
+    assert (conf["beta_1"], conf["beta_2"], conf["epsilon"]) == (0.9, 0.999, 1e-7)   # keras
+    conf.update(learning_rate=0.25)
+    new = get_optimizer_class(conf).from_config(conf)
+    assert isinstance(new, Adam) and new.learning_rate == 0.25 and new.beta_2 == 0.999
+    from_dict = AbstractSingleModel.init_optimizer(
+        {"name": "Adam", "beta_1": 0.5, "learning_rate": 3e-4, "not_a_parameter": 1}, 7.0)
+    assert from_dict.beta_1 == 0.5 and from_dict.learning_rate == 3e-4
+    assert AbstractSingleModel.init_optimizer(opt, 7.0) is opt
+    w = Variable("generator/conv2d/kernel:0", torch.zeros(2, 3))
+    opt.slots_for(w)
+    names = [v.name for v in opt.variables]
+    assert names == ["Adam/iteration:0", "Adam/m/generator/conv2d/kernel:0",
+                     "Adam/v/generator/conv2d/kernel:0"]
+    assert opt.variables[0].numpy() == 0 and opt.variables[1].numpy().shape == (2, 3)
+    state = AbstractSingleModel.get_optimizer_state(opt)
+    assert state["learning_rate"] == 1e-4
+    with pytest.raises(ValueError):
+        get_optimizer_class({"name": "NoSuchOptimizer"})
