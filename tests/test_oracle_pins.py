@@ -158,3 +158,79 @@ def test_conv_oracle_agrees_with_scipy_correlate(nd, strides, padding):
                 acc = acc + correlate(xp[n, ..., ci], w[..., ci, co], mode="valid")[sl]
             ref[n, ..., co] = acc + b[co]
     assert np.allclose(got, ref, atol=1e-12)
+
+
+def test_published_tensorflow_api_examples():
+    """Known answers printed in the TensorFlow API documentation of the ops the generator is
+    built from (third-party published vectors; TensorFlow itself is not installed)."""
+    # tf.nn.depth_to_space (block_size 2, NHWC): the three examples of its docstring
+    x = np.array([[[[1, 2, 3, 4]]]], np.float32)
+    assert L.depth_to_space(x, 2).tolist() == [[[[1], [2]], [[3], [4]]]]
+    x = np.array([[[[1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]]]], np.float32)
+    assert L.depth_to_space(x, 2).tolist() == [[[[1, 2, 3], [4, 5, 6]], [[7, 8, 9], [10, 11, 12]]]]
+    x = np.array([[[[1, 2, 3, 4], [5, 6, 7, 8]], [[9, 10, 11, 12], [13, 14, 15, 16]]]], np.float32)
+    assert L.depth_to_space(x, 2).tolist() == [[[[1], [2], [5], [6]], [[3], [4], [7], [8]],
+                                                [[9], [10], [13], [14]], [[11], [12], [15], [16]]]]
+    # tf.pad: t = [[1, 2, 3], [4, 5, 6]], paddings = [[1, 1], [2, 2]]
+    t = np.array([[1, 2, 3], [4, 5, 6]], np.float32)
+    assert L.tf_pad(t, [[1, 1], [2, 2]], "REFLECT").tolist() == [
+        [6, 5, 4, 5, 6, 5, 4], [3, 2, 1, 2, 3, 2, 1], [6, 5, 4, 5, 6, 5, 4], [3, 2, 1, 2, 3, 2, 1]]
+    assert L.tf_pad(t, [[1, 1], [2, 2]], "SYMMETRIC").tolist() == [
+        [2, 1, 1, 2, 3, 3, 2], [2, 1, 1, 2, 3, 3, 2], [5, 4, 4, 5, 6, 6, 5], [5, 4, 4, 5, 6, 6, 5]]
+    assert L.tf_pad(t, [[1, 1], [2, 2]], "CONSTANT").tolist() == [
+        [0, 0, 0, 0, 0, 0, 0], [0, 0, 1, 2, 3, 0, 0], [0, 0, 4, 5, 6, 0, 0], [0, 0, 0, 0, 0, 0, 0]]
+
+
+def test_published_tensorflow_conv_and_loss_examples():
+    """More known answers from the TensorFlow / Keras API documentation: the ``tf.nn.conv2d``
+    example (cross-correlation, kernel laid out (kh, kw, cin, cout), VALID), ``LeakyReLU``,
+    ``sigmoid_cross_entropy_with_logits``, keras ``MeanSquaredError`` / ``MeanAbsoluteError``,
+    ``tf.roll`` (the shift of the depth-to-time expansion) and the first keras ``Adam`` step."""
+    import torch
+    from oracle import losses_ref, torch_ref
+    x_in = np.array([[[[2], [1], [2], [0], [1]], [[1], [3], [2], [2], [3]], [[1], [1], [3], [3], [0]],
+                      [[2], [2], [0], [1], [1]], [[0], [0], [3], [1], [2]]]], np.float64)
+    kernel_in = np.array([[[[2, 0.1]], [[3, 0.2]]], [[[0, 0.3]], [[1, 0.4]]]])
+    want = np.array([[[[10., 1.9], [10., 2.2], [6., 1.6], [6., 2.]],
+                      [[12., 1.4], [15., 2.2], [13., 2.7], [13., 1.7]],
+                      [[7., 1.7], [11., 1.3], [16., 1.3], [7., 1.]],
+                      [[10., 0.6], [7., 1.4], [4., 1.5], [7., 1.4]]]])
+    np.testing.assert_allclose(L.conv_nd(x_in, kernel_in, None, 1, "valid"), want, atol=1e-12)
+    # the same through the Conv2D layer objects of both oracles (keras weight order)
+    hl = [{"class": "Conv2D", "filters": 2, "kernel_size": 2, "strides": 1}]
+    layers = L.build_layers(hl)
+    L.build_weights(layers, x_in.shape, seed=0)
+    L.set_weights(layers, [kernel_in, np.zeros(2)])
+    np.testing.assert_allclose(L.run_layers(layers, x_in), want, atol=1e-12)
+    net = torch_ref.TorchRefNet(hl, [kernel_in, np.zeros(2)], torch.float64)
+    np.testing.assert_allclose(net(torch.from_numpy(x_in)).numpy(), want, atol=1e-12)
+    # tf.keras.layers.LeakyReLU: default alpha 0.3; alpha=0.1
+    v = np.array([-3.0, -1.0, 0.0, 2.0])
+    np.testing.assert_allclose(L.LeakyReLU()(v), [-0.9, -0.3, 0.0, 2.0], atol=1e-12)
+    np.testing.assert_allclose(L.LeakyReLU(alpha=0.1)(v), [-0.3, -0.1, 0.0, 2.0], atol=1e-12)
+    # tf.nn.sigmoid_cross_entropy_with_logits
+    logits = torch.tensor([1., -1., 0., 1., -1., 0., 0.], dtype=torch.float64)
+    labels = torch.tensor([0., 0., 0., 1., 1., 1., 0.5], dtype=torch.float64)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="none")
+    np.testing.assert_allclose(bce.numpy(), [1.3132616, 0.3132617, 0.6931472, 0.3132617, 1.3132616,
+                                             0.6931472, 0.6931472], atol=1e-7)
+    # (the relativistic loss of the oracle is that function on [true - mean(gen), gen - mean(true)])
+    t, g = torch.tensor([[1.0], [2.0]]), torch.tensor([[0.5], [-0.5]])
+    lg = torch.cat([t - g.mean(), g - t.mean()])
+    lb = torch.cat([torch.ones_like(t), torch.zeros_like(g)])
+    assert float(torch_ref.disc_loss(t, g)) == pytest.approx(float(
+        torch.nn.functional.binary_cross_entropy_with_logits(lg, lb)), rel=1e-12)
+    # tf.keras.losses.MeanSquaredError / MeanAbsoluteError
+    y_true, y_pred = np.array([[0., 1.], [0., 0.]]), np.array([[1., 1.], [1., 0.]])
+    assert losses_ref.mse(y_pred, y_true) == 0.5 and losses_ref.mae(y_pred, y_true) == 0.5
+    # tf.roll
+    assert np.roll(np.arange(5.0), 2).tolist() == [3., 4., 0., 1., 2.]
+    x = np.arange(12, dtype=np.float64).reshape(1, 1, 1, 2, 6)
+    rolled = L.spatiotemporal_expansion(x, 1, 3, "depth_to_time", 2)[0, 0, 0, :, 0]
+    assert rolled.tolist() == np.roll(np.arange(0.0, 12.0, 2.0), 2).tolist()
+    # tf.keras.optimizers.Adam(learning_rate=0.1) on loss = var ** 2 / 2 from var = 10: one step
+    # gives 9.9 (the first Adam step has size lr whatever the gradient)
+    p, grad, lr, b1, b2, eps = 10.0, 10.0, 0.1, 0.9, 0.999, 1e-7
+    m, vv = (1 - b1) * grad, (1 - b2) * grad * grad
+    p -= lr * np.sqrt(1 - b2) / (1 - b1) * m / (np.sqrt(vv) + eps)
+    assert p == pytest.approx(9.9, abs=1e-6)
