@@ -228,6 +228,10 @@ def test_published_tensorflow_conv_and_loss_examples():
     x = np.arange(12, dtype=np.float64).reshape(1, 1, 1, 2, 6)
     rolled = L.spatiotemporal_expansion(x, 1, 3, "depth_to_time", 2)[0, 0, 0, :, 0]
     assert rolled.tolist() == np.roll(np.arange(0.0, 12.0, 2.0), 2).tolist()
+    # tf.repeat(..., axis) repeats element-wise ([1, 1, 2, 2], not a tile): the "nearest" expansion
+    x = np.array([1.0, 2.0, 3.0]).reshape(1, 1, 1, 3, 1)
+    assert L.spatiotemporal_expansion(x, 1, 2, "nearest", 0)[0, 0, 0, :, 0].tolist() == \
+        [1., 1., 2., 2., 3., 3.]
     # tf.keras.optimizers.Adam(learning_rate=0.1) on loss = var ** 2 / 2 from var = 10: one step
     # gives 9.9 (the first Adam step has size lr whatever the gradient)
     p, grad, lr, b1, b2, eps = 10.0, 10.0, 0.1, 0.9, 0.999, 1e-7
