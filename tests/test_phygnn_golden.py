@@ -93,3 +93,79 @@ def test_export_format_round_trip_cuda(cuda, tmp_path):
     for precision, tol in (("fp32", 1e-4), ("fp16c", 1e-3)):
         got = model.generate(x, norm_in=False, un_norm_out=False, precision=precision)
         assert np.abs(got - y).max() / np.abs(y).max() < tol, precision
+
+
+def test_exporter_tool_against_a_stand_in_sup3r(tmp_path, monkeypatch):
+    """tools/export_phygnn_weights.py run end to end (``--config`` mode) against a stand-in
+    ``sup3r.models.Sup3rGan`` that exposes what the tool touches of the real class (lazily built
+    ``generator.weights`` with ``name / numpy() / assign() / shape``, ``generate``, ``is_5d``,
+    feature lists): the directory it writes is what the slot tests above consume."""
+    import importlib.util
+    import sys
+    import types
+
+    class Var:
+        def __init__(self, name, arr):
+            self.name, self._a, self.shape = name, arr, arr.shape
+
+        def numpy(self):
+            return self._a
+
+        def assign(self, v):
+            assert v.shape == self._a.shape
+            self._a = np.asarray(v, self._a.dtype)
+
+    class Net:
+        def __init__(self, fp):
+            self.hl = json.load(open(fp))["hidden_layers"]
+            self.layers, self.weights = None, []
+
+        def run(self, x):
+            if self.layers is None:
+                self.layers = L.build_layers(self.hl)
+                L.build_weights(self.layers, x.shape, seed=5)
+                names = [f"generator/layer_{i // 2}/{'bias' if i % 2 else 'kernel'}:0"
+                         for i in range(len(L.get_weights(self.layers)))]
+                self.weights = [Var(n, w) for n, w in zip(names, L.get_weights(self.layers))]
+            L.set_weights(self.layers, [w.numpy() for w in self.weights])
+            return L.run_layers(self.layers, x.astype(np.float64)).astype(np.float32)
+
+    class FakeGan:
+        lr_features, hr_exo_features, obs_features, is_5d = [], [], [], True
+
+        def __init__(self, fp_gen, fp_disc):
+            self.generator, self.discriminator = Net(fp_gen), Net(fp_disc)
+
+        @staticmethod
+        def seed(s=0):
+            pass
+
+        def generate(self, x, norm_in=True, un_norm_out=True):
+            assert not norm_in and not un_norm_out
+            return self.generator.run(x)
+    pkg, mod = types.ModuleType("sup3r"), types.ModuleType("sup3r.models")
+    mod.Sup3rGan = FakeGan
+    pkg.models = mod
+    monkeypatch.setitem(sys.modules, "sup3r", pkg)
+    monkeypatch.setitem(sys.modules, "sup3r.models", mod)
+    fp_gen, fp_disc = str(tmp_path / "gen.json"), str(tmp_path / "disc.json")
+    json.dump({"hidden_layers": C.spatiotemporal_generator(2, 2, (2,), n_blocks=1, filters=8)},
+              open(fp_gen, "w"))
+    json.dump({"hidden_layers": C.discriminator(3, "same", (8,))}, open(fp_disc, "w"))
+    spec = importlib.util.spec_from_file_location(
+        "export_phygnn_weights", os.path.join(os.path.dirname(HERE), "tools",
+                                              "export_phygnn_weights.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    out = str(tmp_path / "export" / "random_st")
+    tool.main(["--config", fp_gen, fp_disc, out])
+    assert find_golden_dirs(str(tmp_path / "export")) == [out]
+    assert not os.path.exists(os.path.join(out, "disc_weights.npz"))   # never built: not exported
+    x, y = load_golden(out)
+    assert x.shape == (1, 10, 10, 6, 2) and y.shape == (1, 20, 20, 12, 2)
+    ws = _weights(out)
+    assert any(w.ndim == 1 and np.abs(w).max() > 0 for w in ws)          # biases were randomised
+    layers = L.build_layers(_hidden_layers(out))
+    L.set_weights(layers, ws)
+    got = L.run_layers(layers, x.astype(np.float64))
+    assert np.abs(got - y).max() <= 1e-5 * np.abs(y).max()
