@@ -62,6 +62,19 @@ def discriminate_for(xp):
     return _tf_discriminate
 
 
+def order_probe(mean):
+    """A deliberately ASYMMETRIC loss class (every loss the reference ships is symmetric in its
+    two arguments): put into the loss module on both sides, it shows which tensor is passed
+    first (base.py:478-503: the generated one) and that constructor kwargs arrive."""
+    class OrderProbe:
+        def __init__(self, scale=1.0):
+            self.scale = scale
+
+        def __call__(self, x1, x2):
+            return mean(x1) - self.scale * mean(x2 * x2)
+    return OrderProbe
+
+
 def load_reference():
     """Stand-in class carrying the reference's methods."""
     def bce(logits, labels):
@@ -75,7 +88,8 @@ def load_reference():
     tf.unstack = lambda x, axis: [np.take(x, i, axis=axis) for i in range(x.shape[axis])]
     losses_ns = LT.load_reference()
     sup3r = SimpleNamespace(utilities=SimpleNamespace(
-        loss_metrics=SimpleNamespace(**{k: v for k, v in losses_ns.items()
+        loss_metrics=SimpleNamespace(OrderProbe=order_probe(np.mean),
+                                     **{k: v for k, v in losses_ns.items()
                                         if isinstance(v, type)})))
     ns = {"np": np, "tf": tf, "copy": copy, "re": re, "logger": MagicMock(), "sup3r": sup3r,
           "SUP3R_OBS_LAYERS": (ObsLayer,), "SUP3R_LAYERS": (ObsLayer, ExoLayer)}
@@ -125,6 +139,8 @@ LOSSES = {
                     "LowResLoss": {"s_enhance": 2, "t_enhance": 2, "tf_loss": "MeanAbsoluteError"},
                     "term_weights": [0.2, 1.0, 3.0]},
     "no_weights": {"ExpLoss": {}, "TemporalExtremesLoss": {}},
+    "order_probe": {"OrderProbe": {"scale": 2.0}, "MeanAbsoluteError": {},
+                    "term_weights": [0.5, 1.0]},
 }
 FLAGS = [dict(train_gen=True, train_disc=False), dict(train_gen=True, train_disc=False,
                                                       compute_disc=True),

@@ -1,0 +1,32 @@
+"""Mutation check of the golden tests made from the reference's source: each entry breaks ONE
+line of the host logic (argument order, a slice, a weight, a key, the shard order ...), runs the
+test that is supposed to pin it and restores the file.  Every mutation must be DETECTED.
+
+    python tools/mutation_check.py        (CPU only; a few minutes)
+"""
+import os
+os.chdir(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import subprocess, sys
+def mutate(path, old, new, test):
+    s=open(path).read()
+    assert old in s, (path, old)
+    open(path,"w").write(s.replace(old,new,1))
+    try:
+        r=subprocess.run([sys.executable,"-m","pytest",*test.split(),"-q","-x"],capture_output=True,text=True)
+        last=r.stdout.strip().splitlines()[-1]
+    finally:
+        open(path,"w").write(s)
+    print(("DETECTED " if "failed" in last else "MISSED   ")+f"{path}: {old[:50]!r} -> {new[:50]!r}   [{last}]")
+B="sup3r_b200/models/base.py"; A="sup3r_b200/models/abstract.py"
+mutate(B,"return self.loss_fun(hi_res_gen, hi_res_true)","return self.loss_fun(hi_res_true, hi_res_gen)","tests/test_gan_loss_golden.py")
+mutate(B,"loss_gen_advers = self.calc_loss_disc(disc_out_gen, disc_out_true)","loss_gen_advers = self.calc_loss_disc(disc_out_true, disc_out_gen)","tests/test_gan_loss_golden.py")
+mutate(B,"crop = [(0, 0)] * (hi_res_gen.dim() - 1) + [(0, n_exo)]","crop = [(0, 0)] * (hi_res_gen.dim() - 1) + [(0, 0)]","tests/test_gan_loss_golden.py")
+mutate(A,"term = val if w == 1.0 else val * w","term = val","tests/test_gan_loss_golden.py")
+mutate(A,'nm = exo_name.replace("_obs", "") if exo_name not in self._means else exo_name','nm = exo_name',"tests/test_gan_loss_golden.py")
+mutate(B,"if compute_disc or train_disc:","if train_disc:","tests/test_gan_loss_golden.py")
+mutate("sup3r_b200/parallel.py","src = world_size() - 1 if src is None else src","src = 0 if src is None else src","tests/test_parallel_golden.py")
+mutate("sup3r_b200/parallel.py","return x[index * k:(index + 1) * k]","return x[(n_shards - 1 - index) * k:(n_shards - index) * k]","tests/test_parallel_golden.py")
+mutate(B,"epochs = [e + int(self._history.index.values[-1]) + 1 for e in epochs]","epochs = [e + int(self._history.index.values[-1]) for e in epochs]","tests/test_train_loop_golden.py")
+mutate(B,'extras.update({f"OptmDisc/{k}": v for k, v in opt_d.items()})','extras.update({f"OptmDisc/{k}": v for k, v in opt_g.items()})',"tests/test_train_loop_golden.py")
+mutate("sup3r_b200/loss_metrics.py","return t[:, :, :, ::self._t_enhance, :]","return t[:, :, :, 1::self._t_enhance, :]","tests/test_losses_golden.py")
+mutate("sup3r_b200/loss_metrics.py","mmd = mmd - torch.mean(2 * gaussian_kernel(x1, x2, sigma))","mmd = mmd - torch.mean(gaussian_kernel(x1, x2, sigma))","tests/test_losses_golden.py")
