@@ -12,7 +12,7 @@ def mutate(path, old, new, test):
     assert old in s, (path, old)
     open(path,"w").write(s.replace(old,new,1))
     try:
-        r=subprocess.run([sys.executable,"-m","pytest",*test.split(),"-q","-x"],capture_output=True,text=True)
+        r=subprocess.run([sys.executable,"-m","pytest",*test.split(),"-q","-x","-m","not gpu"],capture_output=True,text=True)
         last=r.stdout.strip().splitlines()[-1]
     finally:
         open(path,"w").write(s)
@@ -42,3 +42,14 @@ mutate("sup3r_b200/pipeline/strategy.py","n = int(min(self.max_nodes or np.inf, 
 mutate("sup3r_b200/pipeline/strategy.py","start = 0 if not padded.start else self.temporal_pad","start = 0","tests/test_strategy_golden.py")
 mutate("sup3r_b200/models/with_obs.py","obs_frac = float(np.float32(int((~mask).sum())) / np.float32(mask.numel()))","obs_frac = float(np.float32(int((mask).sum())) / np.float32(mask.numel()))","tests/test_obs_golden.py")
 mutate("sup3r_b200/models/abstract.py","def early_stop(history, column, threshold=0.005, n_epoch=5):","def early_stop(history, column, threshold=0.005, n_epoch=5):\n        n_epoch += 1","tests/test_training_schedule_golden.py")
+# ---- slicer, forward-pass helpers, coarsening, bias, exo data, interface, post-processing
+mutate("sup3r_b200/pipeline/slicer.py","stop = None if self.spatial_pad == 0 else -start","stop = None","tests/test_host_golden.py")
+mutate("sup3r_b200/pipeline/forward_pass.py","            n = model_step + 1","            n = model_step","tests/test_forward_pass_golden.py")
+mutate("sup3r_b200/utilities.py",'"total": np.nansum, "max": np.max','"total": np.nansum, "max": np.min',"tests/test_host_golden.py")
+mutate("sup3r_b200/utilities.py","return data[:, :, :, ::t_enhance, :]","return data[:, :, :, 1::t_enhance, :]","tests/test_host_golden.py")
+mutate("sup3r_b200/bias.py","scalar, adder = _smooth(scalar, smoothing), _smooth(adder, smoothing)\n    return _clip(data * scalar + adder, out_range)","scalar, adder = _smooth(scalar, smoothing), adder\n    return _clip(data * scalar + adder, out_range)","tests/test_postprocess.py")
+mutate("sup3r_b200/exo.py",'new[k] = v[tuple(sl)[: len(v.shape) - 1]] if k == "data" else v','new[k] = v[tuple(sl)[: len(v.shape) - 2]] if k == "data" else v',"tests/test_host_golden.py tests/test_multistep_golden.py")
+mutate("sup3r_b200/exo.py",'if min_step <= s["model"] and (max_step is None or s["model"] < max_step)]','if min_step <= s["model"] and (max_step is None or s["model"] <= max_step)]',"tests/test_host_golden.py tests/test_multistep_golden.py")
+mutate("sup3r_b200/models/interface.py",'obs = [f.replace("_obs", "") for f in self.obs_features]','obs = [f for f in self.obs_features]',"tests/test_interface_golden.py")
+mutate("sup3r_b200/models/abstract.py","hi_res_exo = np.repeat(np.expand_dims(hi_res_exo, 3), hi_res.shape[3], axis=3)","hi_res_exo = np.repeat(np.expand_dims(hi_res_exo, 3), hi_res.shape[3] + 1, axis=3)","tests/test_gan_loss_golden.py")
+mutate("sup3r_b200/pipeline/postprocess.py","dx = (dx + 180) % 360 - 180","dx = (dx + 180) % 360","tests/test_postprocess.py")
