@@ -54,6 +54,9 @@ SCENARIOS = [
     # (train_gen, train_disc, disc_loss_bounds, n_batches) per epoch
     [(True, True, (0.45, 0.6), 6), (True, True, (0.45, 0.6), 6), (True, True, (0.3, 0.5), 5)],
     [(True, False, (0.45, 0.6), 4), (False, True, (0.45, 0.6), 4), (True, True, (0.6, 0.7), 7)],
+    # the running discriminator loss EQUAL to the lower bound (the 0 a fresh record starts from):
+    # "too good" includes equality
+    [(True, True, (0.0, 0.6), 3), (True, True, (0.5, 0.9), 4)],
 ]
 
 

@@ -53,3 +53,16 @@ mutate("sup3r_b200/exo.py",'if min_step <= s["model"] and (max_step is None or s
 mutate("sup3r_b200/models/interface.py",'obs = [f.replace("_obs", "") for f in self.obs_features]','obs = [f for f in self.obs_features]',"tests/test_interface_golden.py")
 mutate("sup3r_b200/models/abstract.py","hi_res_exo = np.repeat(np.expand_dims(hi_res_exo, 3), hi_res.shape[3], axis=3)","hi_res_exo = np.repeat(np.expand_dims(hi_res_exo, 3), hi_res.shape[3] + 1, axis=3)","tests/test_gan_loss_golden.py")
 mutate("sup3r_b200/pipeline/postprocess.py","dx = (dx + 180) % 360 - 180","dx = (dx + 180) % 360","tests/test_postprocess.py")
+# ---- training schedule boundaries, history bookkeeping, output check
+A="sup3r_b200/models/abstract.py"; B="sup3r_b200/models/base.py"; F="sup3r_b200/pipeline/forward_pass.py"; S="sup3r_b200/pipeline/strategy.py"
+T="tests/test_training_schedule_golden.py"
+mutate(A,"return record.iloc[-max_batches:]","return record.iloc[-(max_batches + 1):]",T)
+mutate(A,"key = k if prefix is None or prefix in k else prefix + k","key = k if prefix is None else prefix + k",T)
+mutate(A,"chp = checkpoint_int is not None and (epoch % checkpoint_int) == 0","chp = checkpoint_int is not None and (epoch % checkpoint_int) == 1",T)
+mutate(B,"disc_too_good = loss_disc <= disc_th_low","disc_too_good = loss_disc < disc_th_low",T)
+# (dropping "and train_disc" from disc_too_bad is an equivalent mutant: without discriminator
+#  training the generator step is unconditional, base.py:1008-1031)
+mutate(B,"if only_gen or (train_gen and not gen_too_good):","if only_gen or train_gen:",T)
+mutate(F,"if chk[i, 0] == chk[i, 1] and chk[i, 0] not in allowed_const:","if chk[i, 0] == chk[i, 1]:","tests/test_host_golden.py tests/test_forward_pass_golden.py")
+mutate(F,"if allowed_const is True:\n            return False\n        if allowed_const is False or allowed_const is None:","if allowed_const is True:\n            return True\n        if allowed_const is False or allowed_const is None:","tests/test_host_golden.py tests/test_forward_pass_golden.py")
+mutate(A,"nm = ","nm = exo_name  # ","tests/test_gan_loss_golden.py")
