@@ -120,3 +120,24 @@ def test_golden_is_reproducible_from_the_reference_when_present():
     if not os.path.isdir(T.REF):
         pytest.skip("reference source not present")
     assert json.loads(json.dumps(T.scenario(T.load_reference()))) == G
+
+
+def test_sum_parallel_grad_matches_reference():
+    """``_sum_parallel_grad`` on per-shard results held in one process (abstract.py:785-805):
+    SUM of the gradients, loss details of the last shard."""
+    import time
+    from types import SimpleNamespace
+    from sup3r_b200.models.abstract import AbstractSingleModel
+    for name, n in (("two_gpus_mask", 2), ("four_gpus", 4)):
+        lr, hr, mask = T.batch()
+        with_mask = T.CASES[name][2]
+        futures = []
+        for a, b, m in zip(np.split(lr, n), np.split(hr, n), np.split(mask, n)):
+            grads, det = T.shard_gradient(a, b, m if with_mask else None)
+            futures.append(SimpleNamespace(result=lambda g=grads, d=det: (
+                [torch.tensor(x) for x in g], d)))
+        obj = AbstractSingleModel.__new__(AbstractSingleModel)
+        total, det = obj._sum_parallel_grad(futures, start_time=time.time())
+        for g, w in zip(total, G[name]["applied"]):
+            np.testing.assert_allclose(g.numpy(), np.array(w), rtol=1e-12, err_msg=name)
+        assert {k: float(v) for k, v in det.items()} == pytest.approx(G[name]["details"])

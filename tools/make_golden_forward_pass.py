@@ -146,6 +146,14 @@ def scenario(FP):
             table.append([name, allowed if not isinstance(allowed, tuple) else list(allowed),
                           bool(FP._output_check(arr, allowed))])
     rec["output_check"] = table
+    # a 3-D exo array of a step WITH temporal enhancement: its time axis is the chunk's length
+    # times the step's own t_enhance (forward_pass.py:166-172) -- own generator: the arrays above
+    # keep their values
+    rng2 = np.random.default_rng(22)
+    exo3 = {"sza": {"steps": [{"model": 0, "combine_type": "layer", "s_enhance": 2, "t_enhance": 3,
+                               "data": rng2.standard_normal((10, 12, 1))}]}}
+    out, e = fp.pad_source_data(data.copy(), pad_width, copy.deepcopy(exo3), mode="reflect")
+    arrs["pad_exo3d_t3"] = np.asarray(e["sza"]["steps"][0]["data"])
     return rec, arrs
 
 

@@ -118,6 +118,10 @@ def scenario(Base, warn_log):
         **dict(kw, hr_exo_features=["topography"])))
     rec["set_bad_enhance"] = attempt(lambda: make_model(Base, {}, layers).set_model_params(
         **dict(kw, s_enhance=2)))
+    # both factors differ from the layers' (one matching factor is enough for the reference's
+    # "or" check) while the resolutions still divide evenly: the enhancement check itself
+    rec["set_bad_both_enhance"] = attempt(lambda: make_model(Base, {}, layers).set_model_params(
+        **dict(kw, s_enhance=2, t_enhance=3)))
     rec["set_bad_resolution"] = attempt(lambda: make_model(Base, {}, layers).set_model_params(
         **dict(kw, input_resolution={"spatial": "10km", "temporal": "60min"})))
     rec["set_bad_t_resolution"] = attempt(lambda: make_model(Base, {}, layers).set_model_params(

@@ -66,3 +66,15 @@ mutate(B,"if only_gen or (train_gen and not gen_too_good):","if only_gen or trai
 mutate(F,"if chk[i, 0] == chk[i, 1] and chk[i, 0] not in allowed_const:","if chk[i, 0] == chk[i, 1]:","tests/test_host_golden.py tests/test_forward_pass_golden.py")
 mutate(F,"if allowed_const is True:\n            return False\n        if allowed_const is False or allowed_const is None:","if allowed_const is True:\n            return True\n        if allowed_const is False or allowed_const is None:","tests/test_host_golden.py tests/test_forward_pass_golden.py")
 mutate(A,"nm = ","nm = exo_name  # ","tests/test_gan_loss_golden.py")
+# ---- incremental restart, exo padding, feature combination, resolution / enhancement checks,
+# ---- collector stitching, drop_leap, _sum_parallel_grad
+F="sup3r_b200/pipeline/forward_pass.py"; S="sup3r_b200/pipeline/strategy.py"; I="sup3r_b200/models/interface.py"; M="sup3r_b200/models/multi_step.py"
+mutate(S,"done = out_file is not None and os.path.exists(out_file) and self.incremental","done = out_file is not None and os.path.exists(out_file)","tests/test_strategy_golden.py")
+mutate(F,"for en, pw in zip([s_en, s_en, t_en], pad_width)), (0, 0))","for en, pw in zip([s_en, s_en, 1], pad_width)), (0, 0))","tests/test_forward_pass_golden.py")
+mutate(F,'step["t_enhance"] * input_data.shape[2], axis=2)','input_data.shape[2], axis=2)',"tests/test_forward_pass_golden.py")
+mutate(I,"exo_feats = [] if n_missing <= 0 else features[-n_missing:]","exo_feats = [] if n_missing <= 0 else features[:n_missing]","tests/test_interface_golden.py tests/test_multistep_golden.py")
+mutate(I,'ok = ires["temporal"] / ores["temporal"] == t and ires["spatial"] / ores["spatial"] == s','ok = ires["temporal"] / ores["temporal"] == t or ires["spatial"] / ores["spatial"] == s',"tests/test_interface_golden.py tests/test_reference_host_cases.py")
+mutate(I,"ls = ls if ls is not None else s","ls = s","tests/test_interface_golden.py tests/test_reference_host_cases.py")
+mutate("sup3r_b200/pipeline/writers.py","rows, cols = gids // full_shape[1], gids % full_shape[1]","rows, cols = gids // full_shape[0], gids % full_shape[0]","tests/test_writers.py")
+mutate("sup3r_b200/bias.py","if drop_leap:","if not drop_leap:","tests/test_postprocess.py")
+mutate("sup3r_b200/models/abstract.py","grad, loss_details = future.result()","grad, _ = future.result()","tests/test_parallel_golden.py")
